@@ -1,0 +1,1040 @@
+// Host side of the C-ABI (include/kiss_icp_b200.h). Thin: argument checks, H2D/D2H copies,
+// capacity management of the HBM voxel table, and ONE cooperative launch per call.
+// There is no CPU fallback anywhere in this file: without a CUDA device every compute entry
+// point returns KB_ERR_NO_DEVICE.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "../../include/kiss_icp_b200.h"
+#include "kernels.cuh"
+
+using namespace kb;
+
+namespace {
+
+thread_local std::string tl_err;
+thread_local int tl_device = 0;
+thread_local cudaStream_t tl_user_stream = nullptr;
+thread_local int tl_grid_blocks = 0;
+
+int fail(int status, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    tl_err = buf;
+    return status;
+}
+
+#define CK(call)                                                                              \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess) return fail(KB_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); \
+    } while (0)
+#define RET(call)              \
+    do {                       \
+        int s_ = (call);       \
+        if (s_ != KB_OK) return s_; \
+    } while (0)
+
+int device_count() {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+template <class T>
+struct DBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    int ensure(size_t count) {
+        if (count <= n) return KB_OK;
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+        const size_t want = std::max<size_t>(count, 1024);
+        CK(cudaMalloc(&p, want * sizeof(T)));
+        n = want;
+        return KB_OK;
+    }
+    ~DBuf() {
+        if (p) cudaFree(p);
+    }
+};
+
+size_t pow2_at_least(size_t v) {
+    size_t p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+
+// execution context: device, stream, persistent-grid size and the cross-CTA scratch
+struct Exec {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int grid = 0;
+    Scratch sc{nullptr, nullptr, nullptr};
+    unsigned long long launches = 0;
+
+    int init() {
+        if (device_count() <= 0) return fail(KB_ERR_NO_DEVICE, "no CUDA device visible (this library has no CPU fallback)");
+        device = tl_device;
+        CK(cudaSetDevice(device));
+        if (tl_user_stream) {
+            stream = tl_user_stream;
+        } else {
+            CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+            own_stream = true;
+        }
+        int sms = 0, coop = 0;
+        CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+        CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device));
+        if (!coop) return fail(KB_ERR_CUDA, "device does not support cooperative launch");
+        grid = tl_grid_blocks > 0 ? std::min(tl_grid_blocks, sms) : sms;
+        CK(cudaMalloc(&sc.bar, 256));
+        CK(cudaMalloc(&sc.blk_d, sizeof(double) * 2 * grid * (NACC + 1)));
+        CK(cudaMalloc(&sc.blk_i, sizeof(int) * 2 * grid));
+        return KB_OK;
+    }
+    ~Exec() {
+        if (sc.bar) cudaFree(sc.bar);
+        if (sc.blk_d) cudaFree(sc.blk_d);
+        if (sc.blk_i) cudaFree(sc.blk_i);
+        if (own_stream && stream) cudaStreamDestroy(stream);
+    }
+    template <class P>
+    int coop(void (*kern)(P), const P &p) {
+        CK(cudaSetDevice(device));
+        CK(cudaMemsetAsync(sc.bar, 0, sizeof(unsigned), stream));
+        void *args[] = {const_cast<P *>(&p)};
+        CK(cudaLaunchCooperativeKernel(reinterpret_cast<const void *>(kern), dim3(grid), dim3(BLOCK), args, 0, stream));
+        ++launches;
+        return KB_OK;
+    }
+    int sync() {
+        CK(cudaStreamSynchronize(stream));
+        return KB_OK;
+    }
+};
+
+int make_exec(std::shared_ptr<Exec> *out) {
+    auto e = std::make_shared<Exec>();
+    RET(e->init());
+    *out = e;
+    return KB_OK;
+}
+
+// per-call workspace sized by the largest cloud seen
+struct Work {
+    DBuf<double> in, ts, tmp, pre, ds1, src, work, tp;
+    DBuf<int> next, touched, ds_prefix, cnt;
+    DBuf<int4> ds_slots;
+    int ensure(size_t n) {
+        n = std::max<size_t>(n, 1);
+        RET(in.ensure(3 * n));
+        RET(ts.ensure(n));
+        RET(tmp.ensure(3 * n));
+        RET(pre.ensure(3 * n));
+        RET(ds1.ensure(3 * n));
+        RET(src.ensure(3 * n));
+        RET(work.ensure(3 * n));
+        RET(tp.ensure(3 * n));
+        RET(next.ensure(n));
+        RET(touched.ensure(n));
+        const size_t b = pow2_at_least(2 * n);
+        RET(ds_slots.ensure(b));
+        RET(ds_prefix.ensure(b));
+        RET(cnt.ensure(8));
+        return KB_OK;
+    }
+    Workspace view() {
+        return Workspace{tmp.p, pre.p, ds1.p, src.p, work.p, tp.p, next.p, touched.p, ds_slots.p, ds_prefix.p, cnt.p};
+    }
+};
+
+bool to_se3(const double M[16], SE3 *T) { return se3_from_matrix(M, T); }
+
+}  // namespace
+
+// =============================================================================================
+struct kb_map {
+    std::shared_ptr<Exec> ex;
+    double voxel_size, max_distance;
+    unsigned cap;
+    size_t capacity = 0;
+    int4 *slots = nullptr;
+    double *points = nullptr;
+    int *head = nullptr;
+    int *counters = nullptr;
+    int h_counters[C_NCOUNTERS] = {0};
+    Work ws;
+    DBuf<double> q_in, q_outp, q_outd;
+    DBuf<unsigned long long> q_cand;
+    bool borrowed = false;
+
+    MapView view() const {
+        MapView m;
+        m.slots = slots;
+        m.points = points;
+        m.head = head;
+        m.counters = counters;
+        m.mask = static_cast<unsigned>(capacity - 1);
+        m.cap = static_cast<int>(cap);
+        m.voxel_size = voxel_size;
+        m.max_distance = max_distance;
+        m.map_resolution = std::sqrt(voxel_size * voxel_size / cap);
+        return m;
+    }
+    void free_table() {
+        if (slots) cudaFree(slots);
+        if (points) cudaFree(points);
+        if (head) cudaFree(head);
+        slots = nullptr;
+        points = nullptr;
+        head = nullptr;
+    }
+    ~kb_map() {
+        if (ex) cudaSetDevice(ex->device);
+        free_table();
+        if (counters) cudaFree(counters);
+    }
+    int alloc_table(size_t cap_slots, int4 **s, double **p, int **h) {
+        CK(cudaMalloc(s, cap_slots * sizeof(int4)));
+        CK(cudaMalloc(p, cap_slots * cap * 3 * sizeof(double)));
+        CK(cudaMalloc(h, cap_slots * sizeof(int)));
+        k_map_fill<<<std::min<size_t>(4096, (cap_slots + 255) / 256), 256, 0, ex->stream>>>(*s, *h, cap_slots);
+        ++ex->launches;
+        CK(cudaGetLastError());
+        return KB_OK;
+    }
+    // make room for `extra` more voxels at load factor <= 0.5 (tombstones count as load)
+    int ensure_capacity(size_t extra) {
+        CK(cudaSetDevice(ex->device));
+        if (!counters) {
+            CK(cudaMalloc(&counters, sizeof(int) * C_NCOUNTERS));
+            CK(cudaMemsetAsync(counters, 0, sizeof(int) * C_NCOUNTERS, ex->stream));
+        }
+        const size_t live = static_cast<size_t>(h_counters[C_LIVE]), tomb = static_cast<size_t>(h_counters[C_TOMB]);
+        if (capacity && (live + tomb + extra) * 2 <= capacity) return KB_OK;
+        const size_t want = std::max<size_t>(pow2_at_least(4 * (live + extra)), size_t(1) << 14);
+        if (want > (size_t(1) << 31)) return fail(KB_ERR_INVALID_ARG, "voxel table would exceed 2^31 slots");
+        int4 *ns;
+        double *np;
+        int *nh;
+        RET(alloc_table(want, &ns, &np, &nh));
+        if (capacity && live) {
+            MapView from = view();
+            MapView to = from;
+            to.slots = ns;
+            to.points = np;
+            to.head = nh;
+            to.mask = static_cast<unsigned>(want - 1);
+            int *nc;
+            CK(cudaMalloc(&nc, sizeof(int) * C_NCOUNTERS));
+            CK(cudaMemsetAsync(nc, 0, sizeof(int) * C_NCOUNTERS, ex->stream));
+            to.counters = nc;
+            k_map_rehash<<<std::min<size_t>(2048, (capacity * 32 + 255) / 256), 256, 0, ex->stream>>>(from, to);
+            ++ex->launches;
+            CK(cudaGetLastError());
+            CK(cudaMemcpyAsync(h_counters, nc, sizeof(int) * C_NCOUNTERS, cudaMemcpyDeviceToHost, ex->stream));
+            RET(ex->sync());
+            cudaFree(counters);
+            counters = nc;
+        } else if (capacity) {
+            CK(cudaMemsetAsync(counters, 0, sizeof(int) * C_NCOUNTERS, ex->stream));
+            std::memset(h_counters, 0, sizeof(h_counters));
+            RET(ex->sync());
+        }
+        free_table();
+        slots = ns;
+        points = np;
+        head = nh;
+        capacity = want;
+        return KB_OK;
+    }
+    int pull_counters() {
+        CK(cudaMemcpyAsync(h_counters, counters, sizeof(int) * C_NCOUNTERS, cudaMemcpyDeviceToHost, ex->stream));
+        RET(ex->sync());
+        if (h_counters[C_STATUS] & ST_TABLE_FULL) return fail(KB_ERR_CUDA, "voxel table overflow (internal capacity bug)");
+        return KB_OK;
+    }
+    // d_pts already on the device
+    int update_dev(const double *d_pts, size_t n, bool has_pose, const SE3 &pose, bool do_add, bool do_remove,
+                   const V3 &origin) {
+        RET(ensure_capacity(do_add ? n : 0));
+        MapUpdParams P;
+        P.m = view();
+        P.sc = ex->sc;
+        P.pts = d_pts;
+        P.n = static_cast<int>(n);
+        P.has_pose = has_pose;
+        P.pose = pose;
+        P.do_add = do_add && n > 0;
+        P.do_remove = do_remove;
+        P.origin = origin;
+        P.tp = ws.tp.p;
+        P.next = ws.next.p;
+        P.touched = ws.touched.p;
+        RET(ex->coop(k_map_update, P));
+        return KB_OK;
+    }
+    static constexpr size_t kChunk = size_t(1) << 18;
+    int update_host(const double *xyz, size_t n, bool has_pose, const SE3 &pose, bool do_add, bool do_remove,
+                    const V3 &origin) {
+        CK(cudaSetDevice(ex->device));
+        if (do_add) {
+            for (size_t off = 0; off < n; off += kChunk) {
+                const size_t c = std::min(kChunk, n - off);
+                RET(ws.in.ensure(3 * c));
+                RET(ws.tp.ensure(3 * c));
+                RET(ws.next.ensure(c));
+                RET(ws.touched.ensure(c));
+                CK(cudaMemcpyAsync(ws.in.p, xyz + 3 * off, c * 24, cudaMemcpyHostToDevice, ex->stream));
+                RET(update_dev(ws.in.p, c, has_pose, pose, true, false, origin));
+                RET(pull_counters());
+            }
+        }
+        if (do_remove) {
+            RET(update_dev(nullptr, 0, false, pose, false, true, origin));
+            RET(pull_counters());
+        }
+        return KB_OK;
+    }
+};
+
+struct kb_registration {
+    int max_iter;
+    double conv;
+    int threads;
+    Work ws;
+    DBuf<double> out;  // pose[16] + sys[NACC]
+    DBuf<int> iout;    // iters, ncorr
+    int last_iters = 0;
+};
+
+struct kb_preprocessor {
+    std::shared_ptr<Exec> ex;
+    double max_range, min_range;
+    int deskew, threads;
+    Work ws;
+};
+
+struct kb_threshold {
+    double min_motion_th, max_range, model_sse;
+    int num_samples;
+};
+
+struct kb_pipeline {
+    std::shared_ptr<Exec> ex;
+    kb_config cfg;
+    kb_map *map = nullptr;
+    Work ws;
+    PipeState *d_state = nullptr;
+    FrameResult *d_res = nullptr;
+    FrameResult *h_res = nullptr;  // pinned
+    FrameResult last{};
+    bool has_last = false;
+    ~kb_pipeline() {
+        if (ex) cudaSetDevice(ex->device);
+        delete map;
+        if (d_state) cudaFree(d_state);
+        if (d_res) cudaFree(d_res);
+        if (h_res) cudaFreeHost(h_res);
+    }
+};
+
+namespace {
+struct DefaultCtx {
+    std::shared_ptr<Exec> ex;
+    Work ws;
+};
+thread_local std::unique_ptr<DefaultCtx> tl_ctx;
+int default_ctx(DefaultCtx **out) {
+    if (!tl_ctx || tl_ctx->ex->device != tl_device || (tl_user_stream && tl_ctx->ex->stream != tl_user_stream)) {
+        auto c = std::make_unique<DefaultCtx>();
+        RET(make_exec(&c->ex));
+        tl_ctx = std::move(c);
+    }
+    *out = tl_ctx.get();
+    return KB_OK;
+}
+
+int run_downsample(Exec &ex, Work &ws, const double *d_in, size_t n, double v1, double *d_out, int *d_n1, double v2,
+                   double *d_out2, int *d_n2) {
+    DsParams P;
+    P.sc = ex.sc;
+    P.in = d_in;
+    P.n = static_cast<int>(n);
+    P.voxel_size = v1;
+    P.ds_slots = ws.ds_slots.p;
+    P.ds_prefix = ws.ds_prefix.p;
+    P.out = d_out;
+    P.out_n = d_n1;
+    P.voxel_size2 = v2;
+    P.out2 = d_out2;
+    P.out_n2 = d_n2;
+    return ex.coop(k_downsample, P);
+}
+}  // namespace
+
+extern "C" {
+
+const char *kb_last_error(void) { return tl_err.c_str(); }
+const char *kb_version(void) { return "kiss_icp_b200 0.1 (sm_100a)"; }
+int kb_device_count(void) { return device_count(); }
+int kb_set_device(int device) {
+    if (device < 0 || device >= device_count()) return fail(KB_ERR_INVALID_ARG, "device %d out of range", device);
+    tl_device = device;
+    return KB_OK;
+}
+int kb_set_stream(void *cuda_stream) {
+    tl_user_stream = static_cast<cudaStream_t>(cuda_stream);
+    return KB_OK;
+}
+int kb_set_grid_blocks(int blocks) {
+    if (blocks < 0) return fail(KB_ERR_INVALID_ARG, "blocks < 0");
+    tl_grid_blocks = blocks;
+    return KB_OK;
+}
+
+// ------------------------------------------------------------------------------- VoxelHashMap
+static int map_create_impl(double voxel_size, double max_distance, unsigned cap, std::shared_ptr<Exec> ex, kb_map **out) {
+    if (!out) return fail(KB_ERR_INVALID_ARG, "out == NULL");
+    if (!(voxel_size > 0.0)) return fail(KB_ERR_INVALID_ARG, "voxel_size must be > 0");
+    if (cap < 1 || cap > 1023) return fail(KB_ERR_INVALID_ARG, "max_points_per_voxel must be in [1, 1023]");
+    auto m = std::make_unique<kb_map>();
+    if (ex)
+        m->ex = ex;
+    else
+        RET(make_exec(&m->ex));
+    m->voxel_size = voxel_size;
+    m->max_distance = max_distance;
+    m->cap = cap;
+    RET(m->ensure_capacity(0));
+    RET(m->ex->sync());
+    *out = m.release();
+    return KB_OK;
+}
+int kb_map_create(double voxel_size, double max_distance, unsigned max_points_per_voxel, kb_map **out) {
+    return map_create_impl(voxel_size, max_distance, max_points_per_voxel, nullptr, out);
+}
+int kb_map_destroy(kb_map *map) {
+    if (map && !map->borrowed) delete map;
+    return KB_OK;
+}
+int kb_map_clear(kb_map *map) {
+    if (!map) return fail(KB_ERR_INVALID_ARG, "map == NULL");
+    CK(cudaSetDevice(map->ex->device));
+    k_map_fill<<<std::min<size_t>(4096, (map->capacity + 255) / 256), 256, 0, map->ex->stream>>>(map->slots, map->head,
+                                                                                             map->capacity);
+    ++map->ex->launches;
+    CK(cudaMemsetAsync(map->counters, 0, sizeof(int) * C_NCOUNTERS, map->ex->stream));
+    std::memset(map->h_counters, 0, sizeof(map->h_counters));
+    return map->ex->sync();
+}
+int kb_map_empty(const kb_map *map, int *out_is_empty) {
+    if (!map || !out_is_empty) return fail(KB_ERR_INVALID_ARG, "NULL argument");
+    *out_is_empty = map->h_counters[C_LIVE] == 0 ? 1 : 0;
+    return KB_OK;
+}
+int kb_map_update_origin(kb_map *map, const double *xyz, size_t n, const double origin[3]) {
+    if (!map || (!xyz && n) || !origin) return fail(KB_ERR_INVALID_ARG, "NULL argument");
+    return map->update_host(xyz, n, false, se3_identity(), true, true, V3{origin[0], origin[1], origin[2]});
+}
+int kb_map_update_pose(kb_map *map, const double *xyz, size_t n, const double pose[16]) {
+    if (!map || (!xyz && n) || !pose) return fail(KB_ERR_INVALID_ARG, "NULL argument");
+    SE3 T;
+    if (!to_se3(pose, &T)) return fail(KB_ERR_NOT_SE3, "pose is not in SE(3)");
+    return map->update_host(xyz, n, true, T, true, true, T.t);
+}
+int kb_map_add_points(kb_map *map, const double *xyz, size_t n) {
+    if (!map || (!xyz && n)) return fail(KB_ERR_INVALID_ARG, "NULL argument");
+    return map->update_host(xyz, n, false, se3_identity(), true, false, V3{0, 0, 0});
+}
+int kb_map_remove_far(kb_map *map, const double origin[3]) {
+    if (!map || !origin) return fail(KB_ERR_INVALID_ARG, "NULL argument");
+    return map->update_host(nullptr, 0, false, se3_identity(), false, true, V3{origin[0], origin[1], origin[2]});
+}
+int kb_map_num_points(const kb_map *map, size_t *out) {
+    if (!map || !out) return fail(KB_ERR_INVALID_ARG, "NULL argument");
+    *out = static_cast<size_t>(map->h_counters[C_POINTS]);
+    return KB_OK;
+}
+int kb_map_num_voxels(const kb_map *map, size_t *out) {
+    if (!map || !out) return fail(KB_ERR_INVALID_ARG, "NULL argument");
+    *out = static_cast<size_t>(map->h_counters[C_LIVE]);
+    return KB_OK;
+}
+int kb_map_params(const kb_map *map, double *voxel_size, double *max_distance, unsigned *max_points_per_voxel) {
+    if (!map) return fail(KB_ERR_INVALID_ARG, "map == NULL");
+    if (voxel_size) *voxel_size = map->voxel_size;
+    if (max_distance) *max_distance = map->max_distance;
+    if (max_points_per_voxel) *max_points_per_voxel = map->cap;
+    return KB_OK;
+}
+
+int kb_map_dump(const kb_map *cmap, int *voxels, int *counts, double *points, size_t voxel_capacity,
+                size_t point_capacity, size_t *n_voxels, size_t *n_points) {
+    kb_map *map = const_cast<kb_map *>(cmap);
+    if (!map || !n_voxels || !n_points) return fail(KB_ERR_INVALID_ARG, "NULL argument");
+    CK(cudaSetDevice(map->ex->device));
+    const size_t nv = static_cast<size_t>(map->h_counters[C_LIVE]), np = static_cast<size_t>(map->h_counters[C_POINTS]);
+    *n_voxels = nv;
+    *n_points = np;
+    if (!voxels && !counts && !points) return KB_OK;
+    if (voxel_capacity < nv || point_capacity < np) return fail(KB_ERR_CAPACITY, "dump buffers too small");
+    if (nv == 0) return KB_OK;
+    DBuf<int4> d_vox;
+    DBuf<double> d_pts;
+    DBuf<int> d_tot;
+    RET(d_vox.ensure(nv));
+    RET(d_pts.ensure(3 * np));
+    RET(d_tot.ensure(2));
+    ExportParams P;
+    P.m = map->view();
+    P.sc = map->ex->sc;
+    P.vox_out = d_vox.p;
+    P.pts_out = d_pts.p;
+    P.totals = d_tot.p;
+    RET(map->ex->coop(k_map_export, P));
+    std::vector<int4> hv(nv);
+    std::vector<double> hp(3 * np);
+    int tot[2];
+    CK(cudaMemcpyAsync(hv.data(), d_vox.p, nv * sizeof(int4), cudaMemcpyDeviceToHost, map->ex->stream));
+    CK(cudaMemcpyAsync(hp.data(), d_pts.p, 3 * np * sizeof(double), cudaMemcpyDeviceToHost, map->ex->stream));
+    CK(cudaMemcpyAsync(tot, d_tot.p, sizeof(tot), cudaMemcpyDeviceToHost, map->ex->stream));
+    RET(map->ex->sync());
+    if (static_cast<size_t>(tot[0]) != nv || static_cast<size_t>(tot[1]) != np)
+        return fail(KB_ERR_CUDA, "map export count mismatch (%d/%zu voxels, %d/%zu points)", tot[0], nv, tot[1], np);
+    // canonical voxel order: ascending (x, y, z)
+    std::vector<size_t> start(nv);
+    size_t acc = 0;
+    for (size_t i = 0; i < nv; ++i) {
+        start[i] = acc;
+        acc += static_cast<size_t>(hv[i].w);
+    }
+    std::vector<size_t> order(nv);
+    std::iota(order.begin(), order.end(), size_t(0));
+    std::sort(order.begin(), order.end(), [&](size_t a, size_t b) {
+        if (hv[a].x != hv[b].x) return hv[a].x < hv[b].x;
+        if (hv[a].y != hv[b].y) return hv[a].y < hv[b].y;
+        return hv[a].z < hv[b].z;
+    });
+    size_t o = 0;
+    for (size_t r = 0; r < nv; ++r) {
+        const size_t i = order[r];
+        if (voxels) {
+            voxels[3 * r] = hv[i].x;
+            voxels[3 * r + 1] = hv[i].y;
+            voxels[3 * r + 2] = hv[i].z;
+        }
+        if (counts) counts[r] = hv[i].w;
+        if (points) std::memcpy(points + 3 * o, hp.data() + 3 * start[i], sizeof(double) * 3 * hv[i].w);
+        o += static_cast<size_t>(hv[i].w);
+    }
+    return KB_OK;
+}
+int kb_map_pointcloud(const kb_map *map, double *out_xyz, size_t capacity, size_t *n_out) {
+    if (!map || !n_out) return fail(KB_ERR_INVALID_ARG, "NULL argument");
+    const size_t np = static_cast<size_t>(map->h_counters[C_POINTS]);
+    *n_out = np;
+    if (!out_xyz || capacity == 0) return KB_OK;
+    if (capacity < np) return fail(KB_ERR_CAPACITY, "pointcloud buffer too small");
+    size_t nv, npp;
+    return kb_map_dump(map, nullptr, nullptr, out_xyz, static_cast<size_t>(map->h_counters[C_LIVE]), capacity, &nv, &npp);
+}
+
+static int nn_launch(kb_map *map, const double *d_q, size_t n, double *d_p, double *d_d, unsigned long long *d_cand) {
+    if (n == 0) return KB_OK;
+    const int threads = 256;
+    const size_t want = (n * 32 + threads - 1) / threads;
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, map->ex->device);
+    const unsigned blocks = static_cast<unsigned>(std::min<size_t>(want, static_cast<size_t>(sms) * 8 * 4));
+    if (d_cand)
+        k_nn_query<true><<<blocks, threads, 0, map->ex->stream>>>(map->view(), d_q, n, d_p, d_d, d_cand);
+    else
+        k_nn_query<false><<<blocks, threads, 0, map->ex->stream>>>(map->view(), d_q, n, d_p, d_d, nullptr);
+    ++map->ex->launches;
+    CK(cudaGetLastError());
+    return KB_OK;
+}
+int kb_map_closest_neighbors_dev(const kb_map *cmap, const double *d_queries, size_t n, double *d_out_points,
+                                 double *d_out_dist) {
+    kb_map *map = const_cast<kb_map *>(cmap);
+    if (!map || (n && (!d_queries || !d_out_points || !d_out_dist))) return fail(KB_ERR_INVALID_ARG, "NULL argument");
+    CK(cudaSetDevice(map->ex->device));
+    return nn_launch(map, d_queries, n, d_out_points, d_out_dist, nullptr);  // asynchronous on the map's stream
+}
+int kb_map_closest_neighbors(const kb_map *cmap, const double *queries, size_t n, double *out_points, double *out_dist) {
+    kb_map *map = const_cast<kb_map *>(cmap);
+    if (!map || (n && (!queries || !out_points || !out_dist))) return fail(KB_ERR_INVALID_ARG, "NULL argument");
+    CK(cudaSetDevice(map->ex->device));
+    const size_t chunk = size_t(1) << 22;
+    for (size_t off = 0; off < n; off += chunk) {
+        const size_t c = std::min(chunk, n - off);
+        RET(map->q_in.ensure(3 * c));
+        RET(map->q_outp.ensure(3 * c));
+        RET(map->q_outd.ensure(c));
+        CK(cudaMemcpyAsync(map->q_in.p, queries + 3 * off, c * 24, cudaMemcpyHostToDevice, map->ex->stream));
+        RET(nn_launch(map, map->q_in.p, c, map->q_outp.p, map->q_outd.p, nullptr));
+        CK(cudaMemcpyAsync(out_points + 3 * off, map->q_outp.p, c * 24, cudaMemcpyDeviceToHost, map->ex->stream));
+        CK(cudaMemcpyAsync(out_dist + off, map->q_outd.p, c * 8, cudaMemcpyDeviceToHost, map->ex->stream));
+        RET(map->ex->sync());
+    }
+    return KB_OK;
+}
+int kb_map_query_bytes_dev(const kb_map *cmap, const double *d_queries, size_t n, double *bytes) {
+    kb_map *map = const_cast<kb_map *>(cmap);
+    if (!map || !bytes || (n && !d_queries)) return fail(KB_ERR_INVALID_ARG, "NULL argument");
+    CK(cudaSetDevice(map->ex->device));
+    RET(map->q_outp.ensure(3 * n));
+    RET(map->q_outd.ensure(n));
+    RET(map->q_cand.ensure(1));
+    CK(cudaMemsetAsync(map->q_cand.p, 0, sizeof(unsigned long long), map->ex->stream));
+    RET(nn_launch(map, d_queries, n, map->q_outp.p, map->q_outd.p, map->q_cand.p));
+    unsigned long long cand = 0;
+    CK(cudaMemcpyAsync(&cand, map->q_cand.p, sizeof(cand), cudaMemcpyDeviceToHost, map->ex->stream));
+    RET(map->ex->sync());
+    // 24 (query) + 27*16 (slot probes) + 24*candidates + 32 (result) per query
+    *bytes = static_cast<double>(n) * (24.0 + 27.0 * 16.0 + 32.0) + 24.0 * static_cast<double>(cand);
+    return KB_OK;
+}
+int kb_map_sync(const kb_map *map) {
+    if (!map) return fail(KB_ERR_INVALID_ARG, "map == NULL");
+    return map->ex->sync();
+}
+
+// ------------------------------------------------------------------------------- Registration
+int kb_registration_create(int max_num_iterations, double convergence_criterion, int max_num_threads,
+                           kb_registration **out) {
+    if (!out) return fail(KB_ERR_INVALID_ARG, "out == NULL");
+    if (device_count() <= 0) return fail(KB_ERR_NO_DEVICE, "no CUDA device visible (this library has no CPU fallback)");
+    auto r = new kb_registration();
+    r->max_iter = max_num_iterations;
+    r->conv = convergence_criterion;
+    r->threads = max_num_threads;
+    *out = r;
+    return KB_OK;
+}
+int kb_registration_destroy(kb_registration *reg) {
+    delete reg;
+    return KB_OK;
+}
+static int registration_run(kb_registration *reg, const double *xyz, size_t n, kb_map *map, const SE3 &guess,
+                            double max_dist, double kscale, bool system_only) {
+    Exec &ex = *map->ex;
+    CK(cudaSetDevice(ex.device));
+    RET(reg->ws.src.ensure(3 * std::max<size_t>(n, 1)));
+    RET(reg->ws.work.ensure(3 * std::max<size_t>(n, 1)));
+    RET(reg->out.ensure(16 + NACC));
+    RET(reg->iout.ensure(2));
+    if (n) CK(cudaMemcpyAsync(reg->ws.src.p, xyz, n * 24, cudaMemcpyHostToDevice, ex.stream));
+    IcpParams P;
+    P.m = map->view();
+    P.sc = ex.sc;
+    P.src = reg->ws.src.p;
+    P.work = reg->ws.work.p;
+    P.n = static_cast<int>(n);
+    P.guess = guess;
+    P.max_dist = max_dist;
+    P.kscale = kscale;
+    P.max_iter = reg->max_iter;
+    P.conv = reg->conv;
+    P.out_pose = reg->out.p;
+    P.out_iters = reg->iout.p;
+    P.system_only = system_only ? 1 : 0;
+    P.out_sys = reg->out.p + 16;
+    P.out_ncorr = reg->iout.p + 1;
+    return ex.coop(k_icp, P);
+}
+int kb_registration_align_points_to_map(kb_registration *reg, const double *xyz, size_t n, const kb_map *cmap,
+                                        const double initial_guess[16], double max_correspondence_distance,
+                                        double kernel_scale, double out_pose[16]) {
+    kb_map *map = const_cast<kb_map *>(cmap);
+    if (!reg || !map || (!xyz && n) || !initial_guess || !out_pose) return fail(KB_ERR_INVALID_ARG, "NULL argument");
+    SE3 g;
+    if (!to_se3(initial_guess, &g)) return fail(KB_ERR_NOT_SE3, "initial_guess is not in SE(3)");
+    RET(registration_run(reg, xyz, n, map, g, max_correspondence_distance, kernel_scale, false));
+    int it = 0;
+    CK(cudaMemcpyAsync(out_pose, reg->out.p, 16 * sizeof(double), cudaMemcpyDeviceToHost, map->ex->stream));
+    CK(cudaMemcpyAsync(&it, reg->iout.p, sizeof(int), cudaMemcpyDeviceToHost, map->ex->stream));
+    RET(map->ex->sync());
+    reg->last_iters = it;
+    return KB_OK;
+}
+int kb_registration_last_iterations(const kb_registration *reg, int *out) {
+    if (!reg || !out) return fail(KB_ERR_INVALID_ARG, "NULL argument");
+    *out = reg->last_iters;
+    return KB_OK;
+}
+int kb_registration_build_system(kb_registration *reg, const double *xyz, size_t n, const kb_map *cmap,
+                                 double max_correspondence_distance, double kernel_scale, double JTJ[36], double JTr[6],
+                                 int *n_correspondences) {
+    kb_map *map = const_cast<kb_map *>(cmap);
+    if (!reg || !map || (!xyz && n) || !JTJ || !JTr) return fail(KB_ERR_INVALID_ARG, "NULL argument");
+    RET(registration_run(reg, xyz, n, map, se3_identity(), max_correspondence_distance, kernel_scale, true));
+    double sys[NACC];
+    int nc = 0;
+    CK(cudaMemcpyAsync(sys, reg->out.p + 16, sizeof(sys), cudaMemcpyDeviceToHost, map->ex->stream));
+    CK(cudaMemcpyAsync(&nc, reg->iout.p + 1, sizeof(int), cudaMemcpyDeviceToHost, map->ex->stream));
+    RET(map->ex->sync());
+    // same expansion as the device (icp_expand), host side
+    for (int i = 0; i < 36; ++i) JTJ[i] = 0.0;
+    JTJ[0] = JTJ[7] = JTJ[14] = sys[0];
+    JTJ[6 * 3 + 1] = -sys[3];
+    JTJ[6 * 3 + 2] = sys[2];
+    JTJ[6 * 4 + 0] = sys[3];
+    JTJ[6 * 4 + 2] = -sys[1];
+    JTJ[6 * 5 + 0] = -sys[2];
+    JTJ[6 * 5 + 1] = sys[1];
+    JTJ[6 * 3 + 3] = sys[4];
+    JTJ[6 * 4 + 3] = sys[5];
+    JTJ[6 * 4 + 4] = sys[6];
+    JTJ[6 * 5 + 3] = sys[7];
+    JTJ[6 * 5 + 4] = sys[8];
+    JTJ[6 * 5 + 5] = sys[9];
+    for (int i = 0; i < 6; ++i)
+        for (int j = i + 1; j < 6; ++j) JTJ[6 * i + j] = JTJ[6 * j + i];
+    for (int i = 0; i < 6; ++i) JTr[i] = sys[10 + i];
+    if (n_correspondences) *n_correspondences = nc;
+    return KB_OK;
+}
+
+// ------------------------------------------------------------------------------- Preprocessor
+int kb_preprocessor_create(double max_range, double min_range, int deskew, int max_num_threads, kb_preprocessor **out) {
+    if (!out) return fail(KB_ERR_INVALID_ARG, "out == NULL");
+    auto p = std::make_unique<kb_preprocessor>();
+    RET(make_exec(&p->ex));
+    p->max_range = max_range;
+    p->min_range = min_range;
+    p->deskew = deskew;
+    p->threads = max_num_threads;
+    *out = p.release();
+    return KB_OK;
+}
+int kb_preprocessor_destroy(kb_preprocessor *pre) {
+    delete pre;
+    return KB_OK;
+}
+int kb_preprocessor_preprocess(kb_preprocessor *pre, const double *xyz, size_t n, const double *timestamps,
+                               size_t n_timestamps, const double relative_motion[16], double *out_xyz, size_t capacity,
+                               size_t *n_out) {
+    if (!pre || (!xyz && n) || (!timestamps && n_timestamps) || !relative_motion || !n_out)
+        return fail(KB_ERR_INVALID_ARG, "NULL argument");
+    SE3 T;
+    if (!to_se3(relative_motion, &T)) return fail(KB_ERR_NOT_SE3, "relative_motion is not in SE(3)");
+    const bool do_deskew = pre->deskew && n_timestamps > 0;
+    if (do_deskew && n_timestamps < n)
+        return fail(KB_ERR_OUT_OF_RANGE, "timestamps (%zu) shorter than frame (%zu): the reference throws std::out_of_range",
+                    n_timestamps, n);
+    Exec &ex = *pre->ex;
+    CK(cudaSetDevice(ex.device));
+    RET(pre->ws.ensure(std::max(n, n_timestamps)));
+    if (n) CK(cudaMemcpyAsync(pre->ws.in.p, xyz, n * 24, cudaMemcpyHostToDevice, ex.stream));
+    if (do_deskew) CK(cudaMemcpyAsync(pre->ws.ts.p, timestamps, n_timestamps * 8, cudaMemcpyHostToDevice, ex.stream));
+    PreParams P;
+    P.sc = ex.sc;
+    P.in = pre->ws.in.p;
+    P.ts = pre->ws.ts.p;
+    P.n = static_cast<int>(n);
+    P.n_ts = do_deskew ? static_cast<int>(n_timestamps) : 0;
+    P.deskew = pre->deskew;
+    P.motion = T;
+    P.max_range = pre->max_range;
+    P.min_range = pre->min_range;
+    P.tmp = pre->ws.tmp.p;
+    P.out = pre->ws.pre.p;
+    P.out_n = pre->ws.cnt.p;
+    RET(ex.coop(k_preprocess, P));
+    int kept = 0;
+    CK(cudaMemcpyAsync(&kept, pre->ws.cnt.p, sizeof(int), cudaMemcpyDeviceToHost, ex.stream));
+    RET(ex.sync());
+    *n_out = static_cast<size_t>(kept);
+    if (!out_xyz) return KB_OK;
+    if (capacity < static_cast<size_t>(kept)) return fail(KB_ERR_CAPACITY, "output buffer too small");
+    if (kept) CK(cudaMemcpyAsync(out_xyz, pre->ws.pre.p, static_cast<size_t>(kept) * 24, cudaMemcpyDeviceToHost, ex.stream));
+    return ex.sync();
+}
+
+// ------------------------------------------------------------------------------- AdaptiveThreshold
+int kb_threshold_create(double initial_threshold, double min_motion_threshold, double max_range, kb_threshold **out) {
+    if (!out) return fail(KB_ERR_INVALID_ARG, "out == NULL");
+    auto t = new kb_threshold();
+    t->min_motion_th = min_motion_threshold;
+    t->max_range = max_range;
+    t->model_sse = initial_threshold * initial_threshold;  // Threshold.cpp:35
+    t->num_samples = 1;
+    *out = t;
+    return KB_OK;
+}
+int kb_threshold_destroy(kb_threshold *th) {
+    delete th;
+    return KB_OK;
+}
+int kb_threshold_compute(const kb_threshold *th, double *out_sigma) {
+    if (!th || !out_sigma) return fail(KB_ERR_INVALID_ARG, "NULL argument");
+    *out_sigma = std::sqrt(th->model_sse / th->num_samples);  // Threshold.hpp:38
+    return KB_OK;
+}
+int kb_threshold_update_model_deviation(kb_threshold *th, const double model_deviation[16]) {
+    if (!th || !model_deviation) return fail(KB_ERR_INVALID_ARG, "NULL argument");
+    SE3 T;
+    if (!to_se3(model_deviation, &T)) return fail(KB_ERR_NOT_SE3, "model_deviation is not in SE(3)");
+    // scalar bookkeeping (Threshold.cpp:38-49); inside RegisterFrame the same update runs on the device
+    const double theta = angle_axis_angle(q_to_matrix(T.q));
+    const double delta_rot = 2.0 * th->max_range * std::sin(theta / 2.0);
+    const double delta_trans = norm(T.t);
+    const double model_error = delta_trans + delta_rot;
+    if (model_error > th->min_motion_th) {
+        th->model_sse += model_error * model_error;
+        th->num_samples++;
+    }
+    return KB_OK;
+}
+
+// ------------------------------------------------------------------------------- VoxelDownsample
+int kb_voxel_down_sample(const double *xyz, size_t n, double voxel_size, double *out_xyz, size_t capacity, size_t *n_out) {
+    if ((!xyz && n) || !n_out) return fail(KB_ERR_INVALID_ARG, "NULL argument");
+    if (n >= (size_t(1) << 30)) return fail(KB_ERR_INVALID_ARG, "frame too large");
+    DefaultCtx *c;
+    RET(default_ctx(&c));
+    Exec &ex = *c->ex;
+    CK(cudaSetDevice(ex.device));
+    RET(c->ws.ensure(n));
+    if (n) CK(cudaMemcpyAsync(c->ws.in.p, xyz, n * 24, cudaMemcpyHostToDevice, ex.stream));
+    RET(run_downsample(ex, c->ws, c->ws.in.p, n, voxel_size, c->ws.ds1.p, c->ws.cnt.p, 0.0, nullptr, nullptr));
+    int m = 0;
+    CK(cudaMemcpyAsync(&m, c->ws.cnt.p, sizeof(int), cudaMemcpyDeviceToHost, ex.stream));
+    RET(ex.sync());
+    *n_out = static_cast<size_t>(m);
+    if (!out_xyz) return KB_OK;
+    if (capacity < static_cast<size_t>(m)) return fail(KB_ERR_CAPACITY, "output buffer too small");
+    if (m) CK(cudaMemcpyAsync(out_xyz, c->ws.ds1.p, static_cast<size_t>(m) * 24, cudaMemcpyDeviceToHost, ex.stream));
+    return ex.sync();
+}
+
+// ------------------------------------------------------------------------------- KissICP pipeline
+void kb_config_default(kb_config *cfg) {
+    if (!cfg) return;
+    cfg->voxel_size = 1.0;
+    cfg->max_range = 100.0;
+    cfg->min_range = 0.0;
+    cfg->max_points_per_voxel = 20;
+    cfg->min_motion_th = 0.1;
+    cfg->initial_threshold = 2.0;
+    cfg->max_num_iterations = 500;
+    cfg->convergence_criterion = 0.0001;
+    cfg->max_num_threads = 0;
+    cfg->deskew = 1;
+}
+
+static int pipeline_push_state(kb_pipeline *p, const SE3 &pose, const SE3 &delta, double sse, int ns) {
+    PipeState s;
+    s.last_pose = pose;
+    s.last_delta = delta;
+    s.model_sse = sse;
+    s.num_samples = ns;
+    s.pad0 = 0;
+    CK(cudaMemcpyAsync(p->d_state, &s, sizeof(s), cudaMemcpyHostToDevice, p->ex->stream));
+    return p->ex->sync();
+}
+
+int kb_pipeline_create(const kb_config *cfg, kb_pipeline **out) {
+    if (!cfg || !out) return fail(KB_ERR_INVALID_ARG, "NULL argument");
+    auto p = std::make_unique<kb_pipeline>();
+    RET(make_exec(&p->ex));
+    p->cfg = *cfg;
+    RET(map_create_impl(cfg->voxel_size, cfg->max_range, static_cast<unsigned>(cfg->max_points_per_voxel), p->ex, &p->map));
+    p->map->borrowed = true;
+    CK(cudaMalloc(&p->d_state, sizeof(PipeState)));
+    CK(cudaMalloc(&p->d_res, sizeof(FrameResult)));
+    CK(cudaHostAlloc(&p->h_res, sizeof(FrameResult), cudaHostAllocDefault));
+    std::memset(&p->last, 0, sizeof(p->last));
+    se3_to_matrix(se3_identity(), p->last.pose);
+    se3_to_matrix(se3_identity(), p->last.delta);
+    p->last.model_sse = cfg->initial_threshold * cfg->initial_threshold;
+    p->last.num_samples = 1;
+    RET(pipeline_push_state(p.get(), se3_identity(), se3_identity(), p->last.model_sse, 1));
+    *out = p.release();
+    return KB_OK;
+}
+int kb_pipeline_destroy(kb_pipeline *p) {
+    if (p) {
+        p->map->borrowed = false;
+        kb_map *m = p->map;
+        p->map = nullptr;
+        cudaSetDevice(p->ex->device);
+        delete m;
+        delete p;
+    }
+    return KB_OK;
+}
+
+static int pipeline_run(kb_pipeline *p, const double *d_xyz, size_t n, const double *d_ts, size_t n_ts) {
+    Exec &ex = *p->ex;
+    RET(p->map->ensure_capacity(n));
+    FrameParams P;
+    P.m = p->map->view();
+    P.sc = ex.sc;
+    P.ws = p->ws.view();
+    P.st = p->d_state;
+    P.res = p->d_res;
+    P.in = d_xyz;
+    P.ts = d_ts;
+    P.n = static_cast<int>(n);
+    P.n_ts = static_cast<int>(n_ts);
+    P.deskew = p->cfg.deskew;
+    P.max_range = p->cfg.max_range;
+    P.min_range = p->cfg.min_range;
+    P.voxel_size = p->cfg.voxel_size;
+    P.max_iter = p->cfg.max_num_iterations;
+    P.conv = p->cfg.convergence_criterion;
+    P.min_motion_th = p->cfg.min_motion_th;
+    RET(ex.coop(k_register_frame, P));
+    CK(cudaMemcpyAsync(p->h_res, p->d_res, sizeof(FrameResult), cudaMemcpyDeviceToHost, ex.stream));
+    RET(ex.sync());
+    p->last = *p->h_res;
+    p->has_last = true;
+    p->map->h_counters[C_LIVE] = p->last.map_live;
+    p->map->h_counters[C_TOMB] = p->last.map_tomb;
+    p->map->h_counters[C_POINTS] = p->last.map_points;
+    p->map->h_counters[C_STATUS] = p->last.map_status;
+    if (p->last.map_status & ST_TABLE_FULL) return fail(KB_ERR_CUDA, "voxel table overflow (internal capacity bug)");
+    return KB_OK;
+}
+
+static int pipeline_check(kb_pipeline *p, const void *xyz, size_t n, const void *ts, size_t n_ts, bool *use_ts) {
+    if (!p || (!xyz && n) || (!ts && n_ts)) return fail(KB_ERR_INVALID_ARG, "NULL argument");
+    if (n >= (size_t(1) << 30)) return fail(KB_ERR_INVALID_ARG, "frame too large");
+    *use_ts = p->cfg.deskew && n_ts > 0;
+    if (*use_ts && n_ts < n)
+        return fail(KB_ERR_OUT_OF_RANGE, "timestamps (%zu) shorter than frame (%zu): the reference throws std::out_of_range",
+                    n_ts, n);
+    return KB_OK;
+}
+
+int kb_pipeline_register_frame(kb_pipeline *p, const double *xyz, size_t n, const double *timestamps, size_t n_timestamps) {
+    bool use_ts;
+    RET(pipeline_check(p, xyz, n, timestamps, n_timestamps, &use_ts));
+    Exec &ex = *p->ex;
+    CK(cudaSetDevice(ex.device));
+    RET(p->ws.ensure(std::max(n, use_ts ? n_timestamps : 0)));
+    if (n) CK(cudaMemcpyAsync(p->ws.in.p, xyz, n * 24, cudaMemcpyHostToDevice, ex.stream));
+    if (use_ts) CK(cudaMemcpyAsync(p->ws.ts.p, timestamps, n_timestamps * 8, cudaMemcpyHostToDevice, ex.stream));
+    return pipeline_run(p, p->ws.in.p, n, p->ws.ts.p, use_ts ? n_timestamps : 0);
+}
+int kb_pipeline_register_frame_dev(kb_pipeline *p, const double *d_xyz, size_t n, const double *d_timestamps,
+                                   size_t n_timestamps) {
+    bool use_ts;
+    RET(pipeline_check(p, d_xyz, n, d_timestamps, n_timestamps, &use_ts));
+    CK(cudaSetDevice(p->ex->device));
+    RET(p->ws.ensure(std::max(n, use_ts ? n_timestamps : 0)));
+    return pipeline_run(p, d_xyz, n, d_timestamps, use_ts ? n_timestamps : 0);
+}
+int kb_pipeline_last_cloud_sizes(const kb_pipeline *p, size_t *n_preprocessed, size_t *n_source) {
+    if (!p) return fail(KB_ERR_INVALID_ARG, "p == NULL");
+    if (n_preprocessed) *n_preprocessed = p->has_last ? static_cast<size_t>(p->last.n_pre) : 0;
+    if (n_source) *n_source = p->has_last ? static_cast<size_t>(p->last.n_src) : 0;
+    return KB_OK;
+}
+int kb_pipeline_last_clouds(const kb_pipeline *cp, double *preprocessed_xyz, size_t cap_preprocessed, double *source_xyz,
+                            size_t cap_source) {
+    kb_pipeline *p = const_cast<kb_pipeline *>(cp);
+    if (!p) return fail(KB_ERR_INVALID_ARG, "p == NULL");
+    if (!p->has_last) return KB_OK;
+    CK(cudaSetDevice(p->ex->device));
+    const size_t npre = static_cast<size_t>(p->last.n_pre), nsrc = static_cast<size_t>(p->last.n_src);
+    if (preprocessed_xyz) {
+        if (cap_preprocessed < npre) return fail(KB_ERR_CAPACITY, "preprocessed buffer too small");
+        if (npre) CK(cudaMemcpyAsync(preprocessed_xyz, p->ws.pre.p, npre * 24, cudaMemcpyDeviceToHost, p->ex->stream));
+    }
+    if (source_xyz) {
+        if (cap_source < nsrc) return fail(KB_ERR_CAPACITY, "source buffer too small");
+        if (nsrc) CK(cudaMemcpyAsync(source_xyz, p->ws.src.p, nsrc * 24, cudaMemcpyDeviceToHost, p->ex->stream));
+    }
+    return p->ex->sync();
+}
+int kb_pipeline_voxelize(kb_pipeline *p, const double *xyz, size_t n, double *source_xyz, size_t cap_source,
+                         size_t *n_source, double *downsample_xyz, size_t cap_downsample, size_t *n_downsample) {
+    if (!p || (!xyz && n) || !n_source || !n_downsample) return fail(KB_ERR_INVALID_ARG, "NULL argument");
+    Exec &ex = *p->ex;
+    CK(cudaSetDevice(ex.device));
+    RET(p->ws.ensure(n));
+    if (n) CK(cudaMemcpyAsync(p->ws.in.p, xyz, n * 24, cudaMemcpyHostToDevice, ex.stream));
+    RET(run_downsample(ex, p->ws, p->ws.in.p, n, p->cfg.voxel_size * 0.5, p->ws.ds1.p, p->ws.cnt.p + 1,
+                       p->cfg.voxel_size * 1.5, p->ws.src.p, p->ws.cnt.p + 2));
+    int c[2] = {0, 0};
+    CK(cudaMemcpyAsync(c, p->ws.cnt.p + 1, sizeof(c), cudaMemcpyDeviceToHost, ex.stream));
+    RET(ex.sync());
+    *n_downsample = static_cast<size_t>(c[0]);
+    *n_source = static_cast<size_t>(c[1]);
+    if (source_xyz) {
+        if (cap_source < *n_source) return fail(KB_ERR_CAPACITY, "source buffer too small");
+        if (*n_source) CK(cudaMemcpyAsync(source_xyz, p->ws.src.p, *n_source * 24, cudaMemcpyDeviceToHost, ex.stream));
+    }
+    if (downsample_xyz) {
+        if (cap_downsample < *n_downsample) return fail(KB_ERR_CAPACITY, "downsample buffer too small");
+        if (*n_downsample)
+            CK(cudaMemcpyAsync(downsample_xyz, p->ws.ds1.p, *n_downsample * 24, cudaMemcpyDeviceToHost, ex.stream));
+    }
+    return ex.sync();
+}
+int kb_pipeline_pose(const kb_pipeline *p, double out[16]) {
+    if (!p || !out) return fail(KB_ERR_INVALID_ARG, "NULL argument");
+    std::memcpy(out, p->last.pose, sizeof(double) * 16);
+    return KB_OK;
+}
+int kb_pipeline_delta(const kb_pipeline *p, double out[16]) {
+    if (!p || !out) return fail(KB_ERR_INVALID_ARG, "NULL argument");
+    std::memcpy(out, p->last.delta, sizeof(double) * 16);
+    return KB_OK;
+}
+static int pipeline_set(kb_pipeline *p, const double pose[16], const double delta[16]) {
+    SE3 a, b;
+    if (!to_se3(pose, &a) || !to_se3(delta, &b)) return fail(KB_ERR_NOT_SE3, "matrix is not in SE(3)");
+    CK(cudaSetDevice(p->ex->device));
+    RET(pipeline_push_state(p, a, b, p->last.model_sse, p->last.num_samples));
+    std::memcpy(p->last.pose, pose, sizeof(double) * 16);
+    std::memcpy(p->last.delta, delta, sizeof(double) * 16);
+    return KB_OK;
+}
+int kb_pipeline_set_pose(kb_pipeline *p, const double pose[16]) {
+    if (!p || !pose) return fail(KB_ERR_INVALID_ARG, "NULL argument");
+    return pipeline_set(p, pose, p->last.delta);
+}
+int kb_pipeline_set_delta(kb_pipeline *p, const double delta[16]) {
+    if (!p || !delta) return fail(KB_ERR_INVALID_ARG, "NULL argument");
+    return pipeline_set(p, p->last.pose, delta);
+}
+kb_map *kb_pipeline_voxel_map(kb_pipeline *p) { return p ? p->map : nullptr; }
+int kb_pipeline_last_sigma(const kb_pipeline *p, double *out) {
+    if (!p || !out) return fail(KB_ERR_INVALID_ARG, "NULL argument");
+    *out = p->last.sigma;
+    return KB_OK;
+}
+int kb_pipeline_last_iterations(const kb_pipeline *p, int *out) {
+    if (!p || !out) return fail(KB_ERR_INVALID_ARG, "NULL argument");
+    *out = p->last.iterations;
+    return KB_OK;
+}
+int kb_pipeline_launch_count(const kb_pipeline *p, unsigned long long *out) {
+    if (!p || !out) return fail(KB_ERR_INVALID_ARG, "NULL argument");
+    *out = p->ex->launches;
+    return KB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,748 @@
+// Device-side building blocks of the registration hot path (sm_100a).
+//
+// Execution model: every op below is written for a PERSISTENT COOPERATIVE GRID — one CTA per
+// SM (or fewer), all CTAs co-resident, phases separated by a hand-rolled grid barrier (one
+// L2 atomic + acquire spin, ~1 us) instead of kernel boundaries. A whole
+// KissICP::RegisterFrame is therefore ONE launch (k_register_frame in kernels.cu); the same
+// ops are also wrapped as stand-alone kernels for the module-level API.
+//
+// Data layout in HBM
+//   VoxelHashMap  -> open-addressed table of 16-byte slots {x,y,z,w} (one 128-bit load per
+//                    probe). w = point count (>=0), KB_EMPTY or KB_TOMB. The slot index IS the
+//                    index of the voxel's point block: points[slot][cap][3] FP64 (AoS, 24 B /
+//                    point, insertion order) — no indirection, no allocator; 180 GB of HBM
+//                    makes the sparse block array affordable and the L2 only ever sees the
+//                    touched sectors.
+//   clouds        -> dense double[n][3], exactly the host layout of std::vector<Eigen::Vector3d>.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cfloat>
+#include <climits>
+#include <cstdint>
+
+#include "se3.cuh"
+
+namespace kb {
+
+constexpr int KB_EMPTY = -1;
+constexpr int KB_TOMB = -2;
+constexpr unsigned FULL = 0xffffffffu;
+constexpr int BLOCK = 512;  // threads per CTA of every cooperative kernel
+constexpr int NWARPS = BLOCK / 32;
+constexpr int NACC = 16;  // unique accumulators of the 6x6 normal equations (see icp_accumulate)
+
+enum Counter { C_LIVE = 0, C_TOMB = 1, C_POINTS = 2, C_STATUS = 3, C_TOUCHED = 4, C_NCOUNTERS = 8 };
+enum StatusBit { ST_TABLE_FULL = 1 };
+
+struct MapView {
+    int4 *slots;      // [capacity]
+    double *points;   // [capacity][cap][3]
+    int *head;        // [capacity] pending-insert list head (-1 when idle)
+    int *counters;    // [C_NCOUNTERS]
+    unsigned mask;    // capacity - 1 (capacity is a power of two)
+    int cap;          // max_points_per_voxel
+    double voxel_size;
+    double max_distance;
+    double map_resolution;  // sqrt(voxel_size^2 / max_points_per_voxel)  VoxelHashMap.cpp:98
+};
+
+// cross-CTA scratch, sized by the grid
+struct Scratch {
+    unsigned *bar;  // grid barrier counter (zeroed before each launch)
+    double *blk_d;  // [grid][NACC] x2 (ping-pong) doubles
+    int *blk_i;     // [grid] ints
+};
+
+// ------------------------------------------------------------------------------------------
+// grid barrier (all CTAs co-resident: cooperative launch)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+struct Grid {
+    unsigned *bar;
+    unsigned target;
+    __device__ __forceinline__ void init(unsigned *b) {
+        bar = b;
+        target = 0;
+    }
+    __device__ __forceinline__ void sync() {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            target += gridDim.x;
+            __threadfence();
+            atomicAdd(bar, 1u);
+            while (ld_acquire_u32(bar) < target) {
+            }
+            __threadfence();  // gpu-scope fence also drops this SM's L1 lines
+        }
+        __syncthreads();
+    }
+};
+
+// ------------------------------------------------------------------------------------------
+// voxel arithmetic
+// ------------------------------------------------------------------------------------------
+// core/VoxelUtils.hpp:33-37 — FP64 DIVISION then floor then int cast (bit-exact with the CPU)
+__device__ __forceinline__ int3 point_to_voxel(double x, double y, double z, double voxel_size) {
+    return make_int3(static_cast<int>(floor(x / voxel_size)), static_cast<int>(floor(y / voxel_size)),
+                     static_cast<int>(floor(z / voxel_size)));
+}
+// std::hash<Voxel> core/VoxelUtils.hpp:45-51 — needed ONLY to reproduce VoxelDownsample's
+// output order (robin_map bucket order); the HBM map uses mix_hash below.
+__device__ __forceinline__ unsigned ref_hash(int x, int y, int z) {
+    return (static_cast<unsigned>(x) * 73856093u) ^ (static_cast<unsigned>(y) * 19349669u) ^
+           (static_cast<unsigned>(z) * 83492791u);
+}
+// well-mixed hash for the open-addressed map (short probe chains)
+__device__ __forceinline__ unsigned mix_hash(int x, int y, int z) {
+    unsigned h = static_cast<unsigned>(x) * 0x9E3779B1u;
+    h = (h ^ (h >> 15)) + static_cast<unsigned>(y) * 0x85EBCA77u;
+    h = (h ^ (h >> 13)) + static_cast<unsigned>(z) * 0xC2B2AE3Du;
+    h ^= h >> 16;
+    h *= 0x7FEB352Du;
+    h ^= h >> 15;
+    h *= 0x846CA68Bu;
+    h ^= h >> 16;
+    return h;
+}
+
+__device__ __forceinline__ int4 cas_slot(int4 *addr, int4 expected, int4 desired) {
+    unsigned __int128 e, d;
+    memcpy(&e, &expected, 16);
+    memcpy(&d, &desired, 16);
+    unsigned __int128 old = atomicCAS(reinterpret_cast<unsigned __int128 *>(addr), e, d);
+    int4 o;
+    memcpy(&o, &old, 16);
+    return o;
+}
+
+// lookup: slot index of voxel (x,y,z) or -1; *cnt = its point count
+__device__ __forceinline__ int map_find(const MapView &m, int x, int y, int z, int *cnt) {
+    unsigned h = mix_hash(x, y, z) & m.mask;
+    for (unsigned probes = 0; probes <= m.mask; ++probes) {
+        const int4 s = m.slots[h];
+        if (s.w == KB_EMPTY) return -1;
+        if (s.w != KB_TOMB && s.x == x && s.y == y && s.z == z) {
+            *cnt = s.w;
+            return static_cast<int>(h);
+        }
+        h = (h + 1) & m.mask;
+    }
+    return -1;
+}
+
+// find-or-claim for AddPoints. New voxels are claimed with w = 0 by one 128-bit CAS; tombstones
+// are never reused while inserts race (they are dropped by the host-triggered rehash).
+__device__ __forceinline__ int map_find_or_claim(const MapView &m, int x, int y, int z) {
+    unsigned h = mix_hash(x, y, z) & m.mask;
+    const int4 empty = make_int4(-1, -1, -1, KB_EMPTY);
+    for (unsigned probes = 0; probes <= m.mask; ++probes) {
+        int4 s = m.slots[h];
+        if (s.w == KB_EMPTY) {
+            s = cas_slot(&m.slots[h], empty, make_int4(x, y, z, 0));
+            if (s.w == KB_EMPTY) {
+                atomicAdd(&m.counters[C_LIVE], 1);
+                return static_cast<int>(h);
+            }
+        }
+        if (s.w != KB_TOMB && s.x == x && s.y == y && s.z == z) return static_cast<int>(h);
+        h = (h + 1) & m.mask;
+    }
+    atomicOr(&m.counters[C_STATUS], ST_TABLE_FULL);
+    return -1;
+}
+
+// ------------------------------------------------------------------------------------------
+// block-level helpers
+// ------------------------------------------------------------------------------------------
+// exclusive rank of `flag` among the CTA's threads (thread order) + CTA total
+__device__ __forceinline__ int block_rank(int flag, int *total, int *s_warp /*[NWARPS+1]*/) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned b = __ballot_sync(FULL, flag);
+    const int rank = __popc(b & ((1u << lane) - 1u));
+    __syncthreads();  // protect s_warp reuse
+    if (lane == 0) s_warp[warp] = __popc(b);
+    __syncthreads();
+    int before = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < NWARPS; ++w) {
+        const int c = s_warp[w];
+        if (w < warp) before += c;
+        tot += c;
+    }
+    *total = tot;
+    return before + rank;
+}
+
+__device__ __forceinline__ int block_sum(int v, int *s_warp) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = v;
+    __syncthreads();
+    int tot = 0;
+#pragma unroll
+    for (int w = 0; w < NWARPS; ++w) tot += s_warp[w];
+    return tot;
+}
+
+// offset of this CTA (sum of blk_i[0..b-1]) and grand total, read after a grid barrier
+__device__ __forceinline__ void grid_offsets(const int *blk_i, int *offset, int *total, int *s_two) {
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        int before = 0, tot = 0;
+        for (int i = threadIdx.x; i < static_cast<int>(gridDim.x); i += 32) {
+            const int c = __ldcg(&blk_i[i]);
+            tot += c;
+            if (i < static_cast<int>(blockIdx.x)) before += c;
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            before += __shfl_xor_sync(FULL, before, o);
+            tot += __shfl_xor_sync(FULL, tot, o);
+        }
+        if (threadIdx.x == 0) {
+            s_two[0] = before;
+            s_two[1] = tot;
+        }
+    }
+    __syncthreads();
+    *offset = s_two[0];
+    *total = s_two[1];
+}
+
+__device__ __forceinline__ void chunk_of(long long n, long long *lo, long long *hi) {
+    *lo = n * blockIdx.x / gridDim.x;
+    *hi = n * (blockIdx.x + 1) / gridDim.x;
+}
+
+// ------------------------------------------------------------------------------------------
+// op_preprocess — Preprocessor::Preprocess (core/Preprocessing.cpp:55-95)
+//   deskew (constant velocity, referenced to the END of the scan) + strict range crop +
+//   order-preserving compaction. Two passes around one grid barrier.
+// ------------------------------------------------------------------------------------------
+struct Shared {
+    int warp_i[NWARPS + 1];
+    int two[2];
+    double warp_d[NWARPS][NACC];
+    double sys[NACC];
+    double omega[6];
+    double mm[2];
+    SE3 pending;
+    SE3 t_icp;
+    SE3 result;  // op_icp output (valid in every CTA)
+    int iters;   // op_icp output
+    int flag;
+};
+
+__device__ void op_preprocess(Grid &g, const Scratch &sc, Shared &sh, const double *in, int n, const double *ts,
+                              int n_ts, bool deskew, const SE3 &motion, double max_range, double min_range,
+                              double *tmp, double *out, int *out_n) {
+    const bool do_deskew = deskew && n_ts > 0;
+    if (do_deskew) {
+        // std::minmax_element over ALL stamps (Preprocessing.cpp:62-64)
+        double mn = DBL_MAX, mx = -DBL_MAX;
+        for (int i = blockIdx.x * BLOCK + threadIdx.x; i < n_ts; i += gridDim.x * BLOCK) {
+            const double t = ts[i];
+            mn = fmin(mn, t);
+            mx = fmax(mx, t);
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            mn = fmin(mn, __shfl_xor_sync(FULL, mn, o));
+            mx = fmax(mx, __shfl_xor_sync(FULL, mx, o));
+        }
+        if ((threadIdx.x & 31) == 0) {
+            sh.warp_d[threadIdx.x >> 5][0] = mn;
+            sh.warp_d[threadIdx.x >> 5][1] = mx;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int w = 1; w < NWARPS; ++w) {
+                mn = fmin(mn, sh.warp_d[w][0]);
+                mx = fmax(mx, sh.warp_d[w][1]);
+            }
+            sc.blk_d[2 * blockIdx.x] = mn;
+            sc.blk_d[2 * blockIdx.x + 1] = mx;
+        }
+        g.sync();
+        if (threadIdx.x == 0) {
+            double a = DBL_MAX, b = -DBL_MAX;
+            for (unsigned i = 0; i < gridDim.x; ++i) {
+                a = fmin(a, __ldcg(&sc.blk_d[2 * i]));
+                b = fmax(b, __ldcg(&sc.blk_d[2 * i + 1]));
+            }
+            sh.mm[0] = a;
+            sh.mm[1] = b;
+            se3_log(motion, sh.omega);  // relative_motion.log()  (:68)
+        }
+        __syncthreads();
+    }
+    long long lo, hi;
+    chunk_of(n, &lo, &hi);
+    // pass 1: deskew into tmp, count survivors of the crop
+    int kept = 0;
+    for (long long base = lo; base < hi; base += BLOCK) {
+        const long long i = base + threadIdx.x;
+        if (i < hi) {
+            V3 p{in[3 * i], in[3 * i + 1], in[3 * i + 2]};
+            if (do_deskew) {
+                const double stamp = (ts[i] - sh.mm[0]) / (sh.mm[1] - sh.mm[0]);
+                double a[6];
+#pragma unroll
+                for (int k = 0; k < 6; ++k) a[k] = (stamp - 1.0) * sh.omega[k];
+                p = se3_act(se3_exp(a), p);
+                tmp[3 * i] = p.x;
+                tmp[3 * i + 1] = p.y;
+                tmp[3 * i + 2] = p.z;
+            }
+            const double r = norm(p);
+            kept += (r < max_range && r > min_range) ? 1 : 0;
+        }
+    }
+    const int blk_kept = block_sum(kept, sh.warp_i);
+    if (threadIdx.x == 0) sc.blk_i[blockIdx.x] = blk_kept;
+    g.sync();
+    int offset, total;
+    grid_offsets(sc.blk_i, &offset, &total, sh.two);
+    if (blockIdx.x == 0 && threadIdx.x == 0) *out_n = total;
+    // pass 2: ordered compaction
+    const double *src = do_deskew ? tmp : in;
+    int run = offset;
+    for (long long base = lo; base < hi; base += BLOCK) {
+        const long long i = base + threadIdx.x;
+        V3 p{0, 0, 0};
+        int keep = 0;
+        if (i < hi) {
+            p = V3{src[3 * i], src[3 * i + 1], src[3 * i + 2]};
+            const double r = norm(p);
+            keep = (r < max_range && r > min_range) ? 1 : 0;
+        }
+        int tile_total;
+        const int rank = block_rank(keep, &tile_total, sh.warp_i);
+        if (keep) {
+            const long long o = run + rank;
+            out[3 * o] = p.x;
+            out[3 * o + 1] = p.y;
+            out[3 * o + 2] = p.z;
+        }
+        run += tile_total;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// op_downsample — VoxelDownsample (core/VoxelUtils.cpp:7-21)
+//   keeps the first point (input order) of every voxel and emits them in the ITERATION ORDER
+//   of the reference's tsl::robin_map: bucket_count = pow2 >= 2n (reserve(n), max load 0.5,
+//   never rehashes while filling), home = std::hash<Voxel> & (B-1), robin-hood linear probing.
+//   The final robin-hood layout is canonical: inside every maximal occupied run the entries
+//   are ordered by (home, insertion index) and the set of occupied buckets equals that of
+//   plain linear probing. So: (a) fill a scratch table of B slots by linear probing from the
+//   reference's home bucket with CAS + atomicMin(first index); (b) prefix-count occupied
+//   buckets; (c) every entry ranks itself inside its run and lands at prefix[canonical bucket].
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned robin_bucket_count(int n) {
+    if (n <= 0) return 0;
+    // reserve(n): size_t(ceil(float(n) / 0.5f)) rounded up to a power of two
+    const float c = ceilf(static_cast<float>(n) / 0.5f);
+    unsigned long long want = static_cast<unsigned long long>(c);
+    unsigned long long p = 1;
+    while (p < want) p <<= 1;
+    return static_cast<unsigned>(p);
+}
+
+__device__ void op_downsample(Grid &g, const Scratch &sc, Shared &sh, const double *in, int n, double voxel_size,
+                              int4 *ds_slots, int *ds_prefix, double *out, int *out_n) {
+    const unsigned B = robin_bucket_count(n);
+    if (B == 0) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) *out_n = 0;
+        return;  // uniform across the grid
+    }
+    const unsigned mask = B - 1;
+    const int4 empty = make_int4(-1, -1, -1, KB_EMPTY);
+    for (unsigned i = blockIdx.x * BLOCK + threadIdx.x; i < B; i += gridDim.x * BLOCK) ds_slots[i] = empty;
+    g.sync();
+    // (a) dedupe: first input index per voxel
+    for (int i = blockIdx.x * BLOCK + threadIdx.x; i < n; i += gridDim.x * BLOCK) {
+        const int3 v = point_to_voxel(in[3 * i], in[3 * i + 1], in[3 * i + 2], voxel_size);
+        unsigned h = ref_hash(v.x, v.y, v.z) & mask;
+        while (true) {
+            int4 s = ds_slots[h];
+            if (s.w == KB_EMPTY) s = cas_slot(&ds_slots[h], empty, make_int4(v.x, v.y, v.z, i));
+            if (s.w == KB_EMPTY) break;  // claimed with our index
+            if (s.x == v.x && s.y == v.y && s.z == v.z) {
+                atomicMin(&ds_slots[h].w, i);
+                break;
+            }
+            h = (h + 1) & mask;
+        }
+    }
+    g.sync();
+    // (b) occupancy prefix over buckets (two passes around a barrier)
+    long long lo, hi;
+    chunk_of(B, &lo, &hi);
+    int cnt = 0;
+    for (long long i = lo + threadIdx.x; i < hi; i += BLOCK) cnt += (ds_slots[i].w != KB_EMPTY) ? 1 : 0;
+    const int blk_cnt = block_sum(cnt, sh.warp_i);
+    if (threadIdx.x == 0) sc.blk_i[blockIdx.x] = blk_cnt;
+    g.sync();
+    int offset, total;
+    grid_offsets(sc.blk_i, &offset, &total, sh.two);
+    if (blockIdx.x == 0 && threadIdx.x == 0) *out_n = total;
+    int run = offset;
+    for (long long base = lo; base < hi; base += BLOCK) {
+        const long long i = base + threadIdx.x;
+        const int occ = (i < hi && ds_slots[i].w != KB_EMPTY) ? 1 : 0;
+        int tile_total;
+        const int rank = block_rank(occ, &tile_total, sh.warp_i);
+        if (i < hi) ds_prefix[i] = run + rank;
+        run += tile_total;
+    }
+    g.sync();
+    // (c) canonical robin-hood position of every entry -> output index
+    for (unsigned h = blockIdx.x * BLOCK + threadIdx.x; h < B; h += gridDim.x * BLOCK) {
+        const int4 e = ds_slots[h];
+        if (e.w == KB_EMPTY) continue;
+        unsigned s = h;  // start of the occupied run containing h
+        while (ds_slots[(s - 1) & mask].w != KB_EMPTY) s = (s - 1) & mask;
+        const unsigned my_home = ((ref_hash(e.x, e.y, e.z) & mask) - s) & mask;  // offset inside the run
+        unsigned rank = 0;
+        for (unsigned p = s;; p = (p + 1) & mask) {
+            const int4 f = ds_slots[p];
+            if (f.w == KB_EMPTY) break;
+            const unsigned f_home = ((ref_hash(f.x, f.y, f.z) & mask) - s) & mask;
+            rank += (f_home < my_home || (f_home == my_home && f.w < e.w)) ? 1u : 0u;
+        }
+        const long long o = ds_prefix[(s + rank) & mask];
+        const long long src = e.w;
+        out[3 * o] = in[3 * src];
+        out[3 * o + 1] = in[3 * src + 1];
+        out[3 * o + 2] = in[3 * src + 2];
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// nn_search_warp — VoxelHashMap::GetClosestNeighbor (core/VoxelHashMap.cpp:46-70)
+//   one warp per query: lanes 0..26 probe the 27 neighbour voxels (one 128-bit slot load
+//   each, in the reference's voxel_shifts order), then the warp walks the occupied voxels,
+//   lane i taking point i of the block. Ties resolve like the reference (first voxel in
+//   shift order, first point in the voxel): lexicographic (distance, sequence) minimum.
+//   distance = sqrt((dx*dx + dy*dy) + dz*dz) exactly as Eigen's (neighbor - query).norm().
+// ------------------------------------------------------------------------------------------
+__constant__ int c_shifts[27][3] = {
+    {0, 0, 0},   {1, 0, 0},   {-1, 0, 0},  {0, 1, 0},   {0, -1, 0},  {0, 0, 1},   {0, 0, -1},
+    {1, 1, 0},   {1, -1, 0},  {-1, 1, 0},  {-1, -1, 0}, {1, 0, 1},   {1, 0, -1},  {-1, 0, 1},
+    {-1, 0, -1}, {0, 1, 1},   {0, 1, -1},  {0, -1, 1},  {0, -1, -1}, {1, 1, 1},   {1, 1, -1},
+    {1, -1, 1},  {1, -1, -1}, {-1, 1, 1},  {-1, 1, -1}, {-1, -1, 1}, {-1, -1, -1}};
+
+struct NNResult {
+    double d;  // DBL_MAX on a miss
+    V3 p;      // (0,0,0) on a miss
+    int candidates;
+};
+
+__device__ __forceinline__ NNResult nn_search_warp(const MapView &m, const V3 &q, int lane) {
+    const int3 v = point_to_voxel(q.x, q.y, q.z, m.voxel_size);
+    int cnt = 0, slot = -1;
+    if (lane < 27) {
+        slot = map_find(m, v.x + c_shifts[lane][0], v.y + c_shifts[lane][1], v.z + c_shifts[lane][2], &cnt);
+        if (slot < 0) cnt = 0;
+    }
+    unsigned occ = __ballot_sync(FULL, cnt > 0);
+    double best = DBL_MAX;
+    int bseq = INT_MAX;
+    V3 bp{0, 0, 0};
+    int ncand = 0;
+    const int cap = m.cap;
+    while (occ) {
+        const int vi = __ffs(occ) - 1;
+        occ &= occ - 1;
+        const int c = __shfl_sync(FULL, cnt, vi);
+        const int s = __shfl_sync(FULL, slot, vi);
+        ncand += c;
+        const double *blk = m.points + static_cast<size_t>(s) * cap * 3;
+        for (int k = lane; k < c; k += 32) {
+            const V3 p{blk[3 * k], blk[3 * k + 1], blk[3 * k + 2]};
+            const double d = norm(p - q);
+            if (d < best) {  // per lane the sequence number only grows: strict < keeps the first
+                best = d;
+                bseq = vi * 1024 + k;
+                bp = p;
+            }
+        }
+    }
+    // lexicographic (distance, sequence) minimum across the warp
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double od = __shfl_xor_sync(FULL, best, o);
+        const int os = __shfl_xor_sync(FULL, bseq, o);
+        const double ox = __shfl_xor_sync(FULL, bp.x, o);
+        const double oy = __shfl_xor_sync(FULL, bp.y, o);
+        const double oz = __shfl_xor_sync(FULL, bp.z, o);
+        if (od < best || (od == best && os < bseq)) {
+            best = od;
+            bseq = os;
+            bp = V3{ox, oy, oz};
+        }
+    }
+    return NNResult{best, bp, ncand};
+}
+
+// ------------------------------------------------------------------------------------------
+// icp_accumulate — one correspondence of BuildLinearSystem (core/Registration.cpp:80-121)
+//   J = [I | -hat(s)], w = k^2/(k + |r|^2)^2, JTJ += J^T w J, JTr += J^T w r. With N = -hat(s)
+//   the 6x6 has only 16 distinct accumulators:
+//     acc[0]      sum w                     (JTJ[0][0] = [1][1] = [2][2])
+//     acc[1..3]   sum w*s.x, w*s.y, w*s.z   (the antisymmetric lower-left block)
+//     acc[4..9]   lower triangle of N^T w N ((3,3),(4,3),(4,4),(5,3),(5,4),(5,5))
+//     acc[10..15] JTr
+//   Each product/sum is formed exactly as Eigen forms (J^T*w)*J entry by entry.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void icp_accumulate(double acc[NACC], const V3 &s, const V3 &t, double kscale) {
+    const V3 r = s - t;
+    const double r2 = sqnorm(r);
+    const double w = (kscale * kscale) / ((kscale + r2) * (kscale + r2));
+    const double xw = s.x * w, yw = s.y * w, zw = s.z * w;
+    acc[0] += w;
+    acc[1] += xw;
+    acc[2] += yw;
+    acc[3] += zw;
+    acc[4] += zw * s.z + yw * s.y;     // (3,3)
+    acc[5] += -(xw * s.y);             // (4,3)
+    acc[6] += zw * s.z + xw * s.x;     // (4,4)
+    acc[7] += -(xw * s.z);             // (5,3)
+    acc[8] += -(yw * s.z);             // (5,4)
+    acc[9] += yw * s.y + xw * s.x;     // (5,5)
+    acc[10] += w * r.x;
+    acc[11] += w * r.y;
+    acc[12] += w * r.z;
+    acc[13] += -(zw * r.y) + yw * r.z;
+    acc[14] += zw * r.x - xw * r.z;
+    acc[15] += -(yw * r.x) + xw * r.y;
+}
+
+// expand the 16 accumulators to the (lower-triangle-complete) row-major 6x6 and rhs = -JTr
+__device__ __forceinline__ void icp_expand(const double a[NACC], double JTJ[36], double JTr[6]) {
+    for (int i = 0; i < 36; ++i) JTJ[i] = 0.0;
+    JTJ[0] = JTJ[7] = JTJ[14] = a[0];
+    // rows 3..5, cols 0..2 : entry (3+i, j) = N[j][i] * w,  N = [[0,z,-y],[-z,0,x],[y,-x,0]]
+    JTJ[6 * 3 + 1] = -a[3];
+    JTJ[6 * 3 + 2] = a[2];
+    JTJ[6 * 4 + 0] = a[3];
+    JTJ[6 * 4 + 2] = -a[1];
+    JTJ[6 * 5 + 0] = -a[2];
+    JTJ[6 * 5 + 1] = a[1];
+    JTJ[6 * 3 + 3] = a[4];
+    JTJ[6 * 4 + 3] = a[5];
+    JTJ[6 * 4 + 4] = a[6];
+    JTJ[6 * 5 + 3] = a[7];
+    JTJ[6 * 5 + 4] = a[8];
+    JTJ[6 * 5 + 5] = a[9];
+    for (int i = 0; i < 6; ++i)
+        for (int j = i + 1; j < 6; ++j) JTJ[6 * i + j] = JTJ[6 * j + i];
+    for (int i = 0; i < 6; ++i) JTr[i] = a[10 + i];
+}
+
+// one DataAssociation + BuildLinearSystem pass over the grid (Registration.cpp:60-121).
+// `pending` is applied to every source point first (TransformPoints, :55-58) and the moved
+// point is written back to `work`. Result: sh.sys[NACC] identical in every CTA (fixed
+// reduction order: query-strided per warp -> warps in order -> CTAs in order).
+__device__ void icp_pass(Grid &g, const Scratch &sc, Shared &sh, const MapView &m, const double *src, double *work,
+                         int n, const SE3 &pending, double max_dist, double kscale, int parity, int *n_corr) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int gwarp = blockIdx.x * NWARPS + warp, nwarps = gridDim.x * NWARPS;
+    double acc[NACC];
+#pragma unroll
+    for (int i = 0; i < NACC; ++i) acc[i] = 0.0;
+    int corr = 0;
+    for (int qi = gwarp; qi < n; qi += nwarps) {
+        V3 p{src[3 * qi], src[3 * qi + 1], src[3 * qi + 2]};
+        p = se3_act(pending, p);
+        if (lane == 0) {
+            work[3 * qi] = p.x;
+            work[3 * qi + 1] = p.y;
+            work[3 * qi + 2] = p.z;
+        }
+        const NNResult r = nn_search_warp(m, p, lane);
+        if (r.d < max_dist) {
+            icp_accumulate(acc, p, r.p, kscale);
+            ++corr;
+        }
+    }
+    __syncthreads();
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < NACC; ++i) sh.warp_d[warp][i] = acc[i];
+        sh.warp_i[warp] = corr;
+    }
+    __syncthreads();
+    double *mine = sc.blk_d + (static_cast<size_t>(parity) * gridDim.x + blockIdx.x) * (NACC + 1);
+    if (threadIdx.x < NACC) {
+        double s = 0.0;
+        for (int w = 0; w < NWARPS; ++w) s += sh.warp_d[w][threadIdx.x];
+        mine[threadIdx.x] = s;
+    } else if (threadIdx.x == NACC) {
+        int c = 0;
+        for (int w = 0; w < NWARPS; ++w) c += sh.warp_i[w];
+        mine[NACC] = static_cast<double>(c);
+    }
+    g.sync();
+    // every CTA reduces all partials in the same order -> bitwise identical systems everywhere
+    const double *all = sc.blk_d + static_cast<size_t>(parity) * gridDim.x * (NACC + 1);
+    if (warp <= NACC / 2) {  // warps 0..8 : two accumulators each (17 values incl. the count)
+        for (int e = warp * 2; e < warp * 2 + 2 && e <= NACC; ++e) {
+            double s = 0.0;
+            for (int b = lane; b < static_cast<int>(gridDim.x); b += 32) s += __ldcg(&all[static_cast<size_t>(b) * (NACC + 1) + e]);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
+            if (lane == 0) {
+                if (e < NACC)
+                    sh.sys[e] = s;
+                else
+                    sh.two[0] = static_cast<int>(s);
+            }
+        }
+    }
+    __syncthreads();
+    if (n_corr) *n_corr = sh.two[0];
+}
+
+// ------------------------------------------------------------------------------------------
+// op_icp — Registration::AlignPointsToMap (core/Registration.cpp:138-167), device resident:
+//   no host round trip per iteration, ONE grid barrier per iteration; every CTA solves the
+//   6x6 redundantly (identical inputs, identical code) so no broadcast step is needed.
+// ------------------------------------------------------------------------------------------
+__device__ void op_icp(Grid &g, const Scratch &sc, Shared &sh, const MapView &m, const double *src, double *work,
+                       int n, const SE3 &guess, double max_dist, double kscale, int max_iter, double conv) {
+    if (__ldcg(&m.counters[C_LIVE]) == 0) {  // voxel_map.Empty() -> return initial_guess (:143)
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            sh.result = guess;
+            sh.iters = 0;
+        }
+        __syncthreads();
+        return;
+    }
+    if (threadIdx.x == 0) {
+        sh.pending = guess;
+        sh.t_icp = se3_identity();
+        sh.flag = 0;
+    }
+    __syncthreads();
+    int j = 0;
+    for (; j < max_iter; ++j) {
+        const SE3 pending = sh.pending;
+        icp_pass(g, sc, sh, m, j == 0 ? src : work, work, n, pending, max_dist, kscale, j & 1, nullptr);
+        if (threadIdx.x == 0) {
+            double JTJ[36], JTr[6], rhs[6], dx[6];
+            icp_expand(sh.sys, JTJ, JTr);
+            for (int i = 0; i < 6; ++i) rhs[i] = -JTr[i];
+            ldlt6_solve(JTJ, rhs, dx);               // :156
+            const SE3 est = se3_exp(dx);             // :157
+            sh.t_icp = se3_mul(est, sh.t_icp);       // :161
+            sh.pending = est;                        // applied lazily at the next pass (:159)
+            double n2 = 0.0;
+            for (int i = 0; i < 6; ++i) n2 += dx[i] * dx[i];
+            sh.flag = (sqrt(n2) < conv) ? 1 : 0;     // :163
+        }
+        __syncthreads();
+        if (sh.flag) {
+            ++j;
+            break;
+        }
+    }
+    if (threadIdx.x == 0) {
+        sh.result = se3_mul(sh.t_icp, guess);  // :166
+        sh.iters = j;
+    }
+    __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------
+// op_map_update — VoxelHashMap::Update / AddPoints / RemovePointsFarFromLocation
+//   (core/VoxelHashMap.cpp:83-132). AddPoints is sequential and order dependent in the
+//   reference; voxels are independent of each other, so: phase A every new point finds or
+//   claims its voxel and pushes itself on that voxel's pending list; phase B one thread per
+//   touched voxel replays its pending points in ascending input index (= reference order)
+//   with the reference's accept rule; phase C evicts by the first point of each voxel.
+// ------------------------------------------------------------------------------------------
+__device__ void op_map_add(Grid &g, Shared &sh, const MapView &m, const double *pts, int n, bool has_pose,
+                           const SE3 &pose, double *tp, int *next, int *touched) {
+    for (int i = blockIdx.x * BLOCK + threadIdx.x; i < n; i += gridDim.x * BLOCK) {
+        V3 p{pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]};
+        if (has_pose) p = se3_act(pose, p);  // VoxelHashMap.cpp:91-93
+        tp[3 * i] = p.x;
+        tp[3 * i + 1] = p.y;
+        tp[3 * i + 2] = p.z;
+        const int3 v = point_to_voxel(p.x, p.y, p.z, m.voxel_size);
+        const int s = map_find_or_claim(m, v.x, v.y, v.z);
+        if (s < 0) {
+            next[i] = -1;
+            continue;
+        }
+        const int old = atomicExch(&m.head[s], i);
+        next[i] = old;
+        if (old == -1) touched[atomicAdd(&m.counters[C_TOUCHED], 1)] = s;
+    }
+    g.sync();
+    const int n_touched = __ldcg(&m.counters[C_TOUCHED]);
+    const int cap = m.cap;
+    for (int t = blockIdx.x * BLOCK + threadIdx.x; t < n_touched; t += gridDim.x * BLOCK) {
+        const int s = __ldcg(&touched[t]);
+        int cnt = m.slots[s].w;
+        double *vp = m.points + static_cast<size_t>(s) * cap * 3;
+        const int first = m.head[s];
+        int last = -1, added = 0;
+        while (cnt < cap) {
+            int pick = INT_MAX;
+            for (int j = first; j != -1; j = next[j])
+                if (j > last && j < pick) pick = j;
+            if (pick == INT_MAX) break;
+            last = pick;
+            const V3 p{tp[3 * pick], tp[3 * pick + 1], tp[3 * pick + 2]};
+            bool reject = false;
+            for (int k = 0; k < cnt; ++k) {
+                const V3 e{vp[3 * k], vp[3 * k + 1], vp[3 * k + 2]};
+                if (norm(e - p) < m.map_resolution) {
+                    reject = true;
+                    break;
+                }
+            }
+            if (!reject) {
+                vp[3 * cnt] = p.x;
+                vp[3 * cnt + 1] = p.y;
+                vp[3 * cnt + 2] = p.z;
+                ++cnt;
+                ++added;
+            }
+        }
+        m.slots[s].w = cnt;
+        m.head[s] = -1;
+        if (added) atomicAdd(&m.counters[C_POINTS], added);
+    }
+    g.sync();
+    if (blockIdx.x == 0 && threadIdx.x == 0) m.counters[C_TOUCHED] = 0;
+    (void)sh;
+}
+
+__device__ void op_map_remove_far(const MapView &m, const V3 &origin) {
+    const double max_d2 = m.max_distance * m.max_distance;
+    const size_t cap3 = static_cast<size_t>(m.cap) * 3;
+    for (unsigned s = blockIdx.x * BLOCK + threadIdx.x; s <= m.mask; s += gridDim.x * BLOCK) {
+        const int w = m.slots[s].w;
+        if (w < 0) continue;
+        const double *vp = m.points + s * cap3;
+        const V3 pt{vp[0], vp[1], vp[2]};
+        if (sqnorm(pt - origin) >= max_d2) {  // tests only voxel_points.front()  (:125-126)
+            m.slots[s].w = KB_TOMB;
+            atomicSub(&m.counters[C_LIVE], 1);
+            atomicAdd(&m.counters[C_TOMB], 1);
+            atomicSub(&m.counters[C_POINTS], w);
+        }
+    }
+}
+
+}  // namespace kb

@@ -1,0 +1,365 @@
+// __global__ entry points. Cooperative (persistent-grid) kernels take one parameter struct by
+// value; see device_ops.cuh for the ops and the data layout.
+#pragma once
+
+#include "device_ops.cuh"
+
+namespace kb {
+
+// state of one kiss_icp::pipeline::KissICP instance, resident in HBM (KissICP.hpp:87-95)
+struct PipeState {
+    SE3 last_pose;
+    SE3 last_delta;
+    double model_sse;  // AdaptiveThreshold::model_sse_   Threshold.hpp:45
+    int num_samples;   // AdaptiveThreshold::num_samples_ Threshold.hpp:46
+    int pad0;
+};
+
+// what the host reads back after every RegisterFrame (one small D2H)
+struct FrameResult {
+    double pose[16];   // row-major new pose
+    double delta[16];  // row-major last_delta
+    double sigma;      // adaptive threshold used for this frame
+    double model_sse;
+    int num_samples;
+    int iterations;
+    int n_pre, n_ds, n_src;
+    int map_live, map_tomb, map_points, map_status;
+    int pad;
+};
+
+struct Workspace {
+    double *tmp;    // [n][3] deskewed points
+    double *pre;    // [n][3] preprocessed frame
+    double *ds1;    // [n][3] frame_downsample (0.5 v)
+    double *src;    // [n][3] source (1.5 v)
+    double *work;   // [n][3] source in the map frame (ICP iterate)
+    double *tp;     // [n][3] points being inserted, map frame
+    int *next;      // [n] pending-list links
+    int *touched;   // [n] voxels touched by the current AddPoints
+    int4 *ds_slots;  // [pow2 >= 2n] downsample scratch table
+    int *ds_prefix;  // [pow2 >= 2n]
+    int *cnt;        // [8] device-side counts (n_pre, n_ds, n_src, ...)
+};
+
+struct FrameParams {
+    MapView m;
+    Scratch sc;
+    Workspace ws;
+    PipeState *st;
+    FrameResult *res;
+    const double *in;
+    const double *ts;
+    int n, n_ts;
+    int deskew;
+    double max_range, min_range, voxel_size;
+    int max_iter;
+    double conv, min_motion_th;
+};
+
+__device__ __forceinline__ void threshold_update(const SE3 &dev, double min_motion_th, double max_range,
+                                                 double *sse, int *ns) {
+    // AdaptiveThreshold::UpdateModelDeviation  core/Threshold.cpp:38-49
+    const double theta = angle_axis_angle(q_to_matrix(dev.q));
+    const double delta_rot = 2.0 * max_range * sin(theta / 2.0);
+    const double delta_trans = norm(dev.t);
+    const double model_error = delta_trans + delta_rot;
+    if (model_error > min_motion_th) {
+        *sse += model_error * model_error;
+        *ns += 1;
+    }
+}
+
+// ---- KissICP::RegisterFrame (pipeline/KissICP.cpp:35-68) as ONE persistent kernel ----------
+__global__ void __launch_bounds__(BLOCK, 1) k_register_frame(const FrameParams P) {
+    __shared__ Shared sh;
+    Grid g;
+    g.init(P.sc.bar);
+    const SE3 last_pose = P.st->last_pose;
+    const SE3 last_delta = P.st->last_delta;
+    const double model_sse = P.st->model_sse;
+    const int num_samples = P.st->num_samples;
+
+    // Preprocess (KissICP.cpp:38)
+    op_preprocess(g, P.sc, sh, P.in, P.n, P.ts, P.n_ts, P.deskew != 0, last_delta, P.max_range, P.min_range,
+                  P.ws.tmp, P.ws.pre, &P.ws.cnt[0]);
+    g.sync();
+    const int n_pre = __ldcg(&P.ws.cnt[0]);
+    // Voxelize (KissICP.cpp:70-75)
+    op_downsample(g, P.sc, sh, P.ws.pre, n_pre, P.voxel_size * 0.5, P.ws.ds_slots, P.ws.ds_prefix, P.ws.ds1,
+                  &P.ws.cnt[1]);
+    g.sync();
+    const int n_ds = __ldcg(&P.ws.cnt[1]);
+    op_downsample(g, P.sc, sh, P.ws.ds1, n_ds, P.voxel_size * 1.5, P.ws.ds_slots, P.ws.ds_prefix, P.ws.src,
+                  &P.ws.cnt[2]);
+    g.sync();
+    const int n_src = __ldcg(&P.ws.cnt[2]);
+    // sigma, initial guess (KissICP.cpp:44,47)
+    const double sigma = sqrt(model_sse / num_samples);
+    const SE3 guess = se3_mul(last_pose, last_delta);
+    // ICP (KissICP.cpp:50-54)
+    op_icp(g, P.sc, sh, P.m, P.ws.src, P.ws.work, n_src, guess, 3.0 * sigma, sigma, P.max_iter, P.conv);
+    const SE3 new_pose = sh.result;
+    const int iters = sh.iters;
+    // local_map_.Update(frame_downsample, new_pose) (KissICP.cpp:61)
+    op_map_add(g, sh, P.m, P.ws.ds1, n_ds, true, new_pose, P.ws.tp, P.ws.next, P.ws.touched);
+    op_map_remove_far(P.m, new_pose.t);
+    g.sync();
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        // model deviation, threshold, delta, pose (KissICP.cpp:57-63)
+        const SE3 dev = se3_mul(se3_inverse(guess), new_pose);
+        double sse = model_sse;
+        int ns = num_samples;
+        threshold_update(dev, P.min_motion_th, P.max_range, &sse, &ns);
+        const SE3 delta = se3_mul(se3_inverse(last_pose), new_pose);
+        P.st->model_sse = sse;
+        P.st->num_samples = ns;
+        P.st->last_delta = delta;
+        P.st->last_pose = new_pose;
+        FrameResult *r = P.res;
+        se3_to_matrix(new_pose, r->pose);
+        se3_to_matrix(delta, r->delta);
+        r->sigma = sigma;
+        r->model_sse = sse;
+        r->num_samples = ns;
+        r->iterations = iters;
+        r->n_pre = n_pre;
+        r->n_ds = n_ds;
+        r->n_src = n_src;
+        r->map_live = P.m.counters[C_LIVE];
+        r->map_tomb = P.m.counters[C_TOMB];
+        r->map_points = P.m.counters[C_POINTS];
+        r->map_status = P.m.counters[C_STATUS];
+    }
+}
+
+// ---- stand-alone wrappers (module-level API) -------------------------------------------------
+struct PreParams {
+    Scratch sc;
+    const double *in;
+    const double *ts;
+    int n, n_ts, deskew;
+    SE3 motion;
+    double max_range, min_range;
+    double *tmp, *out;
+    int *out_n;
+};
+__global__ void __launch_bounds__(BLOCK, 1) k_preprocess(const PreParams P) {
+    __shared__ Shared sh;
+    Grid g;
+    g.init(P.sc.bar);
+    op_preprocess(g, P.sc, sh, P.in, P.n, P.ts, P.n_ts, P.deskew != 0, P.motion, P.max_range, P.min_range, P.tmp,
+                  P.out, P.out_n);
+}
+
+struct DsParams {
+    Scratch sc;
+    const double *in;
+    int n;
+    double voxel_size;
+    int4 *ds_slots;
+    int *ds_prefix;
+    double *out;
+    int *out_n;
+    // optional second stage (Voxelize): out2 = downsample(out, voxel_size2)
+    double voxel_size2;
+    double *out2;
+    int *out_n2;
+};
+__global__ void __launch_bounds__(BLOCK, 1) k_downsample(const DsParams P) {
+    __shared__ Shared sh;
+    Grid g;
+    g.init(P.sc.bar);
+    op_downsample(g, P.sc, sh, P.in, P.n, P.voxel_size, P.ds_slots, P.ds_prefix, P.out, P.out_n);
+    if (P.out2) {
+        g.sync();
+        const int n1 = __ldcg(P.out_n);
+        op_downsample(g, P.sc, sh, P.out, n1, P.voxel_size2, P.ds_slots, P.ds_prefix, P.out2, P.out_n2);
+    }
+}
+
+struct IcpParams {
+    MapView m;
+    Scratch sc;
+    const double *src;
+    double *work;
+    int n;
+    SE3 guess;
+    double max_dist, kscale;
+    int max_iter;
+    double conv;
+    double *out_pose;  // [16] row-major
+    int *out_iters;
+    // build-system-only mode (one pass, no solve): out_sys[NACC], out_ncorr
+    int system_only;
+    double *out_sys;
+    int *out_ncorr;
+};
+__global__ void __launch_bounds__(BLOCK, 1) k_icp(const IcpParams P) {
+    __shared__ Shared sh;
+    Grid g;
+    g.init(P.sc.bar);
+    if (P.system_only) {
+        int nc = 0;
+        icp_pass(g, P.sc, sh, P.m, P.src, P.work, P.n, se3_identity(), P.max_dist, P.kscale, 0, &nc);
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            for (int i = 0; i < NACC; ++i) P.out_sys[i] = sh.sys[i];
+            *P.out_ncorr = nc;
+        }
+        return;
+    }
+    op_icp(g, P.sc, sh, P.m, P.src, P.work, P.n, P.guess, P.max_dist, P.kscale, P.max_iter, P.conv);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        se3_to_matrix(sh.result, P.out_pose);
+        *P.out_iters = sh.iters;
+    }
+}
+
+struct MapUpdParams {
+    MapView m;
+    Scratch sc;
+    const double *pts;
+    int n;
+    int has_pose;
+    SE3 pose;
+    int do_add, do_remove;
+    V3 origin;
+    double *tp;
+    int *next;
+    int *touched;
+};
+__global__ void __launch_bounds__(BLOCK, 1) k_map_update(const MapUpdParams P) {
+    __shared__ Shared sh;
+    Grid g;
+    g.init(P.sc.bar);
+    if (P.do_add) op_map_add(g, sh, P.m, P.pts, P.n, P.has_pose != 0, P.pose, P.tp, P.next, P.touched);
+    if (P.do_remove) op_map_remove_far(P.m, P.origin);
+}
+
+// table initialisation / clear
+__global__ void k_map_fill(int4 *slots, int *head, size_t capacity) {
+    const int4 empty = make_int4(-1, -1, -1, KB_EMPTY);
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < capacity;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        slots[i] = empty;
+        head[i] = -1;
+    }
+}
+
+// rebuild into a larger / tombstone-free table: every live voxel moves with its block
+__global__ void k_map_rehash(const MapView from, const MapView to) {
+    const int lane = threadIdx.x & 31;
+    const size_t gw = (blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x) >> 5;
+    const size_t nw = (static_cast<size_t>(gridDim.x) * blockDim.x) >> 5;
+    const size_t cap3 = static_cast<size_t>(from.cap) * 3;
+    for (size_t s = gw; s <= from.mask; s += nw) {
+        const int4 e = from.slots[s];
+        if (e.w < 0) continue;
+        int d = 0;
+        if (lane == 0) d = map_find_or_claim(to, e.x, e.y, e.z);
+        d = __shfl_sync(FULL, d, 0);
+        if (d < 0) continue;
+        const double *a = from.points + s * cap3;
+        double *b = to.points + static_cast<size_t>(d) * cap3;
+        for (int k = lane; k < e.w * 3; k += 32) b[k] = a[k];
+        if (lane == 0) {
+            to.slots[d].w = e.w;
+            atomicAdd(&to.counters[C_POINTS], e.w);
+        }
+    }
+}
+
+// batched GetClosestNeighbor (VoxelHashMap.cpp:46-70): one warp per query, grid-stride
+template <bool COUNT>
+__global__ void __launch_bounds__(256) k_nn_query(const MapView m, const double *__restrict__ q, size_t n,
+                                                  double *__restrict__ out_p, double *__restrict__ out_d,
+                                                  unsigned long long *cand_total) {
+    const int lane = threadIdx.x & 31;
+    const size_t gw = (blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x) >> 5;
+    const size_t nw = (static_cast<size_t>(gridDim.x) * blockDim.x) >> 5;
+    unsigned long long cand = 0;
+    for (size_t i = gw; i < n; i += nw) {
+        const V3 p{q[3 * i], q[3 * i + 1], q[3 * i + 2]};
+        const NNResult r = nn_search_warp(m, p, lane);
+        if (lane == 0) {
+            out_p[3 * i] = r.p.x;
+            out_p[3 * i + 1] = r.p.y;
+            out_p[3 * i + 2] = r.p.z;
+            out_d[i] = r.d;
+        }
+        if (COUNT) cand += r.candidates;
+    }
+    if (COUNT && lane == 0 && cand) atomicAdd(cand_total, cand);
+}
+
+// export of live voxels (checkpoint / Pointcloud / tests): ordered two-pass compaction by slot
+struct ExportParams {
+    MapView m;
+    Scratch sc;
+    int4 *vox_out;    // {x,y,z,count}
+    double *pts_out;  // concatenated per-voxel points, slot order
+    int *totals;      // [2] voxels, points
+};
+__global__ void __launch_bounds__(BLOCK, 1) k_map_export(const ExportParams P) {
+    __shared__ Shared sh;
+    __shared__ int s_scan[BLOCK];
+    Grid g;
+    g.init(P.sc.bar);
+    long long lo, hi;
+    chunk_of(static_cast<long long>(P.m.mask) + 1, &lo, &hi);
+    int nv = 0, np = 0;
+    for (long long i = lo + threadIdx.x; i < hi; i += BLOCK) {
+        const int w = P.m.slots[i].w;
+        if (w >= 0) {
+            ++nv;
+            np += w;
+        }
+    }
+    const int bnv = block_sum(nv, sh.warp_i);
+    const int bnp = block_sum(np, sh.warp_i);
+    if (threadIdx.x == 0) {
+        P.sc.blk_i[blockIdx.x] = bnv;
+        P.sc.blk_i[gridDim.x + blockIdx.x] = bnp;
+    }
+    g.sync();
+    int voff, vtot, poff, ptot;
+    grid_offsets(P.sc.blk_i, &voff, &vtot, sh.two);
+    grid_offsets(P.sc.blk_i + gridDim.x, &poff, &ptot, sh.two);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        P.totals[0] = vtot;
+        P.totals[1] = ptot;
+    }
+    if (P.vox_out == nullptr) return;  // count-only call
+    const size_t cap3 = static_cast<size_t>(P.m.cap) * 3;
+    for (long long base = lo; base < hi; base += BLOCK) {
+        const long long i = base + threadIdx.x;
+        int4 e = make_int4(0, 0, 0, -1);
+        if (i < hi) e = P.m.slots[i];
+        const int live = e.w >= 0 ? 1 : 0;
+        int tile_v;
+        const int vrank = block_rank(live, &tile_v, sh.warp_i);
+        // exclusive scan of point counts over the tile
+        __syncthreads();
+        s_scan[threadIdx.x] = live ? e.w : 0;
+        __syncthreads();
+        for (int o = 1; o < BLOCK; o <<= 1) {
+            const int v = threadIdx.x >= o ? s_scan[threadIdx.x - o] : 0;
+            __syncthreads();
+            s_scan[threadIdx.x] += v;
+            __syncthreads();
+        }
+        const int incl = s_scan[threadIdx.x];
+        const int tile_p = s_scan[BLOCK - 1];
+        if (live) {
+            P.vox_out[voff + vrank] = e;
+            const double *a = P.m.points + static_cast<size_t>(i) * cap3;
+            double *b = P.pts_out + static_cast<size_t>(poff + incl - e.w) * 3;
+            for (int k = 0; k < e.w * 3; ++k) b[k] = a[k];
+        }
+        voff += tile_v;
+        poff += tile_p;
+        __syncthreads();
+    }
+}
+
+}  // namespace kb

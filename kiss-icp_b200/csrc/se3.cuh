@@ -1,0 +1,371 @@
+// SE(3)/SO(3) arithmetic for the device path (and the host side of the C-ABI).
+//
+// The reference does this arithmetic through Sophus 1.24.6 and Eigen 3.4.0 (not vendored in
+// the reference tree). The formulas below follow the published algorithms of those versions
+// at the call sites of the hot path:
+//   SE3::exp / log            cpp/kiss_icp/core/Registration.cpp:157, Preprocessing.cpp:68,78
+//   SE3 * point / SE3 * SE3   Registration.cpp:57,161,166; VoxelHashMap.cpp:92; KissICP.cpp:47,57,62
+//   Matrix6d::ldlt().solve    Registration.cpp:156
+//   AngleAxisd(R).angle()     Threshold.cpp:40
+// Everything is FP64 like the reference. The file is compiled with -fmad=false so that
+// products and sums round exactly like the x86-64 reference build (no FMA contraction).
+#pragma once
+
+#include <cfloat>
+#include <cmath>
+
+#define KB_HD __host__ __device__ __forceinline__
+
+namespace kb {
+
+struct V3 {
+    double x, y, z;
+};
+KB_HD V3 operator+(const V3 &a, const V3 &b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
+KB_HD V3 operator-(const V3 &a, const V3 &b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+KB_HD V3 operator*(double s, const V3 &a) { return {s * a.x, s * a.y, s * a.z}; }
+KB_HD V3 cross(const V3 &a, const V3 &b) {
+    return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
+}
+KB_HD double sqnorm(const V3 &a) { return (a.x * a.x + a.y * a.y) + a.z * a.z; }
+KB_HD double norm(const V3 &a) { return sqrt(sqnorm(a)); }
+
+struct Q4 {
+    double x, y, z, w;
+};
+
+struct SE3 {
+    Q4 q;
+    V3 t;
+};
+KB_HD SE3 se3_identity() { return SE3{{0, 0, 0, 1}, {0, 0, 0}}; }
+
+constexpr double kEps = 1e-10;  // Sophus::Constants<double>::epsilon()
+
+KB_HD Q4 q_normalized(const Q4 &q) {
+    const double len = sqrt(((q.x * q.x + q.y * q.y) + q.z * q.z) + q.w * q.w);
+    return {q.x / len, q.y / len, q.z / len, q.w / len};
+}
+
+KB_HD Q4 q_mul(const Q4 &a, const Q4 &b) {
+    Q4 r;
+    r.w = a.w * b.w - a.x * b.x - a.y * b.y - a.z * b.z;
+    r.x = a.w * b.x + a.x * b.w + a.y * b.z - a.z * b.y;
+    r.y = a.w * b.y + a.y * b.w + a.z * b.x - a.x * b.z;
+    r.z = a.w * b.z + a.z * b.w + a.x * b.y - a.y * b.x;
+    return q_normalized(r);
+}
+
+// v + w*(2 q x v) + q x (2 q x v)
+KB_HD V3 q_rotate(const Q4 &q, const V3 &v) {
+    const V3 qv{q.x, q.y, q.z};
+    V3 uv = cross(qv, v);
+    uv = uv + uv;
+    return (v + q.w * uv) + cross(qv, uv);
+}
+
+KB_HD V3 se3_act(const SE3 &T, const V3 &p) { return q_rotate(T.q, p) + T.t; }
+
+KB_HD SE3 se3_mul(const SE3 &a, const SE3 &b) {
+    SE3 r;
+    r.q = q_mul(a.q, b.q);
+    r.t = a.t + q_rotate(a.q, b.t);
+    return r;
+}
+
+KB_HD SE3 se3_inverse(const SE3 &a) {
+    SE3 r;
+    r.q = q_normalized(Q4{-a.q.x, -a.q.y, -a.q.z, a.q.w});
+    r.t = q_rotate(r.q, V3{a.t.x * -1.0, a.t.y * -1.0, a.t.z * -1.0});
+    return r;
+}
+
+struct M3 {
+    double m[3][3];
+};
+
+KB_HD M3 q_to_matrix(const Q4 &q) {
+    const double tx = 2.0 * q.x, ty = 2.0 * q.y, tz = 2.0 * q.z;
+    const double twx = tx * q.w, twy = ty * q.w, twz = tz * q.w;
+    const double txx = tx * q.x, txy = ty * q.x, txz = tz * q.x;
+    const double tyy = ty * q.y, tyz = tz * q.y, tzz = tz * q.z;
+    M3 r;
+    r.m[0][0] = 1.0 - (tyy + tzz);
+    r.m[0][1] = txy - twz;
+    r.m[0][2] = txz + twy;
+    r.m[1][0] = txy + twz;
+    r.m[1][1] = 1.0 - (txx + tzz);
+    r.m[1][2] = tyz - twx;
+    r.m[2][0] = txz - twy;
+    r.m[2][1] = tyz + twx;
+    r.m[2][2] = 1.0 - (txx + tyy);
+    return r;
+}
+
+// quaternion from rotation matrix (Shoemake), as Eigen does for Quaterniond(Matrix3d)
+KB_HD Q4 q_from_matrix(const M3 &mat) {
+    double c[4];
+    double t = mat.m[0][0] + mat.m[1][1] + mat.m[2][2];
+    if (t > 0.0) {
+        t = sqrt(t + 1.0);
+        c[3] = 0.5 * t;
+        t = 0.5 / t;
+        c[0] = (mat.m[2][1] - mat.m[1][2]) * t;
+        c[1] = (mat.m[0][2] - mat.m[2][0]) * t;
+        c[2] = (mat.m[1][0] - mat.m[0][1]) * t;
+    } else {
+        int i = 0;
+        if (mat.m[1][1] > mat.m[0][0]) i = 1;
+        if (mat.m[2][2] > mat.m[i][i]) i = 2;
+        const int j = (i + 1) % 3;
+        const int k = (j + 1) % 3;
+        t = sqrt(mat.m[i][i] - mat.m[j][j] - mat.m[k][k] + 1.0);
+        c[i] = 0.5 * t;
+        t = 0.5 / t;
+        c[3] = (mat.m[k][j] - mat.m[j][k]) * t;
+        c[j] = (mat.m[j][i] + mat.m[i][j]) * t;
+        c[k] = (mat.m[k][i] + mat.m[i][k]) * t;
+    }
+    return {c[0], c[1], c[2], c[3]};
+}
+
+KB_HD Q4 so3_exp(const V3 &omega, double *theta_out) {
+    const double theta_sq = sqnorm(omega);
+    double imag_factor, real_factor, theta;
+    if (theta_sq < kEps * kEps) {
+        theta = 0.0;
+        const double theta_po4 = theta_sq * theta_sq;
+        imag_factor = 0.5 - (1.0 / 48.0) * theta_sq + (1.0 / 3840.0) * theta_po4;
+        real_factor = 1.0 - (1.0 / 8.0) * theta_sq + (1.0 / 384.0) * theta_po4;
+    } else {
+        theta = sqrt(theta_sq);
+        const double half_theta = 0.5 * theta;
+        imag_factor = sin(half_theta) / theta;
+        real_factor = cos(half_theta);
+    }
+    *theta_out = theta;
+    return {imag_factor * omega.x, imag_factor * omega.y, imag_factor * omega.z, real_factor};
+}
+
+KB_HD V3 so3_log(const Q4 &q, double *theta_out) {
+    const double squared_n = (q.x * q.x + q.y * q.y) + q.z * q.z;
+    const double w = q.w;
+    double two_atan_nbyw_by_n, theta;
+    if (squared_n < kEps * kEps) {
+        const double squared_w = w * w;
+        two_atan_nbyw_by_n = 2.0 / w - (2.0 / 3.0) * (squared_n) / (w * squared_w);
+        theta = 2.0 * squared_n / w;
+    } else {
+        const double n = sqrt(squared_n);
+        const double atan_nbyw = (w < 0.0) ? atan2(-n, -w) : atan2(n, w);
+        two_atan_nbyw_by_n = 2.0 * atan_nbyw / n;
+        theta = two_atan_nbyw_by_n * n;
+    }
+    *theta_out = theta;
+    return {two_atan_nbyw_by_n * q.x, two_atan_nbyw_by_n * q.y, two_atan_nbyw_by_n * q.z};
+}
+
+// y = (I + a*hat(w) + b*hat(w)^2) v, with the same matrix-entry arithmetic as the dense form
+KB_HD V3 apply_I_aW_bW2(const V3 &w, double a, double b, bool use_b, const V3 &v) {
+    // Omega = hat(w); Omega_sq = Omega*Omega (each entry (p0+p1)+p2 with exact zeros)
+    const double O[3][3] = {{0.0, -w.z, w.y}, {w.z, 0.0, -w.x}, {-w.y, w.x, 0.0}};
+    double O2[3][3];
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) O2[i][j] = (O[i][0] * O[0][j] + O[i][1] * O[1][j]) + O[i][2] * O[2][j];
+    double V[3][3];
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) {
+            const double id = (i == j) ? 1.0 : 0.0;
+            V[i][j] = use_b ? ((id + a * O[i][j]) + b * O2[i][j]) : (id + a * O[i][j]);
+        }
+    return {(V[0][0] * v.x + V[0][1] * v.y) + V[0][2] * v.z, (V[1][0] * v.x + V[1][1] * v.y) + V[1][2] * v.z,
+            (V[2][0] * v.x + V[2][1] * v.y) + V[2][2] * v.z};
+}
+
+// Sophus SE3::exp, tangent = (upsilon, omega)
+KB_HD SE3 se3_exp(const double a[6]) {
+    const V3 upsilon{a[0], a[1], a[2]};
+    const V3 omega{a[3], a[4], a[5]};
+    double theta;
+    SE3 r;
+    r.q = so3_exp(omega, &theta);
+    const double theta_sq = theta * theta;
+    if (theta_sq < kEps * kEps) {
+        r.t = apply_I_aW_bW2(omega, 0.5, 0.0, false, upsilon);
+    } else {
+        const double ca = (1.0 - cos(theta)) / theta_sq;
+        const double cb = (theta - sin(theta)) / (theta_sq * theta);
+        r.t = apply_I_aW_bW2(omega, ca, cb, true, upsilon);
+    }
+    return r;
+}
+
+// Sophus SE3::log
+KB_HD void se3_log(const SE3 &T, double out[6]) {
+    double theta;
+    const V3 omega = so3_log(T.q, &theta);
+    V3 u;
+    if (fabs(theta) < kEps) {
+        u = apply_I_aW_bW2(omega, -0.5, 1. / 12., true, T.t);
+    } else {
+        const double half_theta = 0.5 * theta;
+        const double c = (1.0 - theta * cos(half_theta) / (2.0 * sin(half_theta))) / (theta * theta);
+        u = apply_I_aW_bW2(omega, -0.5, c, true, T.t);
+    }
+    out[0] = u.x;
+    out[1] = u.y;
+    out[2] = u.z;
+    out[3] = omega.x;
+    out[4] = omega.y;
+    out[5] = omega.z;
+}
+
+// Eigen::AngleAxisd(Matrix3d).angle()
+KB_HD double angle_axis_angle(const M3 &R) {
+    const Q4 q = q_from_matrix(R);
+    double n = sqrt((q.x * q.x + q.y * q.y) + q.z * q.z);
+    if (n < DBL_EPSILON) {
+        const double m = fmax(fabs(q.x), fmax(fabs(q.y), fabs(q.z)));
+        if (m > 0.0) {
+            const double a = q.x / m, b = q.y / m, c = q.z / m;
+            n = m * sqrt((a * a + b * b) + c * c);
+        } else {
+            n = 0.0;
+        }
+    }
+    if (n != 0.0) return 2.0 * atan2(n, fabs(q.w));
+    return 0.0;
+}
+
+// row-major 4x4 -> SE3; false where Sophus would fail its orthogonality / last-row checks
+KB_HD bool se3_from_matrix(const double M[16], SE3 *out) {
+    M3 R;
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) R.m[i][j] = M[4 * i + j];
+    double fro = 0.0;
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) {
+            double s = 0.0;
+            for (int k = 0; k < 3; ++k) s += R.m[i][k] * R.m[j][k];
+            s -= (i == j) ? 1.0 : 0.0;
+            fro += s * s;
+        }
+    const double det = R.m[0][0] * (R.m[1][1] * R.m[2][2] - R.m[1][2] * R.m[2][1]) -
+                       R.m[0][1] * (R.m[1][0] * R.m[2][2] - R.m[1][2] * R.m[2][0]) +
+                       R.m[0][2] * (R.m[1][0] * R.m[2][1] - R.m[1][1] * R.m[2][0]);
+    if (!(sqrt(fro) < kEps) || !(det > 0.0)) return false;
+    if (!(fabs(M[12]) < kEps && fabs(M[13]) < kEps && fabs(M[14]) < kEps && fabs(M[15] - 1.0) < kEps)) return false;
+    out->q = q_from_matrix(R);
+    out->t = {M[3], M[7], M[11]};
+    return true;
+}
+
+KB_HD void se3_to_matrix(const SE3 &T, double M[16]) {
+    const M3 R = q_to_matrix(T.q);
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) M[4 * i + j] = R.m[i][j];
+    M[3] = T.t.x;
+    M[7] = T.t.y;
+    M[11] = T.t.z;
+    M[12] = M[13] = M[14] = 0.0;
+    M[15] = 1.0;
+}
+
+// LDL^T with diagonal pivoting of a symmetric 6x6 (lower triangle of A, row-major) and solve,
+// following Eigen 3.4 LDLT (Lower, unblocked): first-max pivot, |pivot| <= DBL_MIN -> 0 in D^+.
+KB_HD void ldlt6_solve(const double A_in[36], const double b[6], double x[6]) {
+    constexpr int N = 6;
+    double mat[N][N];
+    for (int i = 0; i < N; ++i)
+        for (int j = 0; j < N; ++j) mat[i][j] = A_in[N * i + j];
+    int tr[N];
+    double temp[N];
+    for (int k = 0; k < N; ++k) {
+        int big = k;
+        double best = fabs(mat[k][k]);
+        for (int i = k + 1; i < N; ++i) {
+            const double v = fabs(mat[i][i]);
+            if (v > best) {
+                best = v;
+                big = i;
+            }
+        }
+        tr[k] = big;
+        if (k != big) {
+            const int s = N - big - 1;
+            for (int j = 0; j < k; ++j) {
+                const double t = mat[k][j];
+                mat[k][j] = mat[big][j];
+                mat[big][j] = t;
+            }
+            for (int i = 0; i < s; ++i) {
+                const double t = mat[N - s + i][k];
+                mat[N - s + i][k] = mat[N - s + i][big];
+                mat[N - s + i][big] = t;
+            }
+            {
+                const double t = mat[k][k];
+                mat[k][k] = mat[big][big];
+                mat[big][big] = t;
+            }
+            for (int i = k + 1; i < big; ++i) {
+                const double t = mat[i][k];
+                mat[i][k] = mat[big][i];
+                mat[big][i] = t;
+            }
+        }
+        const int rs = N - k - 1;
+        if (k > 0) {
+            for (int j = 0; j < k; ++j) temp[j] = mat[j][j] * mat[k][j];
+            double acc = 0.0;
+            for (int j = 0; j < k; ++j) acc += mat[k][j] * temp[j];
+            mat[k][k] -= acc;
+            for (int i = 0; i < rs; ++i) {
+                double a2 = 0.0;
+                for (int j = 0; j < k; ++j) a2 += mat[k + 1 + i][j] * temp[j];
+                mat[k + 1 + i][k] -= a2;
+            }
+        }
+        const double akk = mat[k][k];
+        const bool valid = fabs(akk) > 0.0;
+        if (k == 0 && !valid) {
+            for (int j = 0; j < N; ++j) tr[j] = j;
+            break;
+        }
+        if (rs > 0 && valid)
+            for (int i = 0; i < rs; ++i) mat[k + 1 + i][k] /= akk;
+    }
+    double d[N];
+    for (int i = 0; i < N; ++i) d[i] = b[i];
+    for (int k = 0; k < N; ++k)
+        if (tr[k] != k) {
+            const double t = d[k];
+            d[k] = d[tr[k]];
+            d[tr[k]] = t;
+        }
+    for (int i = 0; i < N; ++i) {
+        double acc = d[i];
+        for (int j = 0; j < i; ++j) acc -= mat[i][j] * d[j];
+        d[i] = acc;
+    }
+    for (int i = 0; i < N; ++i) {
+        if (fabs(mat[i][i]) > DBL_MIN)
+            d[i] /= mat[i][i];
+        else
+            d[i] = 0.0;
+    }
+    for (int i = N - 1; i >= 0; --i) {
+        double acc = d[i];
+        for (int j = i + 1; j < N; ++j) acc -= mat[j][i] * d[j];
+        d[i] = acc;
+    }
+    for (int k = N - 1; k >= 0; --k)
+        if (tr[k] != k) {
+            const double t = d[k];
+            d[k] = d[tr[k]];
+            d[tr[k]] = t;
+        }
+    for (int i = 0; i < N; ++i) x[i] = d[i];
+}
+
+}  // namespace kb

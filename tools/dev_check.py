@@ -1,0 +1,97 @@
+"""Developer parity sweep (GPU box): every C-ABI entry point against the oracle."""
+import os, sys, time
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import kiss_icp_b200 as K
+from kiss_icp_b200 import synthetic
+from oracle import oracle as O
+
+rng = np.random.default_rng(0)
+def hdr(s): print("\n== " + s, flush=True)
+
+hdr("voxel_down_sample")
+for n, vs, scale in [(0, 1.0, 1), (1, 1.0, 1), (2, 0.5, 1), (1000, 0.5, 10), (65536, 0.5, 60), (20000, 1.5, 80), (5000, 0.3, 3)]:
+    pts = rng.normal(size=(n, 3)) * scale
+    if n > 10:
+        pts[:5] = np.round(pts[:5])  # exact multiples
+        pts[5:8] = pts[2:5]          # duplicates
+    a = K.voxel_down_sample(pts, vs); b = O.voxel_down_sample(pts, vs)
+    print(n, vs, "out", len(a), len(b), "exact-ordered-equal:", a.shape == b.shape and np.array_equal(a, b))
+
+lidar = synthetic.small_shape(seed=1, beams=32, cols=512)
+pts, _ = lidar.scan(0)
+a = K.voxel_down_sample(pts, 0.5); b = O.voxel_down_sample(pts, 0.5)
+print("scan", len(pts), "->", len(a), "equal", np.array_equal(a, b))
+
+hdr("preprocess")
+P = K.Preprocessor(100.0, 0.0, True, 0)
+ts = np.linspace(0, 1, len(pts))
+T = O.se3_exp([0.9, 0.05, 0.01, 0.002, -0.001, 0.03])
+a = P.preprocess(pts, np.empty(0), T); b = O.preprocess(pts, np.empty(0), T, 100.0, 0.0, True)
+print("no stamps: equal", np.array_equal(a, b), len(a))
+a = P.preprocess(pts, ts, T); b = O.preprocess(pts, ts, T, 100.0, 0.0, True)
+print("deskew: n", len(a), len(b), "max diff", np.abs(a - b).max() if len(a) == len(b) else None)
+P2 = K.Preprocessor(30.0, 5.0, False, 0)
+a = P2.preprocess(pts, ts, T); b = O.preprocess(pts, ts, T, 30.0, 5.0, False)
+print("crop 5..30: equal", np.array_equal(a, b), len(a))
+
+hdr("map add/remove/dump")
+gm = K.VoxelHashMap(1.0, 100.0, 20); om = O.VoxelHashMap(1.0, 100.0, 20)
+for k in range(4):
+    p, _ = lidar.scan(k)
+    Tk = np.linalg.inv(lidar.pose(0)) @ lidar.pose(k)
+    ds = O.voxel_down_sample(p, 0.5)
+    gm.update(ds, Tk); om.update(ds, Tk)
+def canon(vox, cnt, pts):
+    order = np.lexsort((vox[:, 2], vox[:, 1], vox[:, 0]))
+    starts = np.concatenate([[0], np.cumsum(cnt)])[:-1]
+    return vox[order], cnt[order], np.concatenate([pts[starts[i]:starts[i] + cnt[i]] for i in order]) if len(order) else pts
+gv, gc, gp = gm.dump(); ov, oc, op = canon(*om.dump())
+print("voxels", len(gv), len(ov), "points", len(gp), len(op), "equal:", np.array_equal(gv, ov), np.array_equal(gc, oc), np.array_equal(gp, op))
+gm.remove_far_away_points([30., 0, 0]); om.remove_far_away_points([30., 0, 0])
+gv, gc, gp = gm.dump(); ov, oc, op = canon(*om.dump())
+print("after remove: voxels", len(gv), len(ov), "equal:", np.array_equal(gv, ov), np.array_equal(gp, op))
+raw, _ = lidar.scan(5)
+gm.add_points(raw); om.add_points(raw)   # many points per voxel
+gv, gc, gp = gm.dump(); ov, oc, op = canon(*om.dump())
+print("after add_points(raw): voxels", len(gv), len(ov), "equal:", np.array_equal(gv, ov), np.array_equal(gc, oc), np.array_equal(gp, op))
+
+hdr("closest neighbours")
+q = O.se3_act(np.linalg.inv(lidar.pose(0)) @ lidar.pose(3), lidar.scan(3)[0]) + rng.normal(size=(len(lidar.scan(3)[0]), 3)) * 0.2
+ap, ad = gm.closest_neighbors(q); bp, bd = om.closest_neighbors(q)
+print("n", len(q), "points equal", np.array_equal(ap, bp), "dist equal", np.array_equal(ad, bd), "misses", int((bd > 1e300).sum()))
+
+hdr("build_system / align")
+reg = K.Registration(500, 1e-4, 0)
+src = O.voxel_down_sample(O.voxel_down_sample(lidar.scan(4)[0], 0.5), 1.5)
+T4 = np.linalg.inv(lidar.pose(0)) @ lidar.pose(4)
+srcm = O.se3_act(T4, src)
+A, b_, n1 = reg.build_system(srcm, gm, 3.0, 1.0); A2, b2, n2 = O.build_system(om, srcm, 3.0, 1.0, nthreads=1)
+print("ncorr", n1, n2, "JTJ rel", np.abs(A - A2).max() / np.abs(A2).max(), "JTr rel", np.abs(b_ - b2).max() / np.abs(b2).max())
+guess = T4 @ O.se3_exp([0.3, -0.2, 0.05, 0.01, -0.01, 0.02])
+Pg = reg.align_points_to_map(src, gm, guess, 3.0, 1.0); Po, ito = O.align_points_to_map(om, src, guess, 3.0, 1.0)
+print("align iters", reg.last_iterations, ito, "pose diff", np.abs(Pg - Po).max(), "vs truth", np.abs(Pg - T4).max())
+
+hdr("pipeline (fused) stream")
+for stamps in ("none", "column"):
+    L = synthetic.small_shape(seed=5, beams=32, cols=512, stamps=stamps)
+    g = K.KissICP(K.load_config()); o = O.KissICP()
+    worst = 0
+    for k in range(12):
+        p, t = L.scan(k)
+        g.register_frame(p, t, return_clouds=False); o.register_frame(p, t, want_clouds=False)
+        d = np.abs(g.last_pose - o.pose).max(); worst = max(worst, d)
+    print(stamps, "max |pose diff| over 12 scans", worst, "iters", g.last_iterations, o.last_iterations, "map", g.local_map.num_points(), o.local_map.num_points())
+
+hdr("timing: KITTI-shape fused pipeline")
+L = synthetic.kitti_shape(seed=0, device="cuda")
+g = K.KissICP(K.load_config()); o = O.KissICP()
+tg = to = 0; worst = 0
+for k in range(30):
+    p, t = L.scan(k)
+    t0 = time.perf_counter(); g.register_frame(p, t, return_clouds=False); t1 = time.perf_counter()
+    o.register_frame(p, t, want_clouds=False); t2 = time.perf_counter()
+    if k >= 5: tg += t1 - t0; to += t2 - t1
+    worst = max(worst, np.abs(g.last_pose - o.pose).max())
+print("gpu ms/scan", tg / 25 * 1e3, "cpu ms/scan", to / 25 * 1e3, "threads", O.num_threads(), "max pose diff", worst, "iters", g.last_iterations)
