@@ -191,6 +191,33 @@ kb_map *kb_pipeline_voxel_map(kb_pipeline *p);
 /* diagnostics: adaptive threshold sigma used by / ICP iterations of the last RegisterFrame */
 int kb_pipeline_last_sigma(const kb_pipeline *p, double *out);
 int kb_pipeline_last_iterations(const kb_pipeline *p, int *out);
+/* profiling aids (no reference counterpart): raw %globaltimer stamps [ns, relative to stamp 0]
+ * of the second ICP iteration of the last frame; cost of one grid barrier */
+int kb_pipeline_debug_stamps(const kb_pipeline *p, double *ns, int n);
+int kb_debug_barrier_ns(int iters, double *ns_per_barrier);
+/* work done by the ICP loop of the last RegisterFrame: GetClosestNeighbor calls (iterations x
+ * source points) and map points examined — the inputs of the algorithmic-bytes formula */
+int kb_pipeline_last_icp_work(const kb_pipeline *p, double *queries, double *candidates);
+/* adaptive_threshold_.ComputeThreshold() of the pipeline's own estimator (Threshold.hpp:38):
+ * the sigma the NEXT RegisterFrame will use */
+int kb_pipeline_threshold(const kb_pipeline *p, double *out_sigma);
+/* device-side duration [us] of the phases of the last RegisterFrame, from %globaltimer stamps
+ * inside the kernel: preprocess, downsample(0.5v), downsample(1.5v), ICP, map update, epilogue */
+int kb_pipeline_last_profile(const kb_pipeline *p, double *us, int n);
+/* per-frame statistics, recorded on the host after every RegisterFrame when enabled (so a
+ * benchmark can read them AFTER its timed region): kb_pipeline_set_history(p, capacity) starts
+ * a fresh log of up to `capacity` frames */
+typedef struct kb_frame_stats {
+    double pose[16];
+    double phase_us[6];   /* preprocess, downsample 0.5v, downsample 1.5v, ICP, map update, epilogue */
+    double icp_queries;   /* GetClosestNeighbor calls */
+    double icp_candidates; /* map points examined */
+    int iterations;
+    int n_points_in, n_preprocessed, n_downsampled, n_source;
+    int map_points, map_voxels, pad;
+} kb_frame_stats;
+int kb_pipeline_set_history(kb_pipeline *p, size_t capacity);
+int kb_pipeline_get_history(const kb_pipeline *p, kb_frame_stats *out, size_t capacity, size_t *n_out);
 /* kernels launched by this pipeline so far (bench "gpu_launches") */
 int kb_pipeline_launch_count(const kb_pipeline *p, unsigned long long *out);
 

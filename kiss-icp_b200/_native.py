@@ -73,6 +73,13 @@ class Config(C.Structure):
                 ("convergence_criterion", dbl), ("max_num_threads", i32), ("deskew", i32)]
 
 
+class FrameStats(C.Structure):
+    """kb_frame_stats"""
+    _fields_ = [("pose", dbl * 16), ("phase_us", dbl * 6), ("icp_queries", dbl), ("icp_candidates", dbl),
+                ("iterations", i32), ("n_points_in", i32), ("n_preprocessed", i32), ("n_downsampled", i32),
+                ("n_source", i32), ("map_points", i32), ("map_voxels", i32), ("pad", i32)]
+
+
 # every exported symbol of include/kiss_icp_b200.h: name -> (restype, argtypes)
 SIGNATURES = {
     "kb_last_error": (C.c_char_p, []),
@@ -125,7 +132,14 @@ SIGNATURES = {
     "kb_pipeline_set_delta": (i32, [vp, vp]),
     "kb_pipeline_voxel_map": (vp, [vp]),
     "kb_pipeline_last_sigma": (i32, [vp, C.POINTER(dbl)]),
+    "kb_pipeline_debug_stamps": (i32, [vp, vp, i32]),
+    "kb_debug_barrier_ns": (i32, [i32, C.POINTER(dbl)]),
+    "kb_pipeline_last_icp_work": (i32, [vp, C.POINTER(dbl), C.POINTER(dbl)]),
+    "kb_pipeline_threshold": (i32, [vp, C.POINTER(dbl)]),
     "kb_pipeline_last_iterations": (i32, [vp, C.POINTER(i32)]),
+    "kb_pipeline_last_profile": (i32, [vp, vp, i32]),
+    "kb_pipeline_set_history": (i32, [vp, sz]),
+    "kb_pipeline_get_history": (i32, [vp, vp, sz, C.POINTER(sz)]),
     "kb_pipeline_launch_count": (i32, [vp, C.POINTER(C.c_ulonglong)]),
 }
 

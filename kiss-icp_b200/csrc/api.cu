@@ -86,7 +86,7 @@ struct Exec {
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     int grid = 0;
-    Scratch sc{nullptr, nullptr, nullptr};
+    Scratch sc{nullptr, nullptr, nullptr, nullptr};
     unsigned long long launches = 0;
 
     int init() {
@@ -105,14 +105,17 @@ struct Exec {
         if (!coop) return fail(KB_ERR_CUDA, "device does not support cooperative launch");
         grid = tl_grid_blocks > 0 ? std::min(tl_grid_blocks, sms) : sms;
         CK(cudaMalloc(&sc.bar, 256));
-        CK(cudaMalloc(&sc.blk_d, sizeof(double) * 2 * grid * (NACC + 1)));
+        CK(cudaMalloc(&sc.blk_d, sizeof(double) * 2 * grid * NPART));
         CK(cudaMalloc(&sc.blk_i, sizeof(int) * 2 * grid));
+        CK(cudaMalloc(&sc.dbg, sizeof(unsigned long long) * 64));
+        CK(cudaMemsetAsync(sc.dbg, 0, sizeof(unsigned long long) * 64, stream));
         return KB_OK;
     }
     ~Exec() {
         if (sc.bar) cudaFree(sc.bar);
         if (sc.blk_d) cudaFree(sc.blk_d);
         if (sc.blk_i) cudaFree(sc.blk_i);
+        if (sc.dbg) cudaFree(sc.dbg);
         if (own_stream && stream) cudaStreamDestroy(stream);
     }
     template <class P>
@@ -120,6 +123,15 @@ struct Exec {
         CK(cudaSetDevice(device));
         CK(cudaMemsetAsync(sc.bar, 0, sizeof(unsigned), stream));
         void *args[] = {const_cast<P *>(&p)};
+        CK(cudaLaunchCooperativeKernel(reinterpret_cast<const void *>(kern), dim3(grid), dim3(BLOCK), args, 0, stream));
+        ++launches;
+        return KB_OK;
+    }
+    template <class A, class B>
+    int coop(void (*kern)(A, B), const A &a, const B &b) {
+        CK(cudaSetDevice(device));
+        CK(cudaMemsetAsync(sc.bar, 0, sizeof(unsigned), stream));
+        void *args[] = {const_cast<A *>(&a), const_cast<B *>(&b)};
         CK(cudaLaunchCooperativeKernel(reinterpret_cast<const void *>(kern), dim3(grid), dim3(BLOCK), args, 0, stream));
         ++launches;
         return KB_OK;
@@ -140,8 +152,9 @@ int make_exec(std::shared_ptr<Exec> *out) {
 // per-call workspace sized by the largest cloud seen
 struct Work {
     DBuf<double> in, ts, tmp, pre, ds1, src, work, tp;
-    DBuf<int> next, touched, ds_prefix, cnt;
+    DBuf<int> next, touched, ds_prefix, ds_order, cnt;
     DBuf<int4> ds_slots;
+    DBuf<int2> ds_sim;
     int ensure(size_t n) {
         n = std::max<size_t>(n, 1);
         RET(in.ensure(3 * n));
@@ -157,11 +170,14 @@ struct Work {
         const size_t b = pow2_at_least(2 * n);
         RET(ds_slots.ensure(b));
         RET(ds_prefix.ensure(b));
+        RET(ds_order.ensure(b));
+        RET(ds_sim.ensure(b));
         RET(cnt.ensure(8));
         return KB_OK;
     }
+    DsScratch ds_view() { return DsScratch{ds_slots.p, ds_prefix.p, ds_order.p, ds_sim.p}; }
     Workspace view() {
-        return Workspace{tmp.p, pre.p, ds1.p, src.p, work.p, tp.p, next.p, touched.p, ds_slots.p, ds_prefix.p, cnt.p};
+        return Workspace{tmp.p, pre.p, ds1.p, src.p, work.p, tp.p, next.p, touched.p, ds_view(), cnt.p};
     }
 };
 
@@ -347,6 +363,8 @@ struct kb_pipeline {
     FrameResult *h_res = nullptr;  // pinned
     FrameResult last{};
     bool has_last = false;
+    std::vector<kb_frame_stats> history;
+    size_t history_cap = 0;
     ~kb_pipeline() {
         if (ex) cudaSetDevice(ex->device);
         delete map;
@@ -379,8 +397,7 @@ int run_downsample(Exec &ex, Work &ws, const double *d_in, size_t n, double v1, 
     P.in = d_in;
     P.n = static_cast<int>(n);
     P.voxel_size = v1;
-    P.ds_slots = ws.ds_slots.p;
-    P.ds_prefix = ws.ds_prefix.p;
+    P.ds = ws.ds_view();
     P.out = d_out;
     P.out_n = d_n1;
     P.voxel_size2 = v2;
@@ -913,6 +930,23 @@ static int pipeline_run(kb_pipeline *p, const double *d_xyz, size_t n, const dou
     p->map->h_counters[C_TOMB] = p->last.map_tomb;
     p->map->h_counters[C_POINTS] = p->last.map_points;
     p->map->h_counters[C_STATUS] = p->last.map_status;
+    if (p->history.size() < p->history_cap) {
+        kb_frame_stats st;
+        std::memcpy(st.pose, p->last.pose, sizeof(st.pose));
+        for (int i = 0; i < 6; ++i)
+            st.phase_us[i] = (static_cast<double>(p->last.t_ns[i + 1]) - static_cast<double>(p->last.t_ns[i])) * 1e-3;
+        st.icp_queries = p->last.icp_queries;
+        st.icp_candidates = p->last.icp_candidates;
+        st.iterations = p->last.iterations;
+        st.n_points_in = static_cast<int>(n);
+        st.n_preprocessed = p->last.n_pre;
+        st.n_downsampled = p->last.n_ds;
+        st.n_source = p->last.n_src;
+        st.map_points = p->last.map_points;
+        st.map_voxels = p->last.map_live;
+        st.pad = 0;
+        p->history.push_back(st);
+    }
     if (p->last.map_status & ST_TABLE_FULL) return fail(KB_ERR_CUDA, "voxel table overflow (internal capacity bug)");
     return KB_OK;
 }
@@ -1026,9 +1060,60 @@ int kb_pipeline_last_sigma(const kb_pipeline *p, double *out) {
     *out = p->last.sigma;
     return KB_OK;
 }
+int kb_pipeline_debug_stamps(const kb_pipeline *p, double *ns, int n) {
+    if (!p || !ns) return fail(KB_ERR_INVALID_ARG, "NULL argument");
+    unsigned long long t[64];
+    CK(cudaSetDevice(p->ex->device));
+    CK(cudaMemcpyAsync(t, p->ex->sc.dbg, sizeof(t), cudaMemcpyDeviceToHost, p->ex->stream));
+    RET(p->ex->sync());
+    for (int i = 0; i < n && i < 64; ++i) ns[i] = static_cast<double>(t[i] - t[0]);
+    return KB_OK;
+}
+int kb_debug_barrier_ns(int iters, double *ns_per_barrier) {
+    if (!ns_per_barrier || iters < 1) return fail(KB_ERR_INVALID_ARG, "bad argument");
+    DefaultCtx *c;
+    RET(default_ctx(&c));
+    RET(c->ex->coop(k_barrier_bench, c->ex->sc, iters));
+    unsigned long long t[2];
+    CK(cudaMemcpyAsync(t, c->ex->sc.dbg + 8, sizeof(t), cudaMemcpyDeviceToHost, c->ex->stream));
+    RET(c->ex->sync());
+    *ns_per_barrier = static_cast<double>(t[1] - t[0]) / iters;
+    return KB_OK;
+}
+int kb_pipeline_last_icp_work(const kb_pipeline *p, double *queries, double *candidates) {
+    if (!p) return fail(KB_ERR_INVALID_ARG, "p == NULL");
+    if (queries) *queries = p->last.icp_queries;
+    if (candidates) *candidates = p->last.icp_candidates;
+    return KB_OK;
+}
+int kb_pipeline_threshold(const kb_pipeline *p, double *out_sigma) {
+    if (!p || !out_sigma) return fail(KB_ERR_INVALID_ARG, "NULL argument");
+    *out_sigma = std::sqrt(p->last.model_sse / p->last.num_samples);  // ComputeThreshold(), Threshold.hpp:38
+    return KB_OK;
+}
 int kb_pipeline_last_iterations(const kb_pipeline *p, int *out) {
     if (!p || !out) return fail(KB_ERR_INVALID_ARG, "NULL argument");
     *out = p->last.iterations;
+    return KB_OK;
+}
+int kb_pipeline_last_profile(const kb_pipeline *p, double *us, int n) {
+    if (!p || !us) return fail(KB_ERR_INVALID_ARG, "NULL argument");
+    for (int i = 0; i < n && i < 6; ++i) us[i] = (static_cast<double>(p->last.t_ns[i + 1]) - static_cast<double>(p->last.t_ns[i])) * 1e-3;
+    return KB_OK;
+}
+int kb_pipeline_set_history(kb_pipeline *p, size_t capacity) {
+    if (!p) return fail(KB_ERR_INVALID_ARG, "p == NULL");
+    p->history.clear();
+    p->history.reserve(capacity);
+    p->history_cap = capacity;
+    return KB_OK;
+}
+int kb_pipeline_get_history(const kb_pipeline *p, kb_frame_stats *out, size_t capacity, size_t *n_out) {
+    if (!p || !n_out) return fail(KB_ERR_INVALID_ARG, "NULL argument");
+    *n_out = p->history.size();
+    if (!out) return KB_OK;
+    if (capacity < p->history.size()) return fail(KB_ERR_CAPACITY, "history buffer too small");
+    std::memcpy(out, p->history.data(), p->history.size() * sizeof(kb_frame_stats));
     return KB_OK;
 }
 int kb_pipeline_launch_count(const kb_pipeline *p, unsigned long long *out) {

@@ -32,6 +32,7 @@ constexpr unsigned FULL = 0xffffffffu;
 constexpr int BLOCK = 512;  // threads per CTA of every cooperative kernel
 constexpr int NWARPS = BLOCK / 32;
 constexpr int NACC = 16;  // unique accumulators of the 6x6 normal equations (see icp_accumulate)
+constexpr int NPART = NACC + 2;  // per-CTA partial: accumulators, #correspondences, #candidate points
 
 enum Counter { C_LIVE = 0, C_TOMB = 1, C_POINTS = 2, C_STATUS = 3, C_TOUCHED = 4, C_NCOUNTERS = 8 };
 enum StatusBit { ST_TABLE_FULL = 1 };
@@ -51,8 +52,9 @@ struct MapView {
 // cross-CTA scratch, sized by the grid
 struct Scratch {
     unsigned *bar;  // grid barrier counter (zeroed before each launch)
-    double *blk_d;  // [grid][NACC] x2 (ping-pong) doubles
+    double *blk_d;  // [2][grid][NPART] doubles (ping-pong by ICP iteration parity)
     int *blk_i;     // [grid] ints
+    unsigned long long *dbg;  // [64] %globaltimer stamps of CTA 0 (profiling aid)
 };
 
 // ------------------------------------------------------------------------------------------
@@ -63,6 +65,14 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p) {
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define KB_DBG(sc, i) \
+    if (blockIdx.x == 0 && threadIdx.x == 0) (sc).dbg[i] = globaltimer_ns()
 
 struct Grid {
     unsigned *bar;
@@ -229,6 +239,7 @@ struct Shared {
     int warp_i[NWARPS + 1];
     int two[2];
     double warp_d[NWARPS][NACC];
+    double warp_c[NWARPS];
     double sys[NACC];
     double omega[6];
     double mm[2];
@@ -236,6 +247,8 @@ struct Shared {
     SE3 t_icp;
     SE3 result;  // op_icp output (valid in every CTA)
     int iters;   // op_icp output
+    double cand;     // candidate points examined by the last icp_pass (all CTAs)
+    double cand_total, query_total;  // summed over the iterations of op_icp
     int flag;
 };
 
@@ -338,11 +351,15 @@ __device__ void op_preprocess(Grid &g, const Scratch &sc, Shared &sh, const doub
 //   keeps the first point (input order) of every voxel and emits them in the ITERATION ORDER
 //   of the reference's tsl::robin_map: bucket_count = pow2 >= 2n (reserve(n), max load 0.5,
 //   never rehashes while filling), home = std::hash<Voxel> & (B-1), robin-hood linear probing.
-//   The final robin-hood layout is canonical: inside every maximal occupied run the entries
-//   are ordered by (home, insertion index) and the set of occupied buckets equals that of
-//   plain linear probing. So: (a) fill a scratch table of B slots by linear probing from the
-//   reference's home bucket with CAS + atomicMin(first index); (b) prefix-count occupied
-//   buckets; (c) every entry ranks itself inside its run and lands at prefix[canonical bucket].
+//   Facts used: (1) the SET of occupied buckets of robin-hood hashing equals that of plain
+//   linear probing and does not depend on insertion order; (2) two entries in different
+//   maximal occupied runs of the final table never interacted (the empty bucket between them
+//   was always empty); (3) inside a run the layout DOES depend on history (a displaced entry
+//   leapfrogs residents of equal probe distance), so each run is replayed exactly.
+//   Phases: (a) fill a scratch table by linear probing from the reference's home bucket with a
+//   128-bit CAS + atomicMin(first index); (b) prefix-count occupied buckets; (c1) every entry
+//   ranks itself by first index inside its run; (c2) one thread per run replays the robin-hood
+//   inserts of that run in index order and emits the points at prefix[bucket].
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned robin_bucket_count(int n) {
     if (n <= 0) return 0;
@@ -354,16 +371,27 @@ __device__ __forceinline__ unsigned robin_bucket_count(int n) {
     return static_cast<unsigned>(p);
 }
 
+struct DsScratch {
+    int4 *slots;   // [B] {voxel, first index}
+    int *prefix;   // [B] occupied buckets before this one
+    int *order;    // [B] run-local insertion order: order[s + k] = bucket of the k-th inserted entry
+    int2 *sim;     // [B] replayed robin-hood layout {first index (-1 empty), home offset in run}
+};
+
 __device__ void op_downsample(Grid &g, const Scratch &sc, Shared &sh, const double *in, int n, double voxel_size,
-                              int4 *ds_slots, int *ds_prefix, double *out, int *out_n) {
+                              const DsScratch &ds, double *out, int *out_n) {
     const unsigned B = robin_bucket_count(n);
     if (B == 0) {
         if (blockIdx.x == 0 && threadIdx.x == 0) *out_n = 0;
         return;  // uniform across the grid
     }
     const unsigned mask = B - 1;
+    int4 *ds_slots = ds.slots;
     const int4 empty = make_int4(-1, -1, -1, KB_EMPTY);
-    for (unsigned i = blockIdx.x * BLOCK + threadIdx.x; i < B; i += gridDim.x * BLOCK) ds_slots[i] = empty;
+    for (unsigned i = blockIdx.x * BLOCK + threadIdx.x; i < B; i += gridDim.x * BLOCK) {
+        ds_slots[i] = empty;
+        ds.sim[i] = make_int2(-1, 0);
+    }
     g.sync();
     // (a) dedupe: first input index per voxel
     for (int i = blockIdx.x * BLOCK + threadIdx.x; i < n; i += gridDim.x * BLOCK) {
@@ -398,29 +426,59 @@ __device__ void op_downsample(Grid &g, const Scratch &sc, Shared &sh, const doub
         const int occ = (i < hi && ds_slots[i].w != KB_EMPTY) ? 1 : 0;
         int tile_total;
         const int rank = block_rank(occ, &tile_total, sh.warp_i);
-        if (i < hi) ds_prefix[i] = run + rank;
+        if (i < hi) ds.prefix[i] = run + rank;
         run += tile_total;
     }
-    g.sync();
-    // (c) canonical robin-hood position of every entry -> output index
+    // (c1) insertion order inside every run (no barrier needed between (b) and (c1): disjoint data)
     for (unsigned h = blockIdx.x * BLOCK + threadIdx.x; h < B; h += gridDim.x * BLOCK) {
-        const int4 e = ds_slots[h];
-        if (e.w == KB_EMPTY) continue;
+        const int my = ds_slots[h].w;
+        if (my == KB_EMPTY) continue;
         unsigned s = h;  // start of the occupied run containing h
         while (ds_slots[(s - 1) & mask].w != KB_EMPTY) s = (s - 1) & mask;
-        const unsigned my_home = ((ref_hash(e.x, e.y, e.z) & mask) - s) & mask;  // offset inside the run
         unsigned rank = 0;
         for (unsigned p = s;; p = (p + 1) & mask) {
-            const int4 f = ds_slots[p];
-            if (f.w == KB_EMPTY) break;
-            const unsigned f_home = ((ref_hash(f.x, f.y, f.z) & mask) - s) & mask;
-            rank += (f_home < my_home || (f_home == my_home && f.w < e.w)) ? 1u : 0u;
+            const int w = ds_slots[p].w;
+            if (w == KB_EMPTY) break;
+            rank += (w < my) ? 1u : 0u;
         }
-        const long long o = ds_prefix[(s + rank) & mask];
-        const long long src = e.w;
-        out[3 * o] = in[3 * src];
-        out[3 * o + 1] = in[3 * src + 1];
-        out[3 * o + 2] = in[3 * src + 2];
+        ds.order[(s + rank) & mask] = static_cast<int>(h);
+    }
+    g.sync();
+    // (c2) replay tsl::robin_map::insert for every run, in first-index order, then emit
+    for (unsigned s = blockIdx.x * BLOCK + threadIdx.x; s < B; s += gridDim.x * BLOCK) {
+        if (ds_slots[s].w == KB_EMPTY || ds_slots[(s - 1) & mask].w != KB_EMPTY) continue;  // not a run start
+        unsigned L = 0;
+        for (; ds_slots[(s + L) & mask].w != KB_EMPTY; ++L) {
+            const int4 e = ds_slots[ds.order[(s + L) & mask]];
+            int ci = e.w;                                                               // entry being carried
+            int ch = static_cast<int>(((ref_hash(e.x, e.y, e.z) & mask) - s) & mask);   // its home, run-relative
+            int r = ch;
+            // insert_impl search: stop at the first bucket whose resident is "richer"
+            while (true) {
+                const int2 t = ds.sim[(s + r) & mask];
+                if (t.x < 0 || (r - ch) > (r - t.y)) break;
+                ++r;
+            }
+            // insert_value: robin-hood swap chain until an empty bucket
+            while (true) {
+                const int2 t = ds.sim[(s + r) & mask];
+                if (t.x < 0) break;
+                if ((r - ch) > (r - t.y)) {
+                    ds.sim[(s + r) & mask] = make_int2(ci, ch);
+                    ci = t.x;
+                    ch = t.y;
+                }
+                ++r;
+            }
+            ds.sim[(s + r) & mask] = make_int2(ci, ch);
+        }
+        for (unsigned r = 0; r < L; ++r) {
+            const long long src = ds.sim[(s + r) & mask].x;
+            const long long o = ds.prefix[(s + r) & mask];
+            out[3 * o] = in[3 * src];
+            out[3 * o + 1] = in[3 * src + 1];
+            out[3 * o + 2] = in[3 * src + 2];
+        }
     }
 }
 
@@ -551,13 +609,16 @@ __device__ __forceinline__ void icp_expand(const double a[NACC], double JTJ[36],
 // point is written back to `work`. Result: sh.sys[NACC] identical in every CTA (fixed
 // reduction order: query-strided per warp -> warps in order -> CTAs in order).
 __device__ void icp_pass(Grid &g, const Scratch &sc, Shared &sh, const MapView &m, const double *src, double *work,
-                         int n, const SE3 &pending, double max_dist, double kscale, int parity, int *n_corr) {
+                         int n, const SE3 &pending, double max_dist, double kscale, int parity, int *n_corr,
+                         bool dbg_on = false) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (dbg_on) KB_DBG(sc, 0);
     const int gwarp = blockIdx.x * NWARPS + warp, nwarps = gridDim.x * NWARPS;
     double acc[NACC];
 #pragma unroll
     for (int i = 0; i < NACC; ++i) acc[i] = 0.0;
     int corr = 0;
+    double cand = 0.0;
     for (int qi = gwarp; qi < n; qi += nwarps) {
         V3 p{src[3 * qi], src[3 * qi + 1], src[3 * qi + 2]};
         p = se3_act(pending, p);
@@ -567,19 +628,23 @@ __device__ void icp_pass(Grid &g, const Scratch &sc, Shared &sh, const MapView &
             work[3 * qi + 2] = p.z;
         }
         const NNResult r = nn_search_warp(m, p, lane);
+        cand += r.candidates;
         if (r.d < max_dist) {
             icp_accumulate(acc, p, r.p, kscale);
             ++corr;
         }
     }
+    if (dbg_on && warp == 0) KB_DBG(sc, 1);
     __syncthreads();
+    if (dbg_on) KB_DBG(sc, 2);
     if (lane == 0) {
 #pragma unroll
         for (int i = 0; i < NACC; ++i) sh.warp_d[warp][i] = acc[i];
         sh.warp_i[warp] = corr;
+        sh.warp_c[warp] = cand;
     }
     __syncthreads();
-    double *mine = sc.blk_d + (static_cast<size_t>(parity) * gridDim.x + blockIdx.x) * (NACC + 1);
+    double *mine = sc.blk_d + (static_cast<size_t>(parity) * gridDim.x + blockIdx.x) * NPART;
     if (threadIdx.x < NACC) {
         double s = 0.0;
         for (int w = 0; w < NWARPS; ++w) s += sh.warp_d[w][threadIdx.x];
@@ -588,25 +653,34 @@ __device__ void icp_pass(Grid &g, const Scratch &sc, Shared &sh, const MapView &
         int c = 0;
         for (int w = 0; w < NWARPS; ++w) c += sh.warp_i[w];
         mine[NACC] = static_cast<double>(c);
+    } else if (threadIdx.x == NACC + 1) {
+        double c = 0.0;
+        for (int w = 0; w < NWARPS; ++w) c += sh.warp_c[w];
+        mine[NACC + 1] = c;
     }
+    if (dbg_on) KB_DBG(sc, 3);
     g.sync();
+    if (dbg_on) KB_DBG(sc, 4);
     // every CTA reduces all partials in the same order -> bitwise identical systems everywhere
-    const double *all = sc.blk_d + static_cast<size_t>(parity) * gridDim.x * (NACC + 1);
-    if (warp <= NACC / 2) {  // warps 0..8 : two accumulators each (17 values incl. the count)
-        for (int e = warp * 2; e < warp * 2 + 2 && e <= NACC; ++e) {
+    const double *all = sc.blk_d + static_cast<size_t>(parity) * gridDim.x * NPART;
+    if (warp < NPART / 2) {  // warps 0..8 : two values each
+        for (int e = warp * 2; e < warp * 2 + 2; ++e) {
             double s = 0.0;
-            for (int b = lane; b < static_cast<int>(gridDim.x); b += 32) s += __ldcg(&all[static_cast<size_t>(b) * (NACC + 1) + e]);
+            for (int b = lane; b < static_cast<int>(gridDim.x); b += 32) s += __ldcg(&all[static_cast<size_t>(b) * NPART + e]);
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
             if (lane == 0) {
                 if (e < NACC)
                     sh.sys[e] = s;
-                else
+                else if (e == NACC)
                     sh.two[0] = static_cast<int>(s);
+                else
+                    sh.cand = s;
             }
         }
     }
     __syncthreads();
+    if (dbg_on) KB_DBG(sc, 5);
     if (n_corr) *n_corr = sh.two[0];
 }
 
@@ -622,6 +696,8 @@ __device__ void op_icp(Grid &g, const Scratch &sc, Shared &sh, const MapView &m,
         if (threadIdx.x == 0) {
             sh.result = guess;
             sh.iters = 0;
+            sh.cand_total = 0.0;
+            sh.query_total = 0.0;
         }
         __syncthreads();
         return;
@@ -630,12 +706,14 @@ __device__ void op_icp(Grid &g, const Scratch &sc, Shared &sh, const MapView &m,
         sh.pending = guess;
         sh.t_icp = se3_identity();
         sh.flag = 0;
+        sh.cand_total = 0.0;
+        sh.query_total = 0.0;
     }
     __syncthreads();
     int j = 0;
     for (; j < max_iter; ++j) {
         const SE3 pending = sh.pending;
-        icp_pass(g, sc, sh, m, j == 0 ? src : work, work, n, pending, max_dist, kscale, j & 1, nullptr);
+        icp_pass(g, sc, sh, m, j == 0 ? src : work, work, n, pending, max_dist, kscale, j & 1, nullptr, j == 1);
         if (threadIdx.x == 0) {
             double JTJ[36], JTr[6], rhs[6], dx[6];
             icp_expand(sh.sys, JTJ, JTr);
@@ -647,6 +725,9 @@ __device__ void op_icp(Grid &g, const Scratch &sc, Shared &sh, const MapView &m,
             double n2 = 0.0;
             for (int i = 0; i < 6; ++i) n2 += dx[i] * dx[i];
             sh.flag = (sqrt(n2) < conv) ? 1 : 0;     // :163
+            sh.cand_total += sh.cand;
+            sh.query_total += static_cast<double>(n);
+            if (j == 1 && blockIdx.x == 0) sc.dbg[6] = globaltimer_ns();
         }
         __syncthreads();
         if (sh.flag) {

@@ -26,6 +26,9 @@ struct FrameResult {
     int n_pre, n_ds, n_src;
     int map_live, map_tomb, map_points, map_status;
     int pad;
+    double icp_candidates;  // map points examined by all ICP iterations of this frame
+    double icp_queries;     // GetClosestNeighbor calls (iterations x source points)
+    unsigned long long t_ns[8];  // %globaltimer at phase boundaries (CTA 0): start, pre, ds1, ds2, icp, map, end
 };
 
 struct Workspace {
@@ -37,8 +40,7 @@ struct Workspace {
     double *tp;     // [n][3] points being inserted, map frame
     int *next;      // [n] pending-list links
     int *touched;   // [n] voxels touched by the current AddPoints
-    int4 *ds_slots;  // [pow2 >= 2n] downsample scratch table
-    int *ds_prefix;  // [pow2 >= 2n]
+    DsScratch ds;    // [pow2 >= 2n] downsample scratch tables
     int *cnt;        // [8] device-side counts (n_pre, n_ds, n_src, ...)
 };
 
@@ -71,10 +73,14 @@ __device__ __forceinline__ void threshold_update(const SE3 &dev, double min_moti
 }
 
 // ---- KissICP::RegisterFrame (pipeline/KissICP.cpp:35-68) as ONE persistent kernel ----------
+#define KB_STAMP(i) \
+    if (blockIdx.x == 0 && threadIdx.x == 0) P.res->t_ns[i] = globaltimer_ns()
+
 __global__ void __launch_bounds__(BLOCK, 1) k_register_frame(const FrameParams P) {
     __shared__ Shared sh;
     Grid g;
     g.init(P.sc.bar);
+    KB_STAMP(0);
     const SE3 last_pose = P.st->last_pose;
     const SE3 last_delta = P.st->last_delta;
     const double model_sse = P.st->model_sse;
@@ -84,15 +90,18 @@ __global__ void __launch_bounds__(BLOCK, 1) k_register_frame(const FrameParams P
     op_preprocess(g, P.sc, sh, P.in, P.n, P.ts, P.n_ts, P.deskew != 0, last_delta, P.max_range, P.min_range,
                   P.ws.tmp, P.ws.pre, &P.ws.cnt[0]);
     g.sync();
+    KB_STAMP(1);
     const int n_pre = __ldcg(&P.ws.cnt[0]);
     // Voxelize (KissICP.cpp:70-75)
-    op_downsample(g, P.sc, sh, P.ws.pre, n_pre, P.voxel_size * 0.5, P.ws.ds_slots, P.ws.ds_prefix, P.ws.ds1,
+    op_downsample(g, P.sc, sh, P.ws.pre, n_pre, P.voxel_size * 0.5, P.ws.ds, P.ws.ds1,
                   &P.ws.cnt[1]);
     g.sync();
+    KB_STAMP(2);
     const int n_ds = __ldcg(&P.ws.cnt[1]);
-    op_downsample(g, P.sc, sh, P.ws.ds1, n_ds, P.voxel_size * 1.5, P.ws.ds_slots, P.ws.ds_prefix, P.ws.src,
+    op_downsample(g, P.sc, sh, P.ws.ds1, n_ds, P.voxel_size * 1.5, P.ws.ds, P.ws.src,
                   &P.ws.cnt[2]);
     g.sync();
+    KB_STAMP(3);
     const int n_src = __ldcg(&P.ws.cnt[2]);
     // sigma, initial guess (KissICP.cpp:44,47)
     const double sigma = sqrt(model_sse / num_samples);
@@ -101,10 +110,13 @@ __global__ void __launch_bounds__(BLOCK, 1) k_register_frame(const FrameParams P
     op_icp(g, P.sc, sh, P.m, P.ws.src, P.ws.work, n_src, guess, 3.0 * sigma, sigma, P.max_iter, P.conv);
     const SE3 new_pose = sh.result;
     const int iters = sh.iters;
+    const double icp_cand = sh.cand_total, icp_q = sh.query_total;
+    KB_STAMP(4);
     // local_map_.Update(frame_downsample, new_pose) (KissICP.cpp:61)
     op_map_add(g, sh, P.m, P.ws.ds1, n_ds, true, new_pose, P.ws.tp, P.ws.next, P.ws.touched);
     op_map_remove_far(P.m, new_pose.t);
     g.sync();
+    KB_STAMP(5);
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         // model deviation, threshold, delta, pose (KissICP.cpp:57-63)
         const SE3 dev = se3_mul(se3_inverse(guess), new_pose);
@@ -123,6 +135,8 @@ __global__ void __launch_bounds__(BLOCK, 1) k_register_frame(const FrameParams P
         r->model_sse = sse;
         r->num_samples = ns;
         r->iterations = iters;
+        r->icp_candidates = icp_cand;
+        r->icp_queries = icp_q;
         r->n_pre = n_pre;
         r->n_ds = n_ds;
         r->n_src = n_src;
@@ -130,6 +144,7 @@ __global__ void __launch_bounds__(BLOCK, 1) k_register_frame(const FrameParams P
         r->map_tomb = P.m.counters[C_TOMB];
         r->map_points = P.m.counters[C_POINTS];
         r->map_status = P.m.counters[C_STATUS];
+        r->t_ns[6] = globaltimer_ns();
     }
 }
 
@@ -157,8 +172,7 @@ struct DsParams {
     const double *in;
     int n;
     double voxel_size;
-    int4 *ds_slots;
-    int *ds_prefix;
+    DsScratch ds;
     double *out;
     int *out_n;
     // optional second stage (Voxelize): out2 = downsample(out, voxel_size2)
@@ -170,11 +184,11 @@ __global__ void __launch_bounds__(BLOCK, 1) k_downsample(const DsParams P) {
     __shared__ Shared sh;
     Grid g;
     g.init(P.sc.bar);
-    op_downsample(g, P.sc, sh, P.in, P.n, P.voxel_size, P.ds_slots, P.ds_prefix, P.out, P.out_n);
+    op_downsample(g, P.sc, sh, P.in, P.n, P.voxel_size, P.ds, P.out, P.out_n);
     if (P.out2) {
         g.sync();
         const int n1 = __ldcg(P.out_n);
-        op_downsample(g, P.sc, sh, P.out, n1, P.voxel_size2, P.ds_slots, P.ds_prefix, P.out2, P.out_n2);
+        op_downsample(g, P.sc, sh, P.out, n1, P.voxel_size2, P.ds, P.out2, P.out_n2);
     }
 }
 
@@ -234,6 +248,16 @@ __global__ void __launch_bounds__(BLOCK, 1) k_map_update(const MapUpdParams P) {
     g.init(P.sc.bar);
     if (P.do_add) op_map_add(g, sh, P.m, P.pts, P.n, P.has_pose != 0, P.pose, P.tp, P.next, P.touched);
     if (P.do_remove) op_map_remove_far(P.m, P.origin);
+}
+
+// profiling aid: cost of the grid barrier itself
+__global__ void __launch_bounds__(BLOCK, 1) k_barrier_bench(const Scratch sc, int iters) {
+    Grid g;
+    g.init(sc.bar);
+    g.sync();
+    KB_DBG(sc, 8);
+    for (int i = 0; i < iters; ++i) g.sync();
+    KB_DBG(sc, 9);
 }
 
 // table initialisation / clear

@@ -56,8 +56,6 @@ class KissICP:
             self.local_map = VoxelHashMap(c.voxel_size, c.max_range, c.max_points_per_voxel,
                                           _borrowed=N.lib().kb_pipeline_voxel_map(self._h), _owner=self)
             self.adaptive_threshold = _PipelineThreshold(self)
-            self._model_sse = c.initial_threshold ** 2
-            self._num_samples = 1
         else:
             self._last_pose = np.eye(4)
             self._last_delta = np.eye(4)
@@ -104,7 +102,9 @@ class KissICP:
             N.check(N.lib().kb_pipeline_set_delta(self._h, N.ptr(N.mat4_arg(T))))
 
     def _sigma_next(self):
-        return float(np.sqrt(self._model_sse / self._num_samples))
+        s = N.dbl(0)
+        N.check(N.lib().kb_pipeline_threshold(self._h, C.byref(s)))
+        return s.value
 
     @property
     def last_sigma(self):
@@ -119,6 +119,26 @@ class KissICP:
         it = N.i32(0)
         N.check(N.lib().kb_pipeline_last_iterations(self._h, C.byref(it)))
         return it.value
+
+    @property
+    def last_profile_us(self):
+        """device-side phase durations of the last fused RegisterFrame [us]:
+        preprocess, downsample 0.5v, downsample 1.5v, ICP, map update, epilogue"""
+        us = np.zeros(6)
+        N.check(N.lib().kb_pipeline_last_profile(self._h, N.ptr(us), 6))
+        return us
+
+    def start_history(self, capacity: int):
+        """log per-frame statistics of the next ``capacity`` fused RegisterFrame calls (host side)"""
+        N.check(N.lib().kb_pipeline_set_history(self._h, int(capacity)))
+
+    def history(self):
+        n = N.sz(0)
+        N.check(N.lib().kb_pipeline_get_history(self._h, None, 0, C.byref(n)))
+        arr = (N.FrameStats * n.value)()
+        if n.value:
+            N.check(N.lib().kb_pipeline_get_history(self._h, arr, n.value, C.byref(n)))
+        return list(arr)
 
     # -- RegisterFrame ---------------------------------------------------------------------------
     def register_frame(self, frame, timestamps, return_clouds: bool = True):

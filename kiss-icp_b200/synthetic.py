@@ -109,7 +109,9 @@ class SyntheticLidar:
 
     def pose(self, k: float) -> np.ndarray:
         """Ground-truth sensor pose (4x4, world<-sensor) at (fractional) scan index k."""
-        s = k * self.ds
+        # the vehicle starts from rest and approaches cruise speed exponentially (tau = 10 scans)
+        tau = 10.0
+        s = self.ds * (k + tau * (math.exp(-max(k, 0.0) / tau) - 1.0)) if k > 0 else 0.0
         e = 1e-3
         p = self._xy(s)
         t = (self._xy(s + e) - self._xy(s - e)) / (2 * e)

