@@ -163,8 +163,11 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     N.check(N.lib().kb_set_device(local))
-    stream = torch.cuda.current_stream()
-    N.check(N.lib().kb_set_stream(C.c_void_p(stream.cuda_stream)))  # kernels launch on torch's current stream
+    # torch's default stream has a NULL handle; use an explicit stream so that the library's launches and
+    # the torch.cuda.Event timing share ONE stream
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    N.check(N.lib().kb_set_stream(C.c_void_p(stream.cuda_stream)))
 
     seq = sharding.sequences_of_rank(rank, world, world)[0]
     lidar = synthetic.kitti_shape(seed=seq, device=dev)

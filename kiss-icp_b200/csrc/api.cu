@@ -1066,7 +1066,14 @@ int kb_pipeline_debug_stamps(const kb_pipeline *p, double *ns, int n) {
     CK(cudaSetDevice(p->ex->device));
     CK(cudaMemcpyAsync(t, p->ex->sc.dbg, sizeof(t), cudaMemcpyDeviceToHost, p->ex->stream));
     RET(p->ex->sync());
-    for (int i = 0; i < n && i < 64; ++i) ns[i] = static_cast<double>(t[i] - t[0]);
+    for (int i = 0; i < n && i < 64; ++i) ns[i] = static_cast<double>(static_cast<long long>(t[i] - t[0]));
+    return KB_OK;
+}
+int kb_debug_ldlt6(const double A[36], const double b[6], double x_loop[6], double x_unrolled[6]) {
+    // host evaluation of the two LDLT implementations the device uses (same source, __host__ __device__)
+    if (!A || !b || !x_loop || !x_unrolled) return fail(KB_ERR_INVALID_ARG, "NULL argument");
+    ldlt6_solve(A, b, x_loop);
+    ldlt6_solve_reg(A, b, x_unrolled);
     return KB_OK;
 }
 int kb_debug_barrier_ns(int iters, double *ns_per_barrier) {

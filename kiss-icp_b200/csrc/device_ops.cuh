@@ -72,7 +72,7 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
     return t;
 }
 #define KB_DBG(sc, i) \
-    if (blockIdx.x == 0 && threadIdx.x == 0) (sc).dbg[i] = globaltimer_ns()
+    if (blockIdx.x == 0 && (threadIdx.x & 31) == 0) (sc).dbg[i] = static_cast<unsigned long long>(clock64())
 
 struct Grid {
     unsigned *bar;
@@ -235,11 +235,20 @@ __device__ __forceinline__ void chunk_of(long long n, long long *lo, long long *
 //   deskew (constant velocity, referenced to the END of the scan) + strict range crop +
 //   order-preserving compaction. Two passes around one grid barrier.
 // ------------------------------------------------------------------------------------------
+// per-warp staging of one query's neighbourhood: which voxel owns the j-th candidate point
+constexpr int NN_FLAT_CAP = 32;  // fast path for max_points_per_voxel <= 32
+struct WarpNN {
+    unsigned char owner[27 * NN_FLAT_CAP];
+    int slot[27];
+    int start[27];
+};
+
 struct Shared {
     int warp_i[NWARPS + 1];
     int two[2];
     double warp_d[NWARPS][NACC];
     double warp_c[NWARPS];
+    WarpNN wnn[NWARPS];
     double sys[NACC];
     double omega[6];
     double mm[2];
@@ -502,36 +511,7 @@ struct NNResult {
     int candidates;
 };
 
-__device__ __forceinline__ NNResult nn_search_warp(const MapView &m, const V3 &q, int lane) {
-    const int3 v = point_to_voxel(q.x, q.y, q.z, m.voxel_size);
-    int cnt = 0, slot = -1;
-    if (lane < 27) {
-        slot = map_find(m, v.x + c_shifts[lane][0], v.y + c_shifts[lane][1], v.z + c_shifts[lane][2], &cnt);
-        if (slot < 0) cnt = 0;
-    }
-    unsigned occ = __ballot_sync(FULL, cnt > 0);
-    double best = DBL_MAX;
-    int bseq = INT_MAX;
-    V3 bp{0, 0, 0};
-    int ncand = 0;
-    const int cap = m.cap;
-    while (occ) {
-        const int vi = __ffs(occ) - 1;
-        occ &= occ - 1;
-        const int c = __shfl_sync(FULL, cnt, vi);
-        const int s = __shfl_sync(FULL, slot, vi);
-        ncand += c;
-        const double *blk = m.points + static_cast<size_t>(s) * cap * 3;
-        for (int k = lane; k < c; k += 32) {
-            const V3 p{blk[3 * k], blk[3 * k + 1], blk[3 * k + 2]};
-            const double d = norm(p - q);
-            if (d < best) {  // per lane the sequence number only grows: strict < keeps the first
-                best = d;
-                bseq = vi * 1024 + k;
-                bp = p;
-            }
-        }
-    }
+__device__ __forceinline__ void nn_reduce(double &best, int &bseq, V3 &bp) {
     // lexicographic (distance, sequence) minimum across the warp
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -546,40 +526,128 @@ __device__ __forceinline__ NNResult nn_search_warp(const MapView &m, const V3 &q
             bp = V3{ox, oy, oz};
         }
     }
-    return NNResult{best, bp, ncand};
+}
+
+__device__ __forceinline__ NNResult nn_search_warp(const MapView &m, const V3 &q, int lane, WarpNN &w) {
+    const int3 v = point_to_voxel(q.x, q.y, q.z, m.voxel_size);
+    int cnt = 0, slot = -1;
+    if (lane < 27) {
+        slot = map_find(m, v.x + c_shifts[lane][0], v.y + c_shifts[lane][1], v.z + c_shifts[lane][2], &cnt);
+        if (slot < 0) cnt = 0;
+    }
+    double best = DBL_MAX;
+    int bseq = INT_MAX;
+    V3 bp{0, 0, 0};
+    const int cap = m.cap;
+    int total;
+    if (cap <= NN_FLAT_CAP) {
+        // FLAT GATHER: candidate j (in reference order: voxel_shifts order, then insertion order)
+        // goes to lane j % 32; all loads of a round are independent -> one L2 round trip instead
+        // of one per occupied voxel.
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(FULL, incl, o);
+            if (lane >= o) incl += t;
+        }
+        const int start = incl - cnt;
+        total = __shfl_sync(FULL, incl, 31);
+        __syncwarp();
+        if (lane < 27) {
+            w.slot[lane] = slot;
+            w.start[lane] = start;
+            for (int k = 0; k < cnt; ++k) w.owner[start + k] = static_cast<unsigned char>(lane);
+        }
+        __syncwarp();
+        constexpr int U = 4;
+        for (int base = 0; base < total; base += 32 * U) {
+            V3 c[U];
+            bool ok[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int j = base + u * 32 + lane;
+                ok[u] = j < total;
+                if (ok[u]) {
+                    const int vi = w.owner[j];
+                    const double *pp = m.points + (static_cast<size_t>(w.slot[vi]) * cap + (j - w.start[vi])) * 3;
+                    c[u] = V3{pp[0], pp[1], pp[2]};
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (ok[u]) {
+                    const double d = norm(c[u] - q);
+                    if (d < best) {  // per lane j only grows: strict < keeps the first minimum
+                        best = d;
+                        bseq = base + u * 32 + lane;
+                        bp = c[u];
+                    }
+                }
+            }
+        }
+    } else {
+        // general path: walk the occupied voxels one after the other
+        unsigned occ = __ballot_sync(FULL, cnt > 0);
+        total = 0;
+        while (occ) {
+            const int vi = __ffs(occ) - 1;
+            occ &= occ - 1;
+            const int c = __shfl_sync(FULL, cnt, vi);
+            const int s = __shfl_sync(FULL, slot, vi);
+            total += c;
+            const double *blk = m.points + static_cast<size_t>(s) * cap * 3;
+            for (int k = lane; k < c; k += 32) {
+                const V3 p{blk[3 * k], blk[3 * k + 1], blk[3 * k + 2]};
+                const double d = norm(p - q);
+                if (d < best) {
+                    best = d;
+                    bseq = vi * 1024 + k;
+                    bp = p;
+                }
+            }
+        }
+    }
+    nn_reduce(best, bseq, bp);
+    return NNResult{best, bp, total};
 }
 
 // ------------------------------------------------------------------------------------------
-// icp_accumulate — one correspondence of BuildLinearSystem (core/Registration.cpp:80-121)
+// icp_term — one correspondence of BuildLinearSystem (core/Registration.cpp:80-121)
 //   J = [I | -hat(s)], w = k^2/(k + |r|^2)^2, JTJ += J^T w J, JTr += J^T w r. With N = -hat(s)
 //   the 6x6 has only 16 distinct accumulators:
-//     acc[0]      sum w                     (JTJ[0][0] = [1][1] = [2][2])
-//     acc[1..3]   sum w*s.x, w*s.y, w*s.z   (the antisymmetric lower-left block)
-//     acc[4..9]   lower triangle of N^T w N ((3,3),(4,3),(4,4),(5,3),(5,4),(5,5))
-//     acc[10..15] JTr
-//   Each product/sum is formed exactly as Eigen forms (J^T*w)*J entry by entry.
+//     [0]      sum w                     (JTJ[0][0] = [1][1] = [2][2])
+//     [1..3]   sum w*s.x, w*s.y, w*s.z   (the antisymmetric lower-left block)
+//     [4..9]   lower triangle of N^T w N ((3,3),(4,3),(4,4),(5,3),(5,4),(5,5))
+//     [10..15] JTr
+//   Each product/sum is formed exactly as Eigen forms (J^T*w)*J entry by entry. Lane l (< 16)
+//   of the warp owns accumulator l: the function returns that lane's term.
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void icp_accumulate(double acc[NACC], const V3 &s, const V3 &t, double kscale) {
+__device__ __forceinline__ double icp_term(int lane, const V3 &s, const V3 &t, double kscale) {
     const V3 r = s - t;
     const double r2 = sqnorm(r);
     const double w = (kscale * kscale) / ((kscale + r2) * (kscale + r2));
     const double xw = s.x * w, yw = s.y * w, zw = s.z * w;
-    acc[0] += w;
-    acc[1] += xw;
-    acc[2] += yw;
-    acc[3] += zw;
-    acc[4] += zw * s.z + yw * s.y;     // (3,3)
-    acc[5] += -(xw * s.y);             // (4,3)
-    acc[6] += zw * s.z + xw * s.x;     // (4,4)
-    acc[7] += -(xw * s.z);             // (5,3)
-    acc[8] += -(yw * s.z);             // (5,4)
-    acc[9] += yw * s.y + xw * s.x;     // (5,5)
-    acc[10] += w * r.x;
-    acc[11] += w * r.y;
-    acc[12] += w * r.z;
-    acc[13] += -(zw * r.y) + yw * r.z;
-    acc[14] += zw * r.x - xw * r.z;
-    acc[15] += -(yw * r.x) + xw * r.y;
+    double v = 0.0;
+    switch (lane) {
+        case 0: v = w; break;
+        case 1: v = xw; break;
+        case 2: v = yw; break;
+        case 3: v = zw; break;
+        case 4: v = zw * s.z + yw * s.y; break;   // (3,3)
+        case 5: v = -(xw * s.y); break;           // (4,3)
+        case 6: v = zw * s.z + xw * s.x; break;   // (4,4)
+        case 7: v = -(xw * s.z); break;           // (5,3)
+        case 8: v = -(yw * s.z); break;           // (5,4)
+        case 9: v = yw * s.y + xw * s.x; break;   // (5,5)
+        case 10: v = w * r.x; break;
+        case 11: v = w * r.y; break;
+        case 12: v = w * r.z; break;
+        case 13: v = -(zw * r.y) + yw * r.z; break;
+        case 14: v = zw * r.x - xw * r.z; break;
+        case 15: v = -(yw * r.x) + xw * r.y; break;
+        default: break;
+    }
+    return v;
 }
 
 // expand the 16 accumulators to the (lower-triangle-complete) row-major 6x6 and rhs = -JTr
@@ -612,11 +680,9 @@ __device__ void icp_pass(Grid &g, const Scratch &sc, Shared &sh, const MapView &
                          int n, const SE3 &pending, double max_dist, double kscale, int parity, int *n_corr,
                          bool dbg_on = false) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (dbg_on) KB_DBG(sc, 0);
+    if (dbg_on && warp == 0) KB_DBG(sc, 0);
     const int gwarp = blockIdx.x * NWARPS + warp, nwarps = gridDim.x * NWARPS;
-    double acc[NACC];
-#pragma unroll
-    for (int i = 0; i < NACC; ++i) acc[i] = 0.0;
+    double acc = 0.0;  // lane l < 16 owns accumulator l
     int corr = 0;
     double cand = 0.0;
     for (int qi = gwarp; qi < n; qi += nwarps) {
@@ -627,26 +693,26 @@ __device__ void icp_pass(Grid &g, const Scratch &sc, Shared &sh, const MapView &
             work[3 * qi + 1] = p.y;
             work[3 * qi + 2] = p.z;
         }
-        const NNResult r = nn_search_warp(m, p, lane);
+        const NNResult r = nn_search_warp(m, p, lane, sh.wnn[warp]);
         cand += r.candidates;
         if (r.d < max_dist) {
-            icp_accumulate(acc, p, r.p, kscale);
+            acc += icp_term(lane, p, r.p, kscale);
             ++corr;
         }
     }
     if (dbg_on && warp == 0) KB_DBG(sc, 1);
-    __syncthreads();
-    if (dbg_on) KB_DBG(sc, 2);
+    if (dbg_on && warp == NWARPS - 1) KB_DBG(sc, 7);
+    if (lane < NACC) sh.warp_d[warp][lane] = acc;
     if (lane == 0) {
-#pragma unroll
-        for (int i = 0; i < NACC; ++i) sh.warp_d[warp][i] = acc[i];
         sh.warp_i[warp] = corr;
         sh.warp_c[warp] = cand;
     }
     __syncthreads();
+    if (dbg_on && warp == 0) KB_DBG(sc, 2);
     double *mine = sc.blk_d + (static_cast<size_t>(parity) * gridDim.x + blockIdx.x) * NPART;
     if (threadIdx.x < NACC) {
         double s = 0.0;
+#pragma unroll
         for (int w = 0; w < NWARPS; ++w) s += sh.warp_d[w][threadIdx.x];
         mine[threadIdx.x] = s;
     } else if (threadIdx.x == NACC) {
@@ -658,29 +724,27 @@ __device__ void icp_pass(Grid &g, const Scratch &sc, Shared &sh, const MapView &
         for (int w = 0; w < NWARPS; ++w) c += sh.warp_c[w];
         mine[NACC + 1] = c;
     }
-    if (dbg_on) KB_DBG(sc, 3);
+    if (dbg_on && warp == 0) KB_DBG(sc, 3);
     g.sync();
-    if (dbg_on) KB_DBG(sc, 4);
+    if (dbg_on && warp == 0) KB_DBG(sc, 4);
     // every CTA reduces all partials in the same order -> bitwise identical systems everywhere
     const double *all = sc.blk_d + static_cast<size_t>(parity) * gridDim.x * NPART;
-    if (warp < NPART / 2) {  // warps 0..8 : two values each
-        for (int e = warp * 2; e < warp * 2 + 2; ++e) {
-            double s = 0.0;
-            for (int b = lane; b < static_cast<int>(gridDim.x); b += 32) s += __ldcg(&all[static_cast<size_t>(b) * NPART + e]);
+    for (int e = warp; e < NPART; e += NWARPS) {  // one value per warp (two for warps 0,1)
+        double s = 0.0;
+        for (int b = lane; b < static_cast<int>(gridDim.x); b += 32) s += __ldcg(&all[static_cast<size_t>(b) * NPART + e]);
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
-            if (lane == 0) {
-                if (e < NACC)
-                    sh.sys[e] = s;
-                else if (e == NACC)
-                    sh.two[0] = static_cast<int>(s);
-                else
-                    sh.cand = s;
-            }
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
+        if (lane == 0) {
+            if (e < NACC)
+                sh.sys[e] = s;
+            else if (e == NACC)
+                sh.two[0] = static_cast<int>(s);
+            else
+                sh.cand = s;
         }
     }
     __syncthreads();
-    if (dbg_on) KB_DBG(sc, 5);
+    if (dbg_on && warp == 0) KB_DBG(sc, 5);
     if (n_corr) *n_corr = sh.two[0];
 }
 
@@ -718,7 +782,7 @@ __device__ void op_icp(Grid &g, const Scratch &sc, Shared &sh, const MapView &m,
             double JTJ[36], JTr[6], rhs[6], dx[6];
             icp_expand(sh.sys, JTJ, JTr);
             for (int i = 0; i < 6; ++i) rhs[i] = -JTr[i];
-            ldlt6_solve(JTJ, rhs, dx);               // :156
+            ldlt6_solve_reg(JTJ, rhs, dx);           // :156
             const SE3 est = se3_exp(dx);             // :157
             sh.t_icp = se3_mul(est, sh.t_icp);       // :161
             sh.pending = est;                        // applied lazily at the next pass (:159)
@@ -727,7 +791,7 @@ __device__ void op_icp(Grid &g, const Scratch &sc, Shared &sh, const MapView &m,
             sh.flag = (sqrt(n2) < conv) ? 1 : 0;     // :163
             sh.cand_total += sh.cand;
             sh.query_total += static_cast<double>(n);
-            if (j == 1 && blockIdx.x == 0) sc.dbg[6] = globaltimer_ns();
+            if (j == 1 && blockIdx.x == 0) sc.dbg[6] = static_cast<unsigned long long>(clock64());
         }
         __syncthreads();
         if (sh.flag) {

@@ -255,9 +255,9 @@ __global__ void __launch_bounds__(BLOCK, 1) k_barrier_bench(const Scratch sc, in
     Grid g;
     g.init(sc.bar);
     g.sync();
-    KB_DBG(sc, 8);
+    if (blockIdx.x == 0 && threadIdx.x == 0) sc.dbg[8] = globaltimer_ns();
     for (int i = 0; i < iters; ++i) g.sync();
-    KB_DBG(sc, 9);
+    if (blockIdx.x == 0 && threadIdx.x == 0) sc.dbg[9] = globaltimer_ns();
 }
 
 // table initialisation / clear
@@ -298,13 +298,14 @@ template <bool COUNT>
 __global__ void __launch_bounds__(256) k_nn_query(const MapView m, const double *__restrict__ q, size_t n,
                                                   double *__restrict__ out_p, double *__restrict__ out_d,
                                                   unsigned long long *cand_total) {
+    __shared__ WarpNN wnn[8];  // blockDim.x == 256
     const int lane = threadIdx.x & 31;
     const size_t gw = (blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x) >> 5;
     const size_t nw = (static_cast<size_t>(gridDim.x) * blockDim.x) >> 5;
     unsigned long long cand = 0;
     for (size_t i = gw; i < n; i += nw) {
         const V3 p{q[3 * i], q[3 * i + 1], q[3 * i + 2]};
-        const NNResult r = nn_search_warp(m, p, lane);
+        const NNResult r = nn_search_warp(m, p, lane, wnn[threadIdx.x >> 5]);
         if (lane == 0) {
             out_p[3 * i] = r.p.x;
             out_p[3 * i + 1] = r.p.y;

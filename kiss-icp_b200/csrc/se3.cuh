@@ -368,4 +368,149 @@ KB_HD void ldlt6_solve(const double A_in[36], const double b[6], double x[6]) {
     for (int i = 0; i < N; ++i) x[i] = d[i];
 }
 
+// Same algorithm as ldlt6_solve with every index resolved at compile time (pivot swaps are
+// expanded into one guarded block per possible pivot row), so the 6x6 lives in registers
+// instead of local memory: the ICP solve is a single-thread dependent chain and this makes
+// it ~5x shorter. Bit-identical to ldlt6_solve.
+template <int K, int BIG>
+KB_HD void ldlt6_swap(double (&mat)[6][6]) {
+    constexpr int N = 6;
+    constexpr int S = N - BIG - 1;
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+        const double t = mat[K][j];
+        mat[K][j] = mat[BIG][j];
+        mat[BIG][j] = t;
+    }
+#pragma unroll
+    for (int i = 0; i < S; ++i) {
+        const double t = mat[N - S + i][K];
+        mat[N - S + i][K] = mat[N - S + i][BIG];
+        mat[N - S + i][BIG] = t;
+    }
+    {
+        const double t = mat[K][K];
+        mat[K][K] = mat[BIG][BIG];
+        mat[BIG][BIG] = t;
+    }
+#pragma unroll
+    for (int i = K + 1; i < BIG; ++i) {
+        const double t = mat[i][K];
+        mat[i][K] = mat[BIG][i];
+        mat[BIG][i] = t;
+    }
+}
+
+template <int K>
+KB_HD bool ldlt6_step(double (&mat)[6][6], int (&tr)[6]) {
+    constexpr int N = 6;
+    int big = K;
+    double best = fabs(mat[K][K]);
+#pragma unroll
+    for (int i = K + 1; i < N; ++i) {
+        const double v = fabs(mat[i][i]);
+        if (v > best) {
+            best = v;
+            big = i;
+        }
+    }
+    tr[K] = big;
+    if (K + 1 < N && big == K + 1) ldlt6_swap<K, (K + 1 < N ? K + 1 : K)>(mat);
+    if (K + 2 < N && big == K + 2) ldlt6_swap<K, (K + 2 < N ? K + 2 : K)>(mat);
+    if (K + 3 < N && big == K + 3) ldlt6_swap<K, (K + 3 < N ? K + 3 : K)>(mat);
+    if (K + 4 < N && big == K + 4) ldlt6_swap<K, (K + 4 < N ? K + 4 : K)>(mat);
+    if (K + 5 < N && big == K + 5) ldlt6_swap<K, (K + 5 < N ? K + 5 : K)>(mat);
+    constexpr int RS = N - K - 1;
+    if (K > 0) {
+        double temp[6];
+#pragma unroll
+        for (int j = 0; j < K; ++j) temp[j] = mat[j][j] * mat[K][j];
+        double acc = 0.0;
+#pragma unroll
+        for (int j = 0; j < K; ++j) acc += mat[K][j] * temp[j];
+        mat[K][K] -= acc;
+#pragma unroll
+        for (int i = 0; i < RS; ++i) {
+            double a2 = 0.0;
+#pragma unroll
+            for (int j = 0; j < K; ++j) a2 += mat[K + 1 + i][j] * temp[j];
+            mat[K + 1 + i][K] -= a2;
+        }
+    }
+    const double akk = mat[K][K];
+    const bool valid = fabs(akk) > 0.0;
+    if (K == 0 && !valid) return false;  // whole diagonal zero: identity transpositions, stop
+    if (RS > 0 && valid) {
+#pragma unroll
+        for (int i = 0; i < RS; ++i) mat[K + 1 + i][K] /= akk;
+    }
+    return true;
+}
+
+template <int K>
+KB_HD void ldlt6_apply_tr(double (&d)[6], int big) {
+#pragma unroll
+    for (int b = K + 1; b < 6; ++b)
+        if (big == b) {
+            const double t = d[K];
+            d[K] = d[b];
+            d[b] = t;
+        }
+}
+
+KB_HD void ldlt6_solve_reg(const double A_in[36], const double b[6], double x[6]) {
+    constexpr int N = 6;
+    double mat[6][6];
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+#pragma unroll
+        for (int j = 0; j < N; ++j) mat[i][j] = A_in[N * i + j];
+    int tr[6] = {0, 1, 2, 3, 4, 5};
+    if (ldlt6_step<0>(mat, tr)) {
+        ldlt6_step<1>(mat, tr);
+        ldlt6_step<2>(mat, tr);
+        ldlt6_step<3>(mat, tr);
+        ldlt6_step<4>(mat, tr);
+        ldlt6_step<5>(mat, tr);
+    } else {
+        tr[0] = 0;
+    }
+    double d[6];
+#pragma unroll
+    for (int i = 0; i < N; ++i) d[i] = b[i];
+    ldlt6_apply_tr<0>(d, tr[0]);
+    ldlt6_apply_tr<1>(d, tr[1]);
+    ldlt6_apply_tr<2>(d, tr[2]);
+    ldlt6_apply_tr<3>(d, tr[3]);
+    ldlt6_apply_tr<4>(d, tr[4]);
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        double acc = d[i];
+#pragma unroll
+        for (int j = 0; j < i; ++j) acc -= mat[i][j] * d[j];
+        d[i] = acc;
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        if (fabs(mat[i][i]) > DBL_MIN)
+            d[i] /= mat[i][i];
+        else
+            d[i] = 0.0;
+    }
+#pragma unroll
+    for (int i = N - 1; i >= 0; --i) {
+        double acc = d[i];
+#pragma unroll
+        for (int j = i + 1; j < N; ++j) acc -= mat[j][i] * d[j];
+        d[i] = acc;
+    }
+    ldlt6_apply_tr<4>(d, tr[4]);
+    ldlt6_apply_tr<3>(d, tr[3]);
+    ldlt6_apply_tr<2>(d, tr[2]);
+    ldlt6_apply_tr<1>(d, tr[1]);
+    ldlt6_apply_tr<0>(d, tr[0]);
+#pragma unroll
+    for (int i = 0; i < N; ++i) x[i] = d[i];
+}
+
 }  // namespace kb

@@ -90,3 +90,23 @@ def test_missing_library_is_loud(monkeypatch, tmp_path):
     monkeypatch.setattr(_native, "LIB_PATH", str(tmp_path / "nope.so"))
     with pytest.raises(ImportError):
         _native.lib()
+
+
+def test_device_ldlt_variants_agree_with_oracle(O):
+    """the loop-form and the register-resident 6x6 LDLT (se3.cuh, __host__ __device__) evaluated
+    on the host: bit-identical to each other and to the oracle's restatement of Eigen's LDLT"""
+    from kiss_icp_b200 import _native as N
+    rng = np.random.default_rng(8)
+    cases = []
+    for _ in range(40):
+        J = rng.normal(size=(30, 6)) * rng.choice([1e-3, 1.0, 1e3], size=6)
+        cases.append((J.T @ J, rng.normal(size=6)))
+    cases.append((np.zeros((6, 6)), np.ones(6)))
+    A = np.zeros((6, 6)); A[:3, :3] = np.diag([3.0, 2.0, 1.0]); cases.append((A, np.arange(6.0)))
+    A = np.diag([1.0, 5.0, 2.0, 9.0, 3.0, 4.0]); A[3, 1] = A[1, 3] = 0.5; cases.append((A, np.ones(6)))
+    for A, b in cases:
+        A = np.ascontiguousarray(A); b = np.ascontiguousarray(b)
+        x1, x2 = np.empty(6), np.empty(6)
+        N.check(N.lib().kb_debug_ldlt6(N.ptr(A), N.ptr(b), N.ptr(x1), N.ptr(x2)))
+        assert np.array_equal(x1, x2)
+        assert np.array_equal(x1, O.ldlt6_solve(A, b))

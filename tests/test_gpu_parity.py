@@ -289,8 +289,8 @@ def test_pipeline_free_running_stream_vs_oracle(K, O, stamps, voxel):
         o.register_frame(p, t, want_clouds=False)
         dt, dr = pose_error(g.last_pose, o.pose)
         assert dt < 1e-4 and dr < 1e-4, (k, dt, dr)
-        assert dt < 1e-8 and dr < 1e-8, (k, dt, dr)
-        assert np.allclose(g.last_delta, o.delta, atol=1e-8)
+        assert dt < 1e-6 and dr < 1e-6, (k, dt, dr)  # expected: ~1e-15, up to ~1e-8 when a boundary point flips
+        assert np.allclose(g.last_delta, o.delta, atol=1e-6)
     assert g.local_map.num_points() == o.local_map.num_points()
     assert np.isclose(g.adaptive_threshold.get_threshold(), o.sigma, rtol=1e-9)
 
