@@ -191,12 +191,16 @@ kb_map *kb_pipeline_voxel_map(kb_pipeline *p);
 /* diagnostics: adaptive threshold sigma used by / ICP iterations of the last RegisterFrame */
 int kb_pipeline_last_sigma(const kb_pipeline *p, double *out);
 int kb_pipeline_last_iterations(const kb_pipeline *p, int *out);
-/* profiling aids (no reference counterpart): raw SM clock stamps [cycles, relative to stamp 0]
+/* profiling aids (no reference counterpart): raw %globaltimer stamps [ns, relative to stamp 0]
  * of the second ICP iteration of the last frame (CTA 0); cost of one grid barrier */
 int kb_pipeline_debug_stamps(const kb_pipeline *p, double *ns, int n);
 int kb_debug_barrier_ns(int iters, double *ns_per_barrier);
 /* host evaluation of the device's two 6x6 LDLT code paths (loop form / register-resident form) */
 int kb_debug_ldlt6(const double A[36], const double b[6], double x_loop[6], double x_unrolled[6]);
+/* host evaluation of the exact vs latency-optimised (reciprocal / sincos) ICP solve step:
+ * x = LDLT solve, T = exp(x) * exp(b) */
+int kb_debug_icp_solve(const double A[36], const double b[6], double x_exact[6], double x_fast[6], double T_exact[16],
+                       double T_fast[16]);
 /* work done by the ICP loop of the last RegisterFrame: GetClosestNeighbor calls (iterations x
  * source points) and map points examined — the inputs of the algorithmic-bytes formula */
 int kb_pipeline_last_icp_work(const kb_pipeline *p, double *queries, double *candidates);

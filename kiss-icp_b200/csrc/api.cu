@@ -86,7 +86,7 @@ struct Exec {
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     int grid = 0;
-    Scratch sc{nullptr, nullptr, nullptr, nullptr};
+    Scratch sc{nullptr, nullptr, nullptr, nullptr, nullptr};
     unsigned long long launches = 0;
 
     int init() {
@@ -107,6 +107,7 @@ struct Exec {
         CK(cudaMalloc(&sc.bar, 256));
         CK(cudaMalloc(&sc.blk_d, sizeof(double) * 2 * grid * NPART));
         CK(cudaMalloc(&sc.blk_i, sizeof(int) * 2 * grid));
+        CK(cudaMalloc(&sc.icp_rec, sizeof(double) * 2 * ICP_REC));
         CK(cudaMalloc(&sc.dbg, sizeof(unsigned long long) * 64));
         CK(cudaMemsetAsync(sc.dbg, 0, sizeof(unsigned long long) * 64, stream));
         return KB_OK;
@@ -115,13 +116,14 @@ struct Exec {
         if (sc.bar) cudaFree(sc.bar);
         if (sc.blk_d) cudaFree(sc.blk_d);
         if (sc.blk_i) cudaFree(sc.blk_i);
+        if (sc.icp_rec) cudaFree(sc.icp_rec);
         if (sc.dbg) cudaFree(sc.dbg);
         if (own_stream && stream) cudaStreamDestroy(stream);
     }
     template <class P>
     int coop(void (*kern)(P), const P &p) {
         CK(cudaSetDevice(device));
-        CK(cudaMemsetAsync(sc.bar, 0, sizeof(unsigned), stream));
+        CK(cudaMemsetAsync(sc.bar, 0, 4 * sizeof(unsigned), stream));
         void *args[] = {const_cast<P *>(&p)};
         CK(cudaLaunchCooperativeKernel(reinterpret_cast<const void *>(kern), dim3(grid), dim3(BLOCK), args, 0, stream));
         ++launches;
@@ -130,7 +132,7 @@ struct Exec {
     template <class A, class B>
     int coop(void (*kern)(A, B), const A &a, const B &b) {
         CK(cudaSetDevice(device));
-        CK(cudaMemsetAsync(sc.bar, 0, sizeof(unsigned), stream));
+        CK(cudaMemsetAsync(sc.bar, 0, 4 * sizeof(unsigned), stream));
         void *args[] = {const_cast<A *>(&a), const_cast<B *>(&b)};
         CK(cudaLaunchCooperativeKernel(reinterpret_cast<const void *>(kern), dim3(grid), dim3(BLOCK), args, 0, stream));
         ++launches;
@@ -212,6 +214,7 @@ struct kb_map {
         m.voxel_size = voxel_size;
         m.max_distance = max_distance;
         m.map_resolution = std::sqrt(voxel_size * voxel_size / cap);
+        m.vdiv = make_voxel_div(voxel_size);
         return m;
     }
     void free_table() {
@@ -1074,6 +1077,17 @@ int kb_debug_ldlt6(const double A[36], const double b[6], double x_loop[6], doub
     if (!A || !b || !x_loop || !x_unrolled) return fail(KB_ERR_INVALID_ARG, "NULL argument");
     ldlt6_solve(A, b, x_loop);
     ldlt6_solve_reg(A, b, x_unrolled);
+    return KB_OK;
+}
+int kb_debug_icp_solve(const double A[36], const double b[6], double x_exact[6], double x_fast[6], double T_exact[16],
+                       double T_fast[16]) {
+    // host evaluation of the exact and the latency-optimised solve/exp/compose the ICP loop uses
+    if (!A || !b || !x_exact || !x_fast || !T_exact || !T_fast) return fail(KB_ERR_INVALID_ARG, "NULL argument");
+    ldlt6_solve_reg(A, b, x_exact);
+    ldlt6_solve_fast(A, b, x_fast);
+    const SE3 base = se3_exp(b);
+    se3_to_matrix(se3_mul(se3_exp(x_exact), base), T_exact);
+    se3_to_matrix(se3_mul_fast(se3_exp_fast(x_fast), base), T_fast);
     return KB_OK;
 }
 int kb_debug_barrier_ns(int iters, double *ns_per_barrier) {

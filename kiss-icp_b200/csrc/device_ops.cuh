@@ -33,9 +33,29 @@ constexpr int BLOCK = 512;  // threads per CTA of every cooperative kernel
 constexpr int NWARPS = BLOCK / 32;
 constexpr int NACC = 16;  // unique accumulators of the 6x6 normal equations (see icp_accumulate)
 constexpr int NPART = NACC + 2;  // per-CTA partial: accumulators, #correspondences, #candidate points
+constexpr int ICP_REC = 32;      // est(7) t_icp(7) final(7) conv cand_total query_total ...
 
 enum Counter { C_LIVE = 0, C_TOMB = 1, C_POINTS = 2, C_STATUS = 3, C_TOUCHED = 4, C_NCOUNTERS = 8 };
 enum StatusBit { ST_TABLE_FULL = 1 };
+
+// core/VoxelUtils.hpp:33-37 — FP64 DIVISION then floor then int cast (bit-exact with the CPU).
+// A DDIV costs ~131 cycles on B200; when voxel_size is an exact power of two (1.0, 0.5, 2.0 ...:
+// the reference defaults) x / v == x * (1/v) EXACTLY, so the division is replaced by a multiply.
+struct VoxelDiv {
+    double v, inv;
+    bool pow2;
+};
+__host__ __device__ __forceinline__ VoxelDiv make_voxel_div(double voxel_size) {
+    VoxelDiv d;
+    d.v = voxel_size;
+    unsigned long long bits;
+    memcpy(&bits, &voxel_size, 8);
+    const unsigned long long expo = (bits >> 52) & 0x7ffULL;
+    // normal power of two whose reciprocal is also a normal power of two
+    d.pow2 = (bits & 0x000fffffffffffffULL) == 0 && expo > 2 && expo < 2044 && voxel_size > 0.0;
+    d.inv = d.pow2 ? 1.0 / voxel_size : 0.0;
+    return d;
+}
 
 struct MapView {
     int4 *slots;      // [capacity]
@@ -47,12 +67,14 @@ struct MapView {
     double voxel_size;
     double max_distance;
     double map_resolution;  // sqrt(voxel_size^2 / max_points_per_voxel)  VoxelHashMap.cpp:98
+    VoxelDiv vdiv;          // voxel_size as a divisor (exact multiply when it is a power of two)
 };
 
 // cross-CTA scratch, sized by the grid
 struct Scratch {
-    unsigned *bar;  // grid barrier counter (zeroed before each launch)
+    unsigned *bar;  // [0] grid barrier counter, [1] ICP arrivals, [2] ICP publish epoch (zeroed before each launch)
     double *blk_d;  // [2][grid][NPART] doubles (ping-pong by ICP iteration parity)
+    double *icp_rec;  // [2][ICP_REC] solve results published by the reducing CTA (ping-pong)
     int *blk_i;     // [grid] ints
     unsigned long long *dbg;  // [64] %globaltimer stamps of CTA 0 (profiling aid)
 };
@@ -72,7 +94,7 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
     return t;
 }
 #define KB_DBG(sc, i) \
-    if (blockIdx.x == 0 && (threadIdx.x & 31) == 0) (sc).dbg[i] = static_cast<unsigned long long>(clock64())
+    if (blockIdx.x == 0 && (threadIdx.x & 31) == 0) (sc).dbg[i] = globaltimer_ns()
 
 struct Grid {
     unsigned *bar;
@@ -98,10 +120,14 @@ struct Grid {
 // ------------------------------------------------------------------------------------------
 // voxel arithmetic
 // ------------------------------------------------------------------------------------------
-// core/VoxelUtils.hpp:33-37 — FP64 DIVISION then floor then int cast (bit-exact with the CPU)
+__device__ __forceinline__ int3 point_to_voxel(double x, double y, double z, const VoxelDiv &d) {
+    if (d.pow2)
+        return make_int3(static_cast<int>(floor(x * d.inv)), static_cast<int>(floor(y * d.inv)),
+                         static_cast<int>(floor(z * d.inv)));
+    return make_int3(static_cast<int>(floor(x / d.v)), static_cast<int>(floor(y / d.v)), static_cast<int>(floor(z / d.v)));
+}
 __device__ __forceinline__ int3 point_to_voxel(double x, double y, double z, double voxel_size) {
-    return make_int3(static_cast<int>(floor(x / voxel_size)), static_cast<int>(floor(y / voxel_size)),
-                     static_cast<int>(floor(z / voxel_size)));
+    return point_to_voxel(x, y, z, make_voxel_div(voxel_size));
 }
 // std::hash<Voxel> core/VoxelUtils.hpp:45-51 — needed ONLY to reproduce VoxelDownsample's
 // output order (robin_map bucket order); the HBM map uses mix_hash below.
@@ -246,7 +272,7 @@ struct WarpNN {
 struct Shared {
     int warp_i[NWARPS + 1];
     int two[2];
-    double warp_d[NWARPS][NACC];
+    double warp_d[NWARPS][NPART];
     double warp_c[NWARPS];
     WarpNN wnn[NWARPS];
     double sys[NACC];
@@ -259,6 +285,7 @@ struct Shared {
     double cand;     // candidate points examined by the last icp_pass (all CTAs)
     double cand_total, query_total;  // summed over the iterations of op_icp
     int flag;
+    int is_last;
 };
 
 __device__ void op_preprocess(Grid &g, const Scratch &sc, Shared &sh, const double *in, int n, const double *ts,
@@ -403,8 +430,9 @@ __device__ void op_downsample(Grid &g, const Scratch &sc, Shared &sh, const doub
     }
     g.sync();
     // (a) dedupe: first input index per voxel
+    const VoxelDiv vd = make_voxel_div(voxel_size);
     for (int i = blockIdx.x * BLOCK + threadIdx.x; i < n; i += gridDim.x * BLOCK) {
-        const int3 v = point_to_voxel(in[3 * i], in[3 * i + 1], in[3 * i + 2], voxel_size);
+        const int3 v = point_to_voxel(in[3 * i], in[3 * i + 1], in[3 * i + 2], vd);
         unsigned h = ref_hash(v.x, v.y, v.z) & mask;
         while (true) {
             int4 s = ds_slots[h];
@@ -512,30 +540,54 @@ struct NNResult {
 };
 
 __device__ __forceinline__ void nn_reduce(double &best, int &bseq, V3 &bp) {
-    // lexicographic (distance, sequence) minimum across the warp
+    // lexicographic (distance, sequence) minimum across the warp, then fetch the winner's point
+    double d = best;
+    int sq = bseq;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
-        const double od = __shfl_xor_sync(FULL, best, o);
-        const int os = __shfl_xor_sync(FULL, bseq, o);
-        const double ox = __shfl_xor_sync(FULL, bp.x, o);
-        const double oy = __shfl_xor_sync(FULL, bp.y, o);
-        const double oz = __shfl_xor_sync(FULL, bp.z, o);
-        if (od < best || (od == best && os < bseq)) {
-            best = od;
-            bseq = os;
-            bp = V3{ox, oy, oz};
+        const double od = __shfl_xor_sync(FULL, d, o);
+        const int os = __shfl_xor_sync(FULL, sq, o);
+        if (od < d || (od == d && os < sq)) {
+            d = od;
+            sq = os;
+        }
+    }
+    // every lane now holds the winning (d, seq); its owner is the unique lane with that seq
+    const unsigned who = __ballot_sync(FULL, bseq == sq && best == d);
+    const int src = who ? (__ffs(who) - 1) : 0;
+    bp.x = __shfl_sync(FULL, bp.x, src);
+    bp.y = __shfl_sync(FULL, bp.y, src);
+    bp.z = __shfl_sync(FULL, bp.z, src);
+    best = d;
+    bseq = sq;
+}
+
+// candidate update with the reference's comparison (first strict minimum of the sqrt'ed norm),
+// computing the ~92-cycle DSQRT only when the squared distance could still win:
+// d2 > best_d2 * (1 + 2^-50) implies sqrt(d2) > sqrt(best_d2) after rounding.
+__device__ __forceinline__ void nn_consider(const V3 &c, const V3 &q, int seq, double &best, double &best_d2, int &bseq,
+                                            V3 &bp) {
+    const V3 df = c - q;
+    const double d2 = sqnorm(df);
+    if (d2 <= best_d2 * (1.0 + 8.8817841970012523e-16)) {
+        const double d = sqrt(d2);
+        if (d < best) {
+            best = d;
+            best_d2 = d2;
+            bseq = seq;
+            bp = c;
         }
     }
 }
 
 __device__ __forceinline__ NNResult nn_search_warp(const MapView &m, const V3 &q, int lane, WarpNN &w) {
-    const int3 v = point_to_voxel(q.x, q.y, q.z, m.voxel_size);
+    const int3 v = point_to_voxel(q.x, q.y, q.z, m.vdiv);
     int cnt = 0, slot = -1;
     if (lane < 27) {
         slot = map_find(m, v.x + c_shifts[lane][0], v.y + c_shifts[lane][1], v.z + c_shifts[lane][2], &cnt);
         if (slot < 0) cnt = 0;
     }
-    double best = DBL_MAX;
+    double best = DBL_MAX, best_d2 = DBL_MAX;
     int bseq = INT_MAX;
     V3 bp{0, 0, 0};
     const int cap = m.cap;
@@ -574,16 +626,8 @@ __device__ __forceinline__ NNResult nn_search_warp(const MapView &m, const V3 &q
                 }
             }
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                if (ok[u]) {
-                    const double d = norm(c[u] - q);
-                    if (d < best) {  // per lane j only grows: strict < keeps the first minimum
-                        best = d;
-                        bseq = base + u * 32 + lane;
-                        bp = c[u];
-                    }
-                }
-            }
+            for (int u = 0; u < U; ++u)
+                if (ok[u]) nn_consider(c[u], q, base + u * 32 + lane, best, best_d2, bseq, bp);
         }
     } else {
         // general path: walk the occupied voxels one after the other
@@ -596,15 +640,8 @@ __device__ __forceinline__ NNResult nn_search_warp(const MapView &m, const V3 &q
             const int s = __shfl_sync(FULL, slot, vi);
             total += c;
             const double *blk = m.points + static_cast<size_t>(s) * cap * 3;
-            for (int k = lane; k < c; k += 32) {
-                const V3 p{blk[3 * k], blk[3 * k + 1], blk[3 * k + 2]};
-                const double d = norm(p - q);
-                if (d < best) {
-                    best = d;
-                    bseq = vi * 1024 + k;
-                    bp = p;
-                }
-            }
+            for (int k = lane; k < c; k += 32)
+                nn_consider(V3{blk[3 * k], blk[3 * k + 1], blk[3 * k + 2]}, q, vi * 1024 + k, best, best_d2, bseq, bp);
         }
     }
     nn_reduce(best, bseq, bp);
@@ -672,13 +709,12 @@ __device__ __forceinline__ void icp_expand(const double a[NACC], double JTJ[36],
     for (int i = 0; i < 6; ++i) JTr[i] = a[10 + i];
 }
 
-// one DataAssociation + BuildLinearSystem pass over the grid (Registration.cpp:60-121).
-// `pending` is applied to every source point first (TransformPoints, :55-58) and the moved
-// point is written back to `work`. Result: sh.sys[NACC] identical in every CTA (fixed
-// reduction order: query-strided per warp -> warps in order -> CTAs in order).
-__device__ void icp_pass(Grid &g, const Scratch &sc, Shared &sh, const MapView &m, const double *src, double *work,
-                         int n, const SE3 &pending, double max_dist, double kscale, int parity, int *n_corr,
-                         bool dbg_on = false) {
+// One DataAssociation + BuildLinearSystem pass of THIS CTA (Registration.cpp:60-121): `pending`
+// is applied to every source point first (TransformPoints, :55-58), the moved point is written
+// back to `work`, and the CTA's partial normal equations go to blk_d[parity][cta][NPART].
+// Reduction order is fixed: query-strided per warp -> 16-warp shuffle tree -> CTAs in order.
+__device__ void icp_queries(const Scratch &sc, Shared &sh, const MapView &m, const double *src, double *work, int n,
+                            const SE3 &pending, double max_dist, double kscale, int parity, bool dbg_on) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (dbg_on && warp == 0) KB_DBG(sc, 0);
     const int gwarp = blockIdx.x * NWARPS + warp, nwarps = gridDim.x * NWARPS;
@@ -701,35 +737,40 @@ __device__ void icp_pass(Grid &g, const Scratch &sc, Shared &sh, const MapView &
         }
     }
     if (dbg_on && warp == 0) KB_DBG(sc, 1);
-    if (dbg_on && warp == NWARPS - 1) KB_DBG(sc, 7);
     if (lane < NACC) sh.warp_d[warp][lane] = acc;
-    if (lane == 0) {
-        sh.warp_i[warp] = corr;
-        sh.warp_c[warp] = cand;
-    }
+    if (lane == NACC) sh.warp_d[warp][NACC] = static_cast<double>(corr);
+    if (lane == NACC + 1) sh.warp_d[warp][NACC + 1] = cand;
     __syncthreads();
     if (dbg_on && warp == 0) KB_DBG(sc, 2);
-    double *mine = sc.blk_d + (static_cast<size_t>(parity) * gridDim.x + blockIdx.x) * NPART;
-    if (threadIdx.x < NACC) {
-        double s = 0.0;
+    // 16-warp tree per value: thread t -> value t/16, warp t%16 (NWARPS == 16)
+    if (threadIdx.x < NPART * NWARPS) {
+        double v = sh.warp_d[threadIdx.x & (NWARPS - 1)][threadIdx.x / NWARPS];
 #pragma unroll
-        for (int w = 0; w < NWARPS; ++w) s += sh.warp_d[w][threadIdx.x];
-        mine[threadIdx.x] = s;
-    } else if (threadIdx.x == NACC) {
-        int c = 0;
-        for (int w = 0; w < NWARPS; ++w) c += sh.warp_i[w];
-        mine[NACC] = static_cast<double>(c);
-    } else if (threadIdx.x == NACC + 1) {
-        double c = 0.0;
-        for (int w = 0; w < NWARPS; ++w) c += sh.warp_c[w];
-        mine[NACC + 1] = c;
+        for (int o = NWARPS / 2; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+        if ((threadIdx.x & (NWARPS - 1)) == 0)
+            sc.blk_d[(static_cast<size_t>(parity) * gridDim.x + blockIdx.x) * NPART + threadIdx.x / NWARPS] = v;
     }
     if (dbg_on && warp == 0) KB_DBG(sc, 3);
-    g.sync();
-    if (dbg_on && warp == 0) KB_DBG(sc, 4);
-    // every CTA reduces all partials in the same order -> bitwise identical systems everywhere
+}
+
+// arrival at the per-iteration rendezvous; true in exactly one CTA: the last one to arrive.
+__device__ __forceinline__ bool icp_arrive(const Scratch &sc, Shared &sh, unsigned epoch) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned old = atomicAdd(&sc.bar[1], 1u);
+        sh.is_last = (old == epoch * gridDim.x - 1u) ? 1 : 0;
+        __threadfence();
+    }
+    __syncthreads();
+    return sh.is_last != 0;
+}
+
+// the reducing CTA sums the partials of all CTAs in CTA order -> sh.sys, sh.two[0], sh.cand
+__device__ __forceinline__ void icp_reduce(const Scratch &sc, Shared &sh, int parity) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const double *all = sc.blk_d + static_cast<size_t>(parity) * gridDim.x * NPART;
-    for (int e = warp; e < NPART; e += NWARPS) {  // one value per warp (two for warps 0,1)
+    for (int e = warp; e < NPART; e += NWARPS) {
         double s = 0.0;
         for (int b = lane; b < static_cast<int>(gridDim.x); b += 32) s += __ldcg(&all[static_cast<size_t>(b) * NPART + e]);
 #pragma unroll
@@ -744,18 +785,30 @@ __device__ void icp_pass(Grid &g, const Scratch &sc, Shared &sh, const MapView &
         }
     }
     __syncthreads();
-    if (dbg_on && warp == 0) KB_DBG(sc, 5);
-    if (n_corr) *n_corr = sh.two[0];
 }
 
 // ------------------------------------------------------------------------------------------
-// op_icp — Registration::AlignPointsToMap (core/Registration.cpp:138-167), device resident:
-//   no host round trip per iteration, ONE grid barrier per iteration; every CTA solves the
-//   6x6 redundantly (identical inputs, identical code) so no broadcast step is needed.
+// op_icp — Registration::AlignPointsToMap (core/Registration.cpp:138-167), device resident.
+//   Per iteration: every CTA runs its queries and posts a partial system; the LAST CTA to arrive
+//   (one L2 atomic) reduces the partials in fixed CTA order, solves the 6x6, updates T_icp and
+//   publishes {estimation, T_icp, converged} with a release store; everyone else spins on the
+//   publish epoch. One rendezvous per iteration, no host round trip, no 148-way re-read of the
+//   partials, and the result is independent of which CTA happened to arrive last.
 // ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void rec_store_se3(double *r, const SE3 &T) {
+    r[0] = T.q.x; r[1] = T.q.y; r[2] = T.q.z; r[3] = T.q.w; r[4] = T.t.x; r[5] = T.t.y; r[6] = T.t.z;
+}
+__device__ __forceinline__ SE3 rec_load_se3(const double *r) {
+    return SE3{{__ldcg(r), __ldcg(r + 1), __ldcg(r + 2), __ldcg(r + 3)}, {__ldcg(r + 4), __ldcg(r + 5), __ldcg(r + 6)}};
+}
+__device__ __forceinline__ void st_release_u32(unsigned *p, unsigned v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
 __device__ void op_icp(Grid &g, const Scratch &sc, Shared &sh, const MapView &m, const double *src, double *work,
                        int n, const SE3 &guess, double max_dist, double kscale, int max_iter, double conv) {
-    if (__ldcg(&m.counters[C_LIVE]) == 0) {  // voxel_map.Empty() -> return initial_guess (:143)
+    (void)g;
+    if (__ldcg(&m.counters[C_LIVE]) == 0 || max_iter <= 0) {  // voxel_map.Empty() -> initial_guess (:143)
         __syncthreads();
         if (threadIdx.x == 0) {
             sh.result = guess;
@@ -766,42 +819,62 @@ __device__ void op_icp(Grid &g, const Scratch &sc, Shared &sh, const MapView &m,
         __syncthreads();
         return;
     }
-    if (threadIdx.x == 0) {
-        sh.pending = guess;
-        sh.t_icp = se3_identity();
-        sh.flag = 0;
-        sh.cand_total = 0.0;
-        sh.query_total = 0.0;
-    }
-    __syncthreads();
+    SE3 pending = guess;
     int j = 0;
-    for (; j < max_iter; ++j) {
-        const SE3 pending = sh.pending;
-        icp_pass(g, sc, sh, m, j == 0 ? src : work, work, n, pending, max_dist, kscale, j & 1, nullptr, j == 1);
+    for (;; ++j) {
+        const int parity = j & 1;
+        const bool dbg_on = (j == 1);
+        icp_queries(sc, sh, m, j == 0 ? src : work, work, n, pending, max_dist, kscale, parity, dbg_on);
+        const unsigned epoch = static_cast<unsigned>(j) + 1u;
+        const bool last = icp_arrive(sc, sh, epoch);
+        double *rec = sc.icp_rec + parity * ICP_REC;
+        if (last) {
+            if (dbg_on && threadIdx.x == 0) sc.dbg[4] = globaltimer_ns();
+            icp_reduce(sc, sh, parity);
+            if (threadIdx.x == 0) {
+                if (dbg_on) sc.dbg[5] = globaltimer_ns();
+                const double *prev = sc.icp_rec + (parity ^ 1) * ICP_REC;
+                const SE3 t_prev = (j == 0) ? se3_identity() : rec_load_se3(prev + 7);
+                const double cand_prev = (j == 0) ? 0.0 : __ldcg(prev + 22);
+                double JTJ[36], JTr[6], rhs[6], dx[6];
+                icp_expand(sh.sys, JTJ, JTr);
+#pragma unroll
+                for (int i = 0; i < 6; ++i) rhs[i] = -JTr[i];
+                ldlt6_solve_fast(JTJ, rhs, dx);                 // :156
+                const SE3 est = se3_exp_fast(dx);               // :157
+                const SE3 t_icp = se3_mul_fast(est, t_prev);    // :161
+                double n2 = 0.0;
+#pragma unroll
+                for (int i = 0; i < 6; ++i) n2 += dx[i] * dx[i];
+                const bool done = (sqrt(n2) < conv) || (j + 1 >= max_iter);  // :163 / :151
+                rec_store_se3(rec, est);
+                rec_store_se3(rec + 7, t_icp);
+                if (done) rec_store_se3(rec + 14, se3_mul(t_icp, guess));  // :166
+                rec[21] = done ? 1.0 : 0.0;
+                rec[22] = cand_prev + sh.cand;
+                if (dbg_on) sc.dbg[6] = globaltimer_ns();
+                __threadfence();
+                st_release_u32(&sc.bar[2], epoch);
+            }
+        }
         if (threadIdx.x == 0) {
-            double JTJ[36], JTr[6], rhs[6], dx[6];
-            icp_expand(sh.sys, JTJ, JTr);
-            for (int i = 0; i < 6; ++i) rhs[i] = -JTr[i];
-            ldlt6_solve_reg(JTJ, rhs, dx);           // :156
-            const SE3 est = se3_exp(dx);             // :157
-            sh.t_icp = se3_mul(est, sh.t_icp);       // :161
-            sh.pending = est;                        // applied lazily at the next pass (:159)
-            double n2 = 0.0;
-            for (int i = 0; i < 6; ++i) n2 += dx[i] * dx[i];
-            sh.flag = (sqrt(n2) < conv) ? 1 : 0;     // :163
-            sh.cand_total += sh.cand;
-            sh.query_total += static_cast<double>(n);
-            if (j == 1 && blockIdx.x == 0) sc.dbg[6] = static_cast<unsigned long long>(clock64());
+            while (ld_acquire_u32(&sc.bar[2]) < epoch) {
+            }
+            __threadfence();
+            sh.pending = rec_load_se3(rec);
+            sh.flag = __ldcg(rec + 21) != 0.0 ? 1 : 0;
+            if (dbg_on) KB_DBG(sc, 7);
         }
         __syncthreads();
-        if (sh.flag) {
-            ++j;
-            break;
-        }
+        pending = sh.pending;
+        if (sh.flag) break;
     }
+    const double *rec = sc.icp_rec + (j & 1) * ICP_REC;
     if (threadIdx.x == 0) {
-        sh.result = se3_mul(sh.t_icp, guess);  // :166
-        sh.iters = j;
+        sh.result = rec_load_se3(rec + 14);
+        sh.iters = j + 1;
+        sh.cand_total = __ldcg(rec + 22);
+        sh.query_total = static_cast<double>(n) * (j + 1);
     }
     __syncthreads();
 }
@@ -822,7 +895,7 @@ __device__ void op_map_add(Grid &g, Shared &sh, const MapView &m, const double *
         tp[3 * i] = p.x;
         tp[3 * i + 1] = p.y;
         tp[3 * i + 2] = p.z;
-        const int3 v = point_to_voxel(p.x, p.y, p.z, m.voxel_size);
+        const int3 v = point_to_voxel(p.x, p.y, p.z, m.vdiv);
         const int s = map_find_or_claim(m, v.x, v.y, v.z);
         if (s < 0) {
             next[i] = -1;

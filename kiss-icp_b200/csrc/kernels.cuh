@@ -214,11 +214,13 @@ __global__ void __launch_bounds__(BLOCK, 1) k_icp(const IcpParams P) {
     Grid g;
     g.init(P.sc.bar);
     if (P.system_only) {
-        int nc = 0;
-        icp_pass(g, P.sc, sh, P.m, P.src, P.work, P.n, se3_identity(), P.max_dist, P.kscale, 0, &nc);
-        if (blockIdx.x == 0 && threadIdx.x == 0) {
-            for (int i = 0; i < NACC; ++i) P.out_sys[i] = sh.sys[i];
-            *P.out_ncorr = nc;
+        icp_queries(P.sc, sh, P.m, P.src, P.work, P.n, se3_identity(), P.max_dist, P.kscale, 0, false);
+        if (icp_arrive(P.sc, sh, 1u)) {
+            icp_reduce(P.sc, sh, 0);
+            if (threadIdx.x == 0) {
+                for (int i = 0; i < NACC; ++i) P.out_sys[i] = sh.sys[i];
+                *P.out_ncorr = sh.two[0];
+            }
         }
         return;
     }

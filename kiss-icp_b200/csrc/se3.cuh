@@ -513,4 +513,142 @@ KB_HD void ldlt6_solve_reg(const double A_in[36], const double b[6], double x[6]
     for (int i = 0; i < N; ++i) x[i] = d[i];
 }
 
+// ---- latency-optimised variants for the ICP inner loop -------------------------------------
+// The ICP solve is a single-thread dependent chain executed once per iteration; on B200 a
+// DDIV costs ~131 cycles, DSQRT ~92, sin/cos ~255 against 8.5 for DADD/DMUL (measured,
+// tools/latency_probe.cu). These variants use ONE reciprocal where the exact forms divide
+// several times, and one sincos(theta/2) with double-angle identities instead of four
+// separate sin/cos calls. They differ from the exact forms by a few ulps (tests bound the
+// difference at 1e-13 relative) — far inside the 1e-4 m / 1e-4 rad parity budget.
+template <int K>
+KB_HD bool ldlt6_step_fast(double (&mat)[6][6], int (&tr)[6], double (&inv)[6]) {
+    constexpr int N = 6;
+    int big = K;
+    double best = fabs(mat[K][K]);
+#pragma unroll
+    for (int i = K + 1; i < N; ++i) {
+        const double v = fabs(mat[i][i]);
+        if (v > best) {
+            best = v;
+            big = i;
+        }
+    }
+    tr[K] = big;
+    if (K + 1 < N && big == K + 1) ldlt6_swap<K, (K + 1 < N ? K + 1 : K)>(mat);
+    if (K + 2 < N && big == K + 2) ldlt6_swap<K, (K + 2 < N ? K + 2 : K)>(mat);
+    if (K + 3 < N && big == K + 3) ldlt6_swap<K, (K + 3 < N ? K + 3 : K)>(mat);
+    if (K + 4 < N && big == K + 4) ldlt6_swap<K, (K + 4 < N ? K + 4 : K)>(mat);
+    if (K + 5 < N && big == K + 5) ldlt6_swap<K, (K + 5 < N ? K + 5 : K)>(mat);
+    constexpr int RS = N - K - 1;
+    if (K > 0) {
+        double temp[6];
+#pragma unroll
+        for (int j = 0; j < K; ++j) temp[j] = mat[j][j] * mat[K][j];
+        double acc = 0.0;
+#pragma unroll
+        for (int j = 0; j < K; ++j) acc += mat[K][j] * temp[j];
+        mat[K][K] -= acc;
+#pragma unroll
+        for (int i = 0; i < RS; ++i) {
+            double a2 = 0.0;
+#pragma unroll
+            for (int j = 0; j < K; ++j) a2 += mat[K + 1 + i][j] * temp[j];
+            mat[K + 1 + i][K] -= a2;
+        }
+    }
+    const double akk = mat[K][K];
+    const bool valid = fabs(akk) > 0.0;
+    if (K == 0 && !valid) return false;
+    const double r = valid ? 1.0 / akk : 0.0;
+    inv[K] = (fabs(akk) > DBL_MIN) ? r : 0.0;  // D^+ of the solve (pivots <= DBL_MIN give 0)
+    if (RS > 0 && valid) {
+#pragma unroll
+        for (int i = 0; i < RS; ++i) mat[K + 1 + i][K] *= r;
+    }
+    return true;
+}
+
+KB_HD void ldlt6_solve_fast(const double A_in[36], const double b[6], double x[6]) {
+    constexpr int N = 6;
+    double mat[6][6];
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+#pragma unroll
+        for (int j = 0; j < N; ++j) mat[i][j] = A_in[N * i + j];
+    int tr[6] = {0, 1, 2, 3, 4, 5};
+    double inv[6] = {0, 0, 0, 0, 0, 0};
+    if (ldlt6_step_fast<0>(mat, tr, inv)) {
+        ldlt6_step_fast<1>(mat, tr, inv);
+        ldlt6_step_fast<2>(mat, tr, inv);
+        ldlt6_step_fast<3>(mat, tr, inv);
+        ldlt6_step_fast<4>(mat, tr, inv);
+        ldlt6_step_fast<5>(mat, tr, inv);
+    } else {
+        tr[0] = 0;
+    }
+    double d[6];
+#pragma unroll
+    for (int i = 0; i < N; ++i) d[i] = b[i];
+    ldlt6_apply_tr<0>(d, tr[0]);
+    ldlt6_apply_tr<1>(d, tr[1]);
+    ldlt6_apply_tr<2>(d, tr[2]);
+    ldlt6_apply_tr<3>(d, tr[3]);
+    ldlt6_apply_tr<4>(d, tr[4]);
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        double acc = d[i];
+#pragma unroll
+        for (int j = 0; j < i; ++j) acc -= mat[i][j] * d[j];
+        d[i] = acc;
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i) d[i] *= inv[i];
+#pragma unroll
+    for (int i = N - 1; i >= 0; --i) {
+        double acc = d[i];
+#pragma unroll
+        for (int j = i + 1; j < N; ++j) acc -= mat[j][i] * d[j];
+        d[i] = acc;
+    }
+    ldlt6_apply_tr<4>(d, tr[4]);
+    ldlt6_apply_tr<3>(d, tr[3]);
+    ldlt6_apply_tr<2>(d, tr[2]);
+    ldlt6_apply_tr<1>(d, tr[1]);
+    ldlt6_apply_tr<0>(d, tr[0]);
+#pragma unroll
+    for (int i = 0; i < N; ++i) x[i] = d[i];
+}
+
+KB_HD SE3 se3_exp_fast(const double a[6]) {
+    const V3 upsilon{a[0], a[1], a[2]};
+    const V3 omega{a[3], a[4], a[5]};
+    const double theta_sq = sqnorm(omega);
+    SE3 r;
+    if (theta_sq < kEps * kEps) return se3_exp(a);
+    const double theta = sqrt(theta_sq);
+    const double inv_theta = 1.0 / theta;
+    double sh, ch;
+    sincos(0.5 * theta, &sh, &ch);
+    const double imag = sh * inv_theta;
+    r.q = Q4{imag * omega.x, imag * omega.y, imag * omega.z, ch};
+    // (1 - cos t)/t^2 = 2 sin^2(t/2)/t^2 ;  (t - sin t)/t^3 with sin t = 2 sin(t/2) cos(t/2)
+    const double ca = 2.0 * imag * imag;
+    const double cb = (theta - 2.0 * sh * ch) * (inv_theta * inv_theta * inv_theta);
+    r.t = apply_I_aW_bW2(omega, ca, cb, true, upsilon);
+    return r;
+}
+
+KB_HD SE3 se3_mul_fast(const SE3 &a, const SE3 &b) {
+    Q4 q;
+    q.w = a.q.w * b.q.w - a.q.x * b.q.x - a.q.y * b.q.y - a.q.z * b.q.z;
+    q.x = a.q.w * b.q.x + a.q.x * b.q.w + a.q.y * b.q.z - a.q.z * b.q.y;
+    q.y = a.q.w * b.q.y + a.q.y * b.q.w + a.q.z * b.q.x - a.q.x * b.q.z;
+    q.z = a.q.w * b.q.z + a.q.z * b.q.w + a.q.x * b.q.y - a.q.y * b.q.x;
+    const double inv_len = 1.0 / sqrt(((q.x * q.x + q.y * q.y) + q.z * q.z) + q.w * q.w);
+    SE3 r;
+    r.q = Q4{q.x * inv_len, q.y * inv_len, q.z * inv_len, q.w * inv_len};
+    r.t = a.t + q_rotate(a.q, b.t);
+    return r;
+}
+
 }  // namespace kb

@@ -110,3 +110,23 @@ def test_device_ldlt_variants_agree_with_oracle(O):
         N.check(N.lib().kb_debug_ldlt6(N.ptr(A), N.ptr(b), N.ptr(x1), N.ptr(x2)))
         assert np.array_equal(x1, x2)
         assert np.array_equal(x1, O.ldlt6_solve(A, b))
+
+
+def test_fast_icp_solve_variants_stay_within_ulps_of_exact():
+    """ldlt6_solve_fast / se3_exp_fast / se3_mul_fast (one reciprocal instead of many divisions,
+    sincos + double-angle identities) vs the exact forms, evaluated on the host"""
+    from kiss_icp_b200 import _native as N
+    rng = np.random.default_rng(9)
+    for scale in (1e-6, 1e-3, 0.05, 0.5):
+        for _ in range(20):
+            J = rng.normal(size=(50, 6)) * rng.choice([0.1, 1.0, 30.0], size=6)
+            A = np.ascontiguousarray(J.T @ J)
+            b = np.ascontiguousarray(A @ (rng.normal(size=6) * scale))
+            xe, xf, Te, Tf = np.empty(6), np.empty(6), np.empty((4, 4)), np.empty((4, 4))
+            N.check(N.lib().kb_debug_icp_solve(N.ptr(A), N.ptr(b), N.ptr(xe), N.ptr(xf), N.ptr(Te), N.ptr(Tf)))
+            assert np.allclose(xf, xe, rtol=1e-11, atol=1e-13 * np.abs(xe).max())
+            assert np.abs(Tf - Te).max() < 1e-12 * max(1.0, np.abs(Te).max())
+    A = np.zeros((6, 6)); b = np.ones(6)
+    xe, xf, Te, Tf = np.empty(6), np.empty(6), np.empty((4, 4)), np.empty((4, 4))
+    N.check(N.lib().kb_debug_icp_solve(N.ptr(A), N.ptr(b), N.ptr(xe), N.ptr(xf), N.ptr(Te), N.ptr(Tf)))
+    assert not xe.any() and not xf.any()
