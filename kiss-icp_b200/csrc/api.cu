@@ -121,11 +121,19 @@ struct Exec {
         if (own_stream && stream) cudaStreamDestroy(stream);
     }
     template <class P>
-    int coop(void (*kern)(P), const P &p) {
+    int coop(void (*kern)(P), const P &p, size_t smem = 0) {
         CK(cudaSetDevice(device));
+        if (smem > 48 * 1024) {  // opt in to large dynamic shared memory once per kernel
+            static thread_local std::vector<const void *> done;
+            const void *k = reinterpret_cast<const void *>(kern);
+            if (std::find(done.begin(), done.end(), k) == done.end()) {
+                CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+                done.push_back(k);
+            }
+        }
         CK(cudaMemsetAsync(sc.bar, 0, 4 * sizeof(unsigned), stream));
         void *args[] = {const_cast<P *>(&p)};
-        CK(cudaLaunchCooperativeKernel(reinterpret_cast<const void *>(kern), dim3(grid), dim3(BLOCK), args, 0, stream));
+        CK(cudaLaunchCooperativeKernel(reinterpret_cast<const void *>(kern), dim3(grid), dim3(BLOCK), args, smem, stream));
         ++launches;
         return KB_OK;
     }
@@ -679,7 +687,8 @@ static int registration_run(kb_registration *reg, const double *xyz, size_t n, k
     P.system_only = system_only ? 1 : 0;
     P.out_sys = reg->out.p + 16;
     P.out_ncorr = reg->iout.p + 1;
-    return ex.coop(k_icp, P);
+    P.use_qcache = system_only ? 0 : 1;
+    return ex.coop(k_icp, P, system_only ? 0 : QC_BYTES);
 }
 int kb_registration_align_points_to_map(kb_registration *reg, const double *xyz, size_t n, const kb_map *cmap,
                                         const double initial_guess[16], double max_correspondence_distance,
@@ -924,7 +933,8 @@ static int pipeline_run(kb_pipeline *p, const double *d_xyz, size_t n, const dou
     P.max_iter = p->cfg.max_num_iterations;
     P.conv = p->cfg.convergence_criterion;
     P.min_motion_th = p->cfg.min_motion_th;
-    RET(ex.coop(k_register_frame, P));
+    P.use_qcache = 1;
+    RET(ex.coop(k_register_frame, P, QC_BYTES));
     CK(cudaMemcpyAsync(p->h_res, p->d_res, sizeof(FrameResult), cudaMemcpyDeviceToHost, ex.stream));
     RET(ex.sync());
     p->last = *p->h_res;

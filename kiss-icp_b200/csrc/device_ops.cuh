@@ -82,6 +82,11 @@ struct Scratch {
 // ------------------------------------------------------------------------------------------
 // grid barrier (all CTAs co-resident: cooperative launch)
 // ------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned *p) {
+    unsigned v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p) {
     unsigned v;
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -269,6 +274,21 @@ struct WarpNN {
     int start[27];
 };
 
+// Per-warp cache of a query's whole 27-voxel neighbourhood (dynamic shared memory, 2 slots per
+// warp = the first two queries a warp owns). The map is immutable during AlignPointsToMap and
+// after the first iterations a source point almost never leaves its voxel, so from then on a
+// query costs no global memory traffic at all: point, candidates and their order come from
+// shared memory (~30-cycle LDS instead of ~300-cycle L2 round trips).
+constexpr int QC_MAX = 256;   // candidates cached per query (p99 of a 20-pt/voxel map ~250-310)
+constexpr int QC_SLOTS = 2;   // cached queries per warp
+struct QCache {
+    int vx, vy, vz;  // voxel the cache was filled for
+    int total;       // cached candidates, -1 = invalid
+    double p[3];     // the source point, carried across iterations
+    double pts[QC_MAX][3];
+};
+constexpr size_t QC_BYTES = sizeof(QCache) * QC_SLOTS * NWARPS;
+
 struct Shared {
     int warp_i[NWARPS + 1];
     int two[2];
@@ -288,7 +308,7 @@ struct Shared {
     int is_last;
 };
 
-__device__ void op_preprocess(Grid &g, const Scratch &sc, Shared &sh, const double *in, int n, const double *ts,
+__device__ __noinline__ void op_preprocess(Grid &g, const Scratch &sc, Shared &sh, const double *in, int n, const double *ts,
                               int n_ts, bool deskew, const SE3 &motion, double max_range, double min_range,
                               double *tmp, double *out, int *out_n) {
     const bool do_deskew = deskew && n_ts > 0;
@@ -414,7 +434,7 @@ struct DsScratch {
     int2 *sim;     // [B] replayed robin-hood layout {first index (-1 empty), home offset in run}
 };
 
-__device__ void op_downsample(Grid &g, const Scratch &sc, Shared &sh, const double *in, int n, double voxel_size,
+__device__ __noinline__ void op_downsample(Grid &g, const Scratch &sc, Shared &sh, const double *in, int n, double voxel_size,
                               const DsScratch &ds, double *out, int *out_n) {
     const unsigned B = robin_bucket_count(n);
     if (B == 0) {
@@ -580,7 +600,19 @@ __device__ __forceinline__ void nn_consider(const V3 &c, const V3 &q, int seq, d
     }
 }
 
-__device__ __forceinline__ NNResult nn_search_warp(const MapView &m, const V3 &q, int lane, WarpNN &w) {
+// nearest neighbour among the candidates cached in shared memory (same order, same comparison)
+__device__ __forceinline__ NNResult nn_search_cached(const QCache &qc, const V3 &q, int lane) {
+    double best = DBL_MAX, best_d2 = DBL_MAX;
+    int bseq = INT_MAX;
+    V3 bp{0, 0, 0};
+    const int total = qc.total;
+    for (int j = lane; j < total; j += 32) nn_consider(V3{qc.pts[j][0], qc.pts[j][1], qc.pts[j][2]}, q, j, best, best_d2, bseq, bp);
+    nn_reduce(best, bseq, bp);
+    return NNResult{best, bp, total};
+}
+
+__device__ __forceinline__ NNResult nn_search_warp(const MapView &m, const V3 &q, int lane, WarpNN &w,
+                                                   QCache *fill = nullptr) {
     const int3 v = point_to_voxel(q.x, q.y, q.z, m.vdiv);
     int cnt = 0, slot = -1;
     if (lane < 27) {
@@ -611,6 +643,13 @@ __device__ __forceinline__ NNResult nn_search_warp(const MapView &m, const V3 &q
             for (int k = 0; k < cnt; ++k) w.owner[start + k] = static_cast<unsigned char>(lane);
         }
         __syncwarp();
+        const bool do_fill = fill != nullptr && total <= QC_MAX;
+        if (fill != nullptr && lane == 0) {
+            fill->vx = v.x;
+            fill->vy = v.y;
+            fill->vz = v.z;
+            fill->total = do_fill ? total : -1;
+        }
         constexpr int U = 4;
         for (int base = 0; base < total; base += 32 * U) {
             V3 c[U];
@@ -627,7 +666,15 @@ __device__ __forceinline__ NNResult nn_search_warp(const MapView &m, const V3 &q
             }
 #pragma unroll
             for (int u = 0; u < U; ++u)
-                if (ok[u]) nn_consider(c[u], q, base + u * 32 + lane, best, best_d2, bseq, bp);
+                if (ok[u]) {
+                    const int j = base + u * 32 + lane;
+                    if (do_fill) {
+                        fill->pts[j][0] = c[u].x;
+                        fill->pts[j][1] = c[u].y;
+                        fill->pts[j][2] = c[u].z;
+                    }
+                    nn_consider(c[u], q, j, best, best_d2, bseq, bp);
+                }
         }
     } else {
         // general path: walk the occupied voxels one after the other
@@ -643,7 +690,9 @@ __device__ __forceinline__ NNResult nn_search_warp(const MapView &m, const V3 &q
             for (int k = lane; k < c; k += 32)
                 nn_consider(V3{blk[3 * k], blk[3 * k + 1], blk[3 * k + 2]}, q, vi * 1024 + k, best, best_d2, bseq, bp);
         }
+        if (fill != nullptr && lane == 0) fill->total = -1;
     }
+    __syncwarp();
     nn_reduce(best, bseq, bp);
     return NNResult{best, bp, total};
 }
@@ -713,23 +762,47 @@ __device__ __forceinline__ void icp_expand(const double a[NACC], double JTJ[36],
 // is applied to every source point first (TransformPoints, :55-58), the moved point is written
 // back to `work`, and the CTA's partial normal equations go to blk_d[parity][cta][NPART].
 // Reduction order is fixed: query-strided per warp -> 16-warp shuffle tree -> CTAs in order.
-__device__ void icp_queries(const Scratch &sc, Shared &sh, const MapView &m, const double *src, double *work, int n,
-                            const SE3 &pending, double max_dist, double kscale, int parity, bool dbg_on) {
+__device__ __noinline__ void icp_queries(const Scratch &sc, Shared &sh, const MapView &m, const double *src, double *work, int n,
+                            const SE3 &pending, double max_dist, double kscale, int parity, bool dbg_on,
+                            QCache *qcache = nullptr, bool first = true) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (dbg_on && warp == 0) KB_DBG(sc, 0);
     const int gwarp = blockIdx.x * NWARPS + warp, nwarps = gridDim.x * NWARPS;
     double acc = 0.0;  // lane l < 16 owns accumulator l
     int corr = 0;
     double cand = 0.0;
-    for (int qi = gwarp; qi < n; qi += nwarps) {
-        V3 p{src[3 * qi], src[3 * qi + 1], src[3 * qi + 2]};
+    int k = 0;
+    for (int qi = gwarp; qi < n; qi += nwarps, ++k) {
+        QCache *qc = (qcache != nullptr && k < QC_SLOTS) ? &qcache[warp * QC_SLOTS + k] : nullptr;
+        V3 p;
+        if (qc != nullptr && !first)
+            p = V3{qc->p[0], qc->p[1], qc->p[2]};
+        else
+            p = V3{src[3 * qi], src[3 * qi + 1], src[3 * qi + 2]};
         p = se3_act(pending, p);
-        if (lane == 0) {
-            work[3 * qi] = p.x;
-            work[3 * qi + 1] = p.y;
-            work[3 * qi + 2] = p.z;
+        NNResult r;
+        if (qc != nullptr) {
+            __syncwarp();
+            if (lane == 0) {
+                qc->p[0] = p.x;
+                qc->p[1] = p.y;
+                qc->p[2] = p.z;
+                if (first) qc->total = -1;
+            }
+            __syncwarp();
+            const int3 v = point_to_voxel(p.x, p.y, p.z, m.vdiv);
+            if (qc->total >= 0 && qc->vx == v.x && qc->vy == v.y && qc->vz == v.z)
+                r = nn_search_cached(*qc, p, lane);
+            else
+                r = nn_search_warp(m, p, lane, sh.wnn[warp], qc);
+        } else {
+            if (lane == 0) {
+                work[3 * qi] = p.x;
+                work[3 * qi + 1] = p.y;
+                work[3 * qi + 2] = p.z;
+            }
+            r = nn_search_warp(m, p, lane, sh.wnn[warp]);
         }
-        const NNResult r = nn_search_warp(m, p, lane, sh.wnn[warp]);
         cand += r.candidates;
         if (r.d < max_dist) {
             acc += icp_term(lane, p, r.p, kscale);
@@ -757,31 +830,54 @@ __device__ void icp_queries(const Scratch &sc, Shared &sh, const MapView &m, con
 __device__ __forceinline__ bool icp_arrive(const Scratch &sc, Shared &sh, unsigned epoch) {
     __syncthreads();
     if (threadIdx.x == 0) {
-        __threadfence();
-        const unsigned old = atomicAdd(&sc.bar[1], 1u);
+        unsigned old;  // release: our partial is visible before the arrival; acquire: the last arriver sees all partials
+        asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(old) : "l"(&sc.bar[1]) : "memory");
         sh.is_last = (old == epoch * gridDim.x - 1u) ? 1 : 0;
-        __threadfence();
     }
     __syncthreads();
     return sh.is_last != 0;
 }
 
-// the reducing CTA sums the partials of all CTAs in CTA order -> sh.sys, sh.two[0], sh.cand
+// the reducing CTA sums the partials of all CTAs in a fixed order -> sh.sys, sh.two[0], sh.cand.
+// All loads of a lane are issued before the first add (memory-level parallelism: one L2 round
+// trip instead of one per partial); grids larger than 32*RMAX CTAs take extra rounds.
 __device__ __forceinline__ void icp_reduce(const Scratch &sc, Shared &sh, int parity) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const double *all = sc.blk_d + static_cast<size_t>(parity) * gridDim.x * NPART;
-    for (int e = warp; e < NPART; e += NWARPS) {
-        double s = 0.0;
-        for (int b = lane; b < static_cast<int>(gridDim.x); b += 32) s += __ldcg(&all[static_cast<size_t>(b) * NPART + e]);
+    constexpr int RMAX = 8;
+    const int nb = static_cast<int>(gridDim.x);
+    // warp w reduces value w, and (w < NPART - NWARPS) also value w + NWARPS, interleaved
+    const int e0 = warp, e1 = warp + NWARPS;
+    const bool two = e1 < NPART;
+    double s0 = 0.0, s1 = 0.0;
+    for (int base = 0; base < nb; base += 32 * RMAX) {
+        double v0[RMAX], v1[RMAX];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
-        if (lane == 0) {
-            if (e < NACC)
-                sh.sys[e] = s;
-            else if (e == NACC)
-                sh.two[0] = static_cast<int>(s);
-            else
-                sh.cand = s;
+        for (int r = 0; r < RMAX; ++r) {
+            const int b = base + r * 32 + lane;
+            v0[r] = (b < nb) ? __ldcg(&all[static_cast<size_t>(b) * NPART + e0]) : 0.0;
+            v1[r] = (two && b < nb) ? __ldcg(&all[static_cast<size_t>(b) * NPART + e1]) : 0.0;
+        }
+#pragma unroll
+        for (int r = 0; r < RMAX; ++r) {
+            s0 += v0[r];
+            s1 += v1[r];
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s0 += __shfl_xor_sync(FULL, s0, o);
+        s1 += __shfl_xor_sync(FULL, s1, o);
+    }
+    if (lane == 0) {
+        if (e0 < NACC) sh.sys[e0] = s0;
+        if (two) {
+            if (e1 == NACC)
+                sh.two[0] = static_cast<int>(s1);
+            else if (e1 == NACC + 1)
+                sh.cand = s1;
+            else if (e1 < NACC)
+                sh.sys[e1] = s1;
         }
     }
     __syncthreads();
@@ -805,8 +901,9 @@ __device__ __forceinline__ void st_release_u32(unsigned *p, unsigned v) {
     asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-__device__ void op_icp(Grid &g, const Scratch &sc, Shared &sh, const MapView &m, const double *src, double *work,
-                       int n, const SE3 &guess, double max_dist, double kscale, int max_iter, double conv) {
+__device__ __noinline__ void op_icp(Grid &g, const Scratch &sc, Shared &sh, const MapView &m, const double *src, double *work,
+                       int n, const SE3 &guess, double max_dist, double kscale, int max_iter, double conv,
+                       QCache *qcache) {
     (void)g;
     if (__ldcg(&m.counters[C_LIVE]) == 0 || max_iter <= 0) {  // voxel_map.Empty() -> initial_guess (:143)
         __syncthreads();
@@ -824,7 +921,7 @@ __device__ void op_icp(Grid &g, const Scratch &sc, Shared &sh, const MapView &m,
     for (;; ++j) {
         const int parity = j & 1;
         const bool dbg_on = (j == 1);
-        icp_queries(sc, sh, m, j == 0 ? src : work, work, n, pending, max_dist, kscale, parity, dbg_on);
+        icp_queries(sc, sh, m, j == 0 ? src : work, work, n, pending, max_dist, kscale, parity, dbg_on, qcache, j == 0);
         const unsigned epoch = static_cast<unsigned>(j) + 1u;
         const bool last = icp_arrive(sc, sh, epoch);
         double *rec = sc.icp_rec + parity * ICP_REC;
@@ -857,13 +954,25 @@ __device__ void op_icp(Grid &g, const Scratch &sc, Shared &sh, const MapView &m,
                 st_release_u32(&sc.bar[2], epoch);
             }
         }
-        if (threadIdx.x == 0) {
-            while (ld_acquire_u32(&sc.bar[2]) < epoch) {
+        if (threadIdx.x < 32) {
+            // warp 0 polls the publish epoch (relaxed loads, one acquire at the end), then its lanes
+            // fetch the record in parallel
+            if (threadIdx.x == 0) {
+                while (ld_relaxed_u32(&sc.bar[2]) < epoch) {
+                }
+                (void)ld_acquire_u32(&sc.bar[2]);
             }
-            __threadfence();
-            sh.pending = rec_load_se3(rec);
-            sh.flag = __ldcg(rec + 21) != 0.0 ? 1 : 0;
-            if (dbg_on) KB_DBG(sc, 7);
+            __syncwarp();
+            double v = 0.0;
+            if (threadIdx.x < 7 || threadIdx.x == 21) v = __ldcg(rec + threadIdx.x);
+            const double qx = __shfl_sync(FULL, v, 0), qy = __shfl_sync(FULL, v, 1), qz = __shfl_sync(FULL, v, 2);
+            const double qw = __shfl_sync(FULL, v, 3), tx = __shfl_sync(FULL, v, 4), ty = __shfl_sync(FULL, v, 5);
+            const double tz = __shfl_sync(FULL, v, 6), dn = __shfl_sync(FULL, v, 21);
+            if (threadIdx.x == 0) {
+                sh.pending = SE3{{qx, qy, qz, qw}, {tx, ty, tz}};
+                sh.flag = dn != 0.0 ? 1 : 0;
+                if (dbg_on) KB_DBG(sc, 7);
+            }
         }
         __syncthreads();
         pending = sh.pending;
@@ -887,7 +996,7 @@ __device__ void op_icp(Grid &g, const Scratch &sc, Shared &sh, const MapView &m,
 //   touched voxel replays its pending points in ascending input index (= reference order)
 //   with the reference's accept rule; phase C evicts by the first point of each voxel.
 // ------------------------------------------------------------------------------------------
-__device__ void op_map_add(Grid &g, Shared &sh, const MapView &m, const double *pts, int n, bool has_pose,
+__device__ __noinline__ void op_map_add(Grid &g, Shared &sh, const MapView &m, const double *pts, int n, bool has_pose,
                            const SE3 &pose, double *tp, int *next, int *touched) {
     for (int i = blockIdx.x * BLOCK + threadIdx.x; i < n; i += gridDim.x * BLOCK) {
         V3 p{pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]};
@@ -946,7 +1055,7 @@ __device__ void op_map_add(Grid &g, Shared &sh, const MapView &m, const double *
     (void)sh;
 }
 
-__device__ void op_map_remove_far(const MapView &m, const V3 &origin) {
+__device__ __noinline__ void op_map_remove_far(const MapView &m, const V3 &origin) {
     const double max_d2 = m.max_distance * m.max_distance;
     const size_t cap3 = static_cast<size_t>(m.cap) * 3;
     for (unsigned s = blockIdx.x * BLOCK + threadIdx.x; s <= m.mask; s += gridDim.x * BLOCK) {

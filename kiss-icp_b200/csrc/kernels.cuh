@@ -57,6 +57,7 @@ struct FrameParams {
     double max_range, min_range, voxel_size;
     int max_iter;
     double conv, min_motion_th;
+    int use_qcache;
 };
 
 __device__ __forceinline__ void threshold_update(const SE3 &dev, double min_motion_th, double max_range,
@@ -76,8 +77,11 @@ __device__ __forceinline__ void threshold_update(const SE3 &dev, double min_moti
 #define KB_STAMP(i) \
     if (blockIdx.x == 0 && threadIdx.x == 0) P.res->t_ns[i] = globaltimer_ns()
 
+extern __shared__ __align__(16) unsigned char kb_dyn_smem[];  // QCache[NWARPS][QC_SLOTS] when launched with QC_BYTES
+
 __global__ void __launch_bounds__(BLOCK, 1) k_register_frame(const FrameParams P) {
     __shared__ Shared sh;
+    QCache *qcache = P.use_qcache ? reinterpret_cast<QCache *>(kb_dyn_smem) : nullptr;
     Grid g;
     g.init(P.sc.bar);
     KB_STAMP(0);
@@ -107,7 +111,7 @@ __global__ void __launch_bounds__(BLOCK, 1) k_register_frame(const FrameParams P
     const double sigma = sqrt(model_sse / num_samples);
     const SE3 guess = se3_mul(last_pose, last_delta);
     // ICP (KissICP.cpp:50-54)
-    op_icp(g, P.sc, sh, P.m, P.ws.src, P.ws.work, n_src, guess, 3.0 * sigma, sigma, P.max_iter, P.conv);
+    op_icp(g, P.sc, sh, P.m, P.ws.src, P.ws.work, n_src, guess, 3.0 * sigma, sigma, P.max_iter, P.conv, qcache);
     const SE3 new_pose = sh.result;
     const int iters = sh.iters;
     const double icp_cand = sh.cand_total, icp_q = sh.query_total;
@@ -208,6 +212,7 @@ struct IcpParams {
     int system_only;
     double *out_sys;
     int *out_ncorr;
+    int use_qcache;
 };
 __global__ void __launch_bounds__(BLOCK, 1) k_icp(const IcpParams P) {
     __shared__ Shared sh;
@@ -224,7 +229,8 @@ __global__ void __launch_bounds__(BLOCK, 1) k_icp(const IcpParams P) {
         }
         return;
     }
-    op_icp(g, P.sc, sh, P.m, P.src, P.work, P.n, P.guess, P.max_dist, P.kscale, P.max_iter, P.conv);
+    op_icp(g, P.sc, sh, P.m, P.src, P.work, P.n, P.guess, P.max_dist, P.kscale, P.max_iter, P.conv,
+           P.use_qcache ? reinterpret_cast<QCache *>(kb_dyn_smem) : nullptr);
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         se3_to_matrix(sh.result, P.out_pose);
         *P.out_iters = sh.iters;
