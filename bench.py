@@ -206,10 +206,13 @@ def main():
     work = np.zeros((len(timed), 2))
     npts = np.zeros(len(timed))
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    wall_dev = np.zeros(len(timed))
     barrier()
     e0.record(stream)
-    for t in timed:
+    for i, t in enumerate(timed):
+        t0 = time.perf_counter()
         reg_dev(icp, t)
+        wall_dev[i] = time.perf_counter() - t0
     e1.record(stream)
     barrier()
     ms_dev = e0.elapsed_time(e1)
@@ -228,9 +231,12 @@ def main():
     h2d = float(np.mean([p.numel() * 8 for p in pinned]))
     icp2.start_history(len(pinned))  # per-frame stats are logged inside the C call, read after timing
     barrier()
+    wall_e2e = np.zeros(len(pinned))
     e0.record(stream)
-    for p in pinned:
+    for i, p in enumerate(pinned):
+        t0 = time.perf_counter()
         N.check(L.kb_pipeline_register_frame(icp2._h, C.c_void_p(p.data_ptr()), p.shape[0], None, 0))
+        wall_e2e[i] = time.perf_counter() - t0
     e1.record(stream)
     barrier()
     for i, st in enumerate(icp2.history()):
@@ -284,6 +290,8 @@ def main():
                              "legitimately L2-resident across steps",
                        "phase_us": dict(zip(["preprocess", "downsample_0.5v", "downsample_1.5v", "icp", "map_update", "epilogue"],
                                             [float(x) for x in prof.mean(0)])),
+                       "call_latency_ms": {"resident": {"p50": float(np.percentile(wall_dev, 50) * 1e3), "p99": float(np.percentile(wall_dev, 99) * 1e3), "max": float(wall_dev.max() * 1e3)},
+                                           "e2e": {"p50": float(np.percentile(wall_e2e, 50) * 1e3), "p99": float(np.percentile(wall_e2e, 99) * 1e3), "max": float(wall_e2e.max() * 1e3)}},
                        "deterministic_replay": same, "gathered_trajectories": list(all_poses.shape)},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "scans/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

@@ -64,7 +64,9 @@ struct DBuf {
         if (p) cudaFree(p);
         p = nullptr;
         n = 0;
-        const size_t want = std::max<size_t>(count, 1024);
+        // grow with 25% headroom: scan sizes jitter from frame to frame and a cudaFree/cudaMalloc
+        // pair per new maximum would put milliseconds of allocator time on the hot path
+        const size_t want = std::max<size_t>(count + count / 4, 1024);
         CK(cudaMalloc(&p, want * sizeof(T)));
         n = want;
         return KB_OK;

@@ -274,18 +274,25 @@ struct WarpNN {
     int start[27];
 };
 
-// Per-warp cache of a query's whole 27-voxel neighbourhood (dynamic shared memory, 2 slots per
-// warp = the first two queries a warp owns). The map is immutable during AlignPointsToMap and
-// after the first iterations a source point almost never leaves its voxel, so from then on a
-// query costs no global memory traffic at all: point, candidates and their order come from
-// shared memory (~30-cycle LDS instead of ~300-cycle L2 round trips).
-constexpr int QC_MAX = 256;   // candidates cached per query (p99 of a 20-pt/voxel map ~250-310)
-constexpr int QC_SLOTS = 2;   // cached queries per warp
+// Per-warp cache of the candidates that can still become a query's nearest neighbour (dynamic
+// shared memory, QC_SLOTS queries per warp). Exactness argument: let p_f be the query position
+// when the cache was filled, d* its nearest-neighbour distance then, and S the candidates with
+// |c - p_f| <= d* + 2R. While the query has moved by delta <= R, its true nearest neighbour c'
+// satisfies |c' - p| <= |c* - p| <= d* + delta, hence |c' - p_f| <= d* + 2 delta <= d* + 2R, so
+// c' is in S; every candidate outside S is strictly farther than the minimum, so ties (resolved
+// by the stored reference sequence numbers) are unaffected. The map is immutable during
+// AlignPointsToMap and ICP steps shrink geometrically, so after the first iterations a query
+// costs no global memory traffic at all: ~30-cycle LDS instead of ~300-cycle L2 round trips,
+// and ~10-40 candidates instead of the 135-300 of the full 27-voxel neighbourhood.
+constexpr int QC_MAX = 64;   // cached candidates per query
+constexpr int QC_SLOTS = 2;  // cached queries per warp
 struct QCache {
-    int vx, vy, vz;  // voxel the cache was filled for
-    int total;       // cached candidates, -1 = invalid
-    double p[3];     // the source point, carried across iterations
+    double pf[3];  // query position at fill time
+    double p[3];   // current query position, carried across iterations
+    int total;     // cached candidates, -1 = invalid
+    int full;      // candidates of the full neighbourhood (bookkeeping of algorithmic bytes)
     double pts[QC_MAX][3];
+    int seq[QC_MAX];  // reference order of each cached candidate (tie-breaking)
 };
 constexpr size_t QC_BYTES = sizeof(QCache) * QC_SLOTS * NWARPS;
 
@@ -606,13 +613,14 @@ __device__ __forceinline__ NNResult nn_search_cached(const QCache &qc, const V3 
     int bseq = INT_MAX;
     V3 bp{0, 0, 0};
     const int total = qc.total;
-    for (int j = lane; j < total; j += 32) nn_consider(V3{qc.pts[j][0], qc.pts[j][1], qc.pts[j][2]}, q, j, best, best_d2, bseq, bp);
+    for (int k = lane; k < total; k += 32)
+        nn_consider(V3{qc.pts[k][0], qc.pts[k][1], qc.pts[k][2]}, q, qc.seq[k], best, best_d2, bseq, bp);
     nn_reduce(best, bseq, bp);
-    return NNResult{best, bp, total};
+    return NNResult{best, bp, qc.full};
 }
 
 __device__ __forceinline__ NNResult nn_search_warp(const MapView &m, const V3 &q, int lane, WarpNN &w,
-                                                   QCache *fill = nullptr) {
+                                                   QCache *fill = nullptr, double cache_radius = 0.0) {
     const int3 v = point_to_voxel(q.x, q.y, q.z, m.vdiv);
     int cnt = 0, slot = -1;
     if (lane < 27) {
@@ -643,13 +651,6 @@ __device__ __forceinline__ NNResult nn_search_warp(const MapView &m, const V3 &q
             for (int k = 0; k < cnt; ++k) w.owner[start + k] = static_cast<unsigned char>(lane);
         }
         __syncwarp();
-        const bool do_fill = fill != nullptr && total <= QC_MAX;
-        if (fill != nullptr && lane == 0) {
-            fill->vx = v.x;
-            fill->vy = v.y;
-            fill->vz = v.z;
-            fill->total = do_fill ? total : -1;
-        }
         constexpr int U = 4;
         for (int base = 0; base < total; base += 32 * U) {
             V3 c[U];
@@ -666,15 +667,7 @@ __device__ __forceinline__ NNResult nn_search_warp(const MapView &m, const V3 &q
             }
 #pragma unroll
             for (int u = 0; u < U; ++u)
-                if (ok[u]) {
-                    const int j = base + u * 32 + lane;
-                    if (do_fill) {
-                        fill->pts[j][0] = c[u].x;
-                        fill->pts[j][1] = c[u].y;
-                        fill->pts[j][2] = c[u].z;
-                    }
-                    nn_consider(c[u], q, j, best, best_d2, bseq, bp);
-                }
+                if (ok[u]) nn_consider(c[u], q, base + u * 32 + lane, best, best_d2, bseq, bp);
         }
     } else {
         // general path: walk the occupied voxels one after the other
@@ -691,9 +684,51 @@ __device__ __forceinline__ NNResult nn_search_warp(const MapView &m, const V3 &q
                 nn_consider(V3{blk[3 * k], blk[3 * k + 1], blk[3 * k + 2]}, q, vi * 1024 + k, best, best_d2, bseq, bp);
         }
         if (fill != nullptr && lane == 0) fill->total = -1;
+        fill = nullptr;
     }
-    __syncwarp();
     nn_reduce(best, bseq, bp);
+    if (fill != nullptr) {
+        // second pass (L1-hot): keep the candidates within d* + 2R of the query, in reference order
+        int count = -1;
+        if (best < DBL_MAX) {
+            const double thr = best + 2.0 * cache_radius;
+            const double thr2 = thr * thr * (1.0 + 1e-12);
+            count = 0;
+            constexpr int U2 = 4;
+            for (int base = 0; base < total; base += 32 * U2) {
+#pragma unroll
+                for (int u = 0; u < U2; ++u) {
+                    const int j = base + u * 32 + lane;
+                    bool keep = false;
+                    V3 c{0, 0, 0};
+                    if (j < total) {
+                        const int vi = w.owner[j];
+                        const double *pp = m.points + (static_cast<size_t>(w.slot[vi]) * cap + (j - w.start[vi])) * 3;
+                        c = V3{pp[0], pp[1], pp[2]};
+                        keep = sqnorm(c - q) <= thr2;
+                    }
+                    const unsigned mask = __ballot_sync(FULL, keep);
+                    const int pos = count + __popc(mask & ((1u << lane) - 1u));
+                    if (keep && pos < QC_MAX) {
+                        fill->pts[pos][0] = c.x;
+                        fill->pts[pos][1] = c.y;
+                        fill->pts[pos][2] = c.z;
+                        fill->seq[pos] = j;
+                    }
+                    count += __popc(mask);
+                }
+            }
+            if (count > QC_MAX) count = -1;
+        }
+        if (lane == 0) {
+            fill->total = count;
+            fill->full = total;
+            fill->pf[0] = q.x;
+            fill->pf[1] = q.y;
+            fill->pf[2] = q.z;
+        }
+        __syncwarp();
+    }
     return NNResult{best, bp, total};
 }
 
@@ -790,11 +825,12 @@ __device__ __noinline__ void icp_queries(const Scratch &sc, Shared &sh, const Ma
                 if (first) qc->total = -1;
             }
             __syncwarp();
-            const int3 v = point_to_voxel(p.x, p.y, p.z, m.vdiv);
-            if (qc->total >= 0 && qc->vx == v.x && qc->vy == v.y && qc->vz == v.z)
+            const double radius = 0.25 * m.voxel_size;
+            const V3 moved = p - V3{qc->pf[0], qc->pf[1], qc->pf[2]};
+            if (qc->total >= 0 && sqnorm(moved) <= radius * radius)
                 r = nn_search_cached(*qc, p, lane);
             else
-                r = nn_search_warp(m, p, lane, sh.wnn[warp], qc);
+                r = nn_search_warp(m, p, lane, sh.wnn[warp], qc, radius);
         } else {
             if (lane == 0) {
                 work[3 * qi] = p.x;
