@@ -73,7 +73,7 @@ struct MapView {
 // cross-CTA scratch, sized by the grid
 struct Scratch {
     unsigned *bar;  // [0] grid barrier counter, [1] ICP arrivals, [2] ICP publish epoch (zeroed before each launch)
-    double *blk_d;  // [2][grid][NPART] doubles (ping-pong by ICP iteration parity)
+    double *blk_d;  // [2][NPART][grid] doubles (ping-pong by ICP iteration parity; value-major so the reduce is coalesced)
     double *icp_rec;  // [2][ICP_REC] solve results published by the reducing CTA (ping-pong)
     int *blk_i;     // [grid] ints
     unsigned long long *dbg;  // [64] %globaltimer stamps of CTA 0 (profiling aid)
@@ -101,6 +101,8 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 #define KB_DBG(sc, i) \
     if (blockIdx.x == 0 && (threadIdx.x & 31) == 0) (sc).dbg[i] = globaltimer_ns()
 
+__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+
 struct Grid {
     unsigned *bar;
     unsigned target;
@@ -112,11 +114,11 @@ struct Grid {
         __syncthreads();
         if (threadIdx.x == 0) {
             target += gridDim.x;
-            __threadfence();
-            atomicAdd(bar, 1u);
-            while (ld_acquire_u32(bar) < target) {
+            unsigned old;  // release our writes / acquire everybody else's
+            asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(old) : "l"(bar) : "memory");
+            while (ld_relaxed_u32(bar) < target) {
             }
-            __threadfence();  // gpu-scope fence also drops this SM's L1 lines
+            __threadfence();  // acquire side; a gpu-scope fence also drops this SM's L1 lines (plain loads follow)
         }
         __syncthreads();
     }
@@ -280,13 +282,17 @@ struct WarpNN {
 // |c - p_f| <= d* + 2R. While the query has moved by delta <= R, its true nearest neighbour c'
 // satisfies |c' - p| <= |c* - p| <= d* + delta, hence |c' - p_f| <= d* + 2 delta <= d* + 2R, so
 // c' is in S; every candidate outside S is strictly farther than the minimum, so ties (resolved
-// by the stored reference sequence numbers) are unaffected. The map is immutable during
+// by the stored reference sequence numbers) are unaffected. The cache is also tied to the
+// query's VOXEL: GetClosestNeighbor only looks at the 27 voxels around the current voxel, so a
+// query that crosses a voxel face sees a different candidate set and must be re-probed. The map is immutable during
 // AlignPointsToMap and ICP steps shrink geometrically, so after the first iterations a query
 // costs no global memory traffic at all: ~30-cycle LDS instead of ~300-cycle L2 round trips,
 // and ~10-40 candidates instead of the 135-300 of the full 27-voxel neighbourhood.
 constexpr int QC_MAX = 64;   // cached candidates per query
 constexpr int QC_SLOTS = 2;  // cached queries per warp
 struct QCache {
+    int vx, vy, vz;  // voxel of the query at fill time (the reference searches the 27 voxels around it)
+    int pad;
     double pf[3];  // query position at fill time
     double p[3];   // current query position, carried across iterations
     int total;     // cached candidates, -1 = invalid
@@ -721,6 +727,9 @@ __device__ __forceinline__ NNResult nn_search_warp(const MapView &m, const V3 &q
             if (count > QC_MAX) count = -1;
         }
         if (lane == 0) {
+            fill->vx = v.x;
+            fill->vy = v.y;
+            fill->vz = v.z;
             fill->total = count;
             fill->full = total;
             fill->pf[0] = q.x;
@@ -827,7 +836,8 @@ __device__ __noinline__ void icp_queries(const Scratch &sc, Shared &sh, const Ma
             __syncwarp();
             const double radius = 0.25 * m.voxel_size;
             const V3 moved = p - V3{qc->pf[0], qc->pf[1], qc->pf[2]};
-            if (qc->total >= 0 && sqnorm(moved) <= radius * radius)
+            const int3 v = point_to_voxel(p.x, p.y, p.z, m.vdiv);
+            if (qc->total >= 0 && qc->vx == v.x && qc->vy == v.y && qc->vz == v.z && sqnorm(moved) <= radius * radius)
                 r = nn_search_cached(*qc, p, lane);
             else
                 r = nn_search_warp(m, p, lane, sh.wnn[warp], qc, radius);
@@ -857,7 +867,7 @@ __device__ __noinline__ void icp_queries(const Scratch &sc, Shared &sh, const Ma
 #pragma unroll
         for (int o = NWARPS / 2; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
         if ((threadIdx.x & (NWARPS - 1)) == 0)
-            sc.blk_d[(static_cast<size_t>(parity) * gridDim.x + blockIdx.x) * NPART + threadIdx.x / NWARPS] = v;
+            sc.blk_d[(static_cast<size_t>(parity) * NPART + threadIdx.x / NWARPS) * gridDim.x + blockIdx.x] = v;
     }
     if (dbg_on && warp == 0) KB_DBG(sc, 3);
 }
@@ -891,8 +901,8 @@ __device__ __forceinline__ void icp_reduce(const Scratch &sc, Shared &sh, int pa
 #pragma unroll
         for (int r = 0; r < RMAX; ++r) {
             const int b = base + r * 32 + lane;
-            v0[r] = (b < nb) ? __ldcg(&all[static_cast<size_t>(b) * NPART + e0]) : 0.0;
-            v1[r] = (two && b < nb) ? __ldcg(&all[static_cast<size_t>(b) * NPART + e1]) : 0.0;
+            v0[r] = (b < nb) ? __ldcg(&all[static_cast<size_t>(e0) * nb + b]) : 0.0;  // [value][cta]: coalesced
+            v1[r] = (two && b < nb) ? __ldcg(&all[static_cast<size_t>(e1) * nb + b]) : 0.0;
         }
 #pragma unroll
         for (int r = 0; r < RMAX; ++r) {
@@ -985,9 +995,8 @@ __device__ __noinline__ void op_icp(Grid &g, const Scratch &sc, Shared &sh, cons
                 if (done) rec_store_se3(rec + 14, se3_mul(t_icp, guess));  // :166
                 rec[21] = done ? 1.0 : 0.0;
                 rec[22] = cand_prev + sh.cand;
+                st_release_u32(&sc.bar[2], epoch);  // release: the record is visible before the epoch
                 if (dbg_on) sc.dbg[6] = globaltimer_ns();
-                __threadfence();
-                st_release_u32(&sc.bar[2], epoch);
             }
         }
         if (threadIdx.x < 32) {
