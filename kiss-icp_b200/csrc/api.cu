@@ -106,7 +106,7 @@ struct Exec {
         CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device));
         if (!coop) return fail(KB_ERR_CUDA, "device does not support cooperative launch");
         grid = tl_grid_blocks > 0 ? std::min(tl_grid_blocks, sms) : sms;
-        CK(cudaMalloc(&sc.bar, 256));
+        CK(cudaMalloc(&sc.bar, BAR_WORDS * sizeof(unsigned)));
         CK(cudaMalloc(&sc.blk_d, sizeof(double) * 2 * grid * NPART));
         CK(cudaMalloc(&sc.blk_i, sizeof(int) * 2 * grid));
         CK(cudaMalloc(&sc.icp_rec, sizeof(double) * 2 * ICP_REC));
@@ -133,7 +133,7 @@ struct Exec {
                 done.push_back(k);
             }
         }
-        CK(cudaMemsetAsync(sc.bar, 0, 4 * sizeof(unsigned), stream));
+        CK(cudaMemsetAsync(sc.bar, 0, BAR_WORDS * sizeof(unsigned), stream));
         void *args[] = {const_cast<P *>(&p)};
         CK(cudaLaunchCooperativeKernel(reinterpret_cast<const void *>(kern), dim3(grid), dim3(BLOCK), args, smem, stream));
         ++launches;
@@ -142,7 +142,7 @@ struct Exec {
     template <class A, class B>
     int coop(void (*kern)(A, B), const A &a, const B &b) {
         CK(cudaSetDevice(device));
-        CK(cudaMemsetAsync(sc.bar, 0, 4 * sizeof(unsigned), stream));
+        CK(cudaMemsetAsync(sc.bar, 0, BAR_WORDS * sizeof(unsigned), stream));
         void *args[] = {const_cast<A *>(&a), const_cast<B *>(&b)};
         CK(cudaLaunchCooperativeKernel(reinterpret_cast<const void *>(kern), dim3(grid), dim3(BLOCK), args, 0, stream));
         ++launches;

@@ -33,6 +33,7 @@ constexpr int BLOCK = 512;  // threads per CTA of every cooperative kernel
 constexpr int NWARPS = BLOCK / 32;
 constexpr int NACC = 16;  // unique accumulators of the 6x6 normal equations (see icp_accumulate)
 constexpr int NPART = NACC + 2;  // per-CTA partial: accumulators, #correspondences, #candidate points
+constexpr int BAR_ARRIVE = 32, BAR_EPOCH = 64, BAR_WORDS = 96;  // word offsets inside Scratch::bar
 constexpr int ICP_REC = 32;      // est(7) t_icp(7) final(7) conv cand_total query_total ...
 
 enum Counter { C_LIVE = 0, C_TOMB = 1, C_POINTS = 2, C_STATUS = 3, C_TOUCHED = 4, C_NCOUNTERS = 8 };
@@ -72,7 +73,8 @@ struct MapView {
 
 // cross-CTA scratch, sized by the grid
 struct Scratch {
-    unsigned *bar;  // [0] grid barrier counter, [1] ICP arrivals, [2] ICP publish epoch (zeroed before each launch)
+    unsigned *bar;  // [0] grid barrier counter, [BAR_ARRIVE] ICP arrivals, [BAR_EPOCH] ICP publish epoch: one 128-B
+                    // line each (arrival atomics must not fight the epoch pollers); zeroed before each launch
     double *blk_d;  // [2][NPART][grid] doubles (ping-pong by ICP iteration parity; value-major so the reduce is coalesced)
     double *icp_rec;  // [2][ICP_REC] solve results published by the reducing CTA (ping-pong)
     int *blk_i;     // [grid] ints
@@ -872,16 +874,25 @@ __device__ __noinline__ void icp_queries(const Scratch &sc, Shared &sh, const Ma
     if (dbg_on && warp == 0) KB_DBG(sc, 3);
 }
 
-// arrival at the per-iteration rendezvous; true in exactly one CTA: the last one to arrive.
+// per-iteration rendezvous. Every CTA posts its arrival with a release reduction (no return
+// value -> nothing to wait for); CTA 0 is the fixed COORDINATOR: it waits until all CTAs of
+// this epoch have arrived, then reduces + solves + publishes. (A "last arriver does it" scheme
+// would run the large unrolled solve on a different SM every iteration — always instruction-
+// cache cold, measured 3x slower.)
 __device__ __forceinline__ bool icp_arrive(const Scratch &sc, Shared &sh, unsigned epoch) {
     __syncthreads();
     if (threadIdx.x == 0) {
-        unsigned old;  // release: our partial is visible before the arrival; acquire: the last arriver sees all partials
-        asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(old) : "l"(&sc.bar[1]) : "memory");
-        sh.is_last = (old == epoch * gridDim.x - 1u) ? 1 : 0;
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(&sc.bar[BAR_ARRIVE]) : "memory");
+        if (blockIdx.x == 0) {
+            const unsigned want = epoch * gridDim.x;
+            while (ld_relaxed_u32(&sc.bar[BAR_ARRIVE]) < want) {
+            }
+            (void)ld_acquire_u32(&sc.bar[BAR_ARRIVE]);
+        }
     }
+    if (blockIdx.x != 0) return false;
     __syncthreads();
-    return sh.is_last != 0;
+    return true;
 }
 
 // the reducing CTA sums the partials of all CTAs in a fixed order -> sh.sys, sh.two[0], sh.cand.
@@ -931,11 +942,11 @@ __device__ __forceinline__ void icp_reduce(const Scratch &sc, Shared &sh, int pa
 
 // ------------------------------------------------------------------------------------------
 // op_icp — Registration::AlignPointsToMap (core/Registration.cpp:138-167), device resident.
-//   Per iteration: every CTA runs its queries and posts a partial system; the LAST CTA to arrive
-//   (one L2 atomic) reduces the partials in fixed CTA order, solves the 6x6, updates T_icp and
+//   Per iteration: every CTA runs its queries and posts a partial system + an arrival; CTA 0 (the
+//   coordinator) reduces the partials in fixed CTA order, solves the 6x6, updates T_icp and
 //   publishes {estimation, T_icp, converged} with a release store; everyone else spins on the
 //   publish epoch. One rendezvous per iteration, no host round trip, no 148-way re-read of the
-//   partials, and the result is independent of which CTA happened to arrive last.
+//   partials.
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void rec_store_se3(double *r, const SE3 &T) {
     r[0] = T.q.x; r[1] = T.q.y; r[2] = T.q.z; r[3] = T.q.w; r[4] = T.t.x; r[5] = T.t.y; r[6] = T.t.z;
@@ -966,7 +977,7 @@ __device__ __noinline__ void op_icp(Grid &g, const Scratch &sc, Shared &sh, cons
     int j = 0;
     for (;; ++j) {
         const int parity = j & 1;
-        const bool dbg_on = (j == 1);
+        const bool dbg_on = (j == 4);
         icp_queries(sc, sh, m, j == 0 ? src : work, work, n, pending, max_dist, kscale, parity, dbg_on, qcache, j == 0);
         const unsigned epoch = static_cast<unsigned>(j) + 1u;
         const bool last = icp_arrive(sc, sh, epoch);
@@ -995,7 +1006,7 @@ __device__ __noinline__ void op_icp(Grid &g, const Scratch &sc, Shared &sh, cons
                 if (done) rec_store_se3(rec + 14, se3_mul(t_icp, guess));  // :166
                 rec[21] = done ? 1.0 : 0.0;
                 rec[22] = cand_prev + sh.cand;
-                st_release_u32(&sc.bar[2], epoch);  // release: the record is visible before the epoch
+                st_release_u32(&sc.bar[BAR_EPOCH], epoch);  // release: the record is visible before the epoch
                 if (dbg_on) sc.dbg[6] = globaltimer_ns();
             }
         }
@@ -1003,9 +1014,9 @@ __device__ __noinline__ void op_icp(Grid &g, const Scratch &sc, Shared &sh, cons
             // warp 0 polls the publish epoch (relaxed loads, one acquire at the end), then its lanes
             // fetch the record in parallel
             if (threadIdx.x == 0) {
-                while (ld_relaxed_u32(&sc.bar[2]) < epoch) {
+                while (ld_relaxed_u32(&sc.bar[BAR_EPOCH]) < epoch) {
                 }
-                (void)ld_acquire_u32(&sc.bar[2]);
+                (void)ld_acquire_u32(&sc.bar[BAR_EPOCH]);
             }
             __syncwarp();
             double v = 0.0;

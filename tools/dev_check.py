@@ -98,7 +98,7 @@ for k in range(30):
 import ctypes as C
 from kiss_icp_b200 import _native as N
 ns = np.zeros(16); N.check(N.lib().kb_pipeline_debug_stamps(g._h, N.ptr(ns), 16))
-print("icp iteration-1 stamps [ns]: start, queries done (warp0), block synced, partial posted | reducer: elected, reduced, solved+published | cta0 sees result:", ns[:8])
+print("icp iteration-4 stamps [ns]: start, queries done (warp0), block synced, partial posted | reducer: elected, reduced, solved+published | cta0 sees result:", ns[:8])
 b = C.c_double(0)
 for it in (1, 10, 100):
     N.check(N.lib().kb_debug_barrier_ns(it, C.byref(b))); print("grid barrier ns (avg over %d):" % it, b.value)
