@@ -110,8 +110,8 @@ struct Exec {
         CK(cudaMalloc(&sc.blk_d, sizeof(double) * 2 * grid * NPART));
         CK(cudaMalloc(&sc.blk_i, sizeof(int) * 2 * grid));
         CK(cudaMalloc(&sc.icp_rec, sizeof(double) * 2 * ICP_REC));
-        CK(cudaMalloc(&sc.dbg, sizeof(unsigned long long) * 64));
-        CK(cudaMemsetAsync(sc.dbg, 0, sizeof(unsigned long long) * 64, stream));
+        CK(cudaMalloc(&sc.dbg, sizeof(unsigned long long) * (64 + 4 * grid)));
+        CK(cudaMemsetAsync(sc.dbg, 0, sizeof(unsigned long long) * (64 + 4 * grid), stream));
         return KB_OK;
     }
     ~Exec() {
@@ -1077,11 +1077,12 @@ int kb_pipeline_last_sigma(const kb_pipeline *p, double *out) {
 }
 int kb_pipeline_debug_stamps(const kb_pipeline *p, double *ns, int n) {
     if (!p || !ns) return fail(KB_ERR_INVALID_ARG, "NULL argument");
-    unsigned long long t[64];
+    const int total = 64 + 4 * p->ex->grid;
+    std::vector<unsigned long long> t(total);
     CK(cudaSetDevice(p->ex->device));
-    CK(cudaMemcpyAsync(t, p->ex->sc.dbg, sizeof(t), cudaMemcpyDeviceToHost, p->ex->stream));
+    CK(cudaMemcpyAsync(t.data(), p->ex->sc.dbg, sizeof(unsigned long long) * total, cudaMemcpyDeviceToHost, p->ex->stream));
     RET(p->ex->sync());
-    for (int i = 0; i < n && i < 64; ++i) ns[i] = static_cast<double>(static_cast<long long>(t[i] - t[0]));
+    for (int i = 0; i < n && i < total; ++i) ns[i] = static_cast<double>(static_cast<long long>(t[i] - t[0]));
     return KB_OK;
 }
 int kb_debug_ldlt6(const double A[36], const double b[6], double x_loop[6], double x_unrolled[6]) {

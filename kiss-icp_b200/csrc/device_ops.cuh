@@ -102,6 +102,9 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 }
 #define KB_DBG(sc, i) \
     if (blockIdx.x == 0 && (threadIdx.x & 31) == 0) (sc).dbg[i] = globaltimer_ns()
+// per-CTA timeline of the profiled ICP iteration: dbg[64 + 4*cta + k]
+#define KB_DBG_CTA(sc, k) \
+    if (threadIdx.x == 0) (sc).dbg[64 + 4 * blockIdx.x + (k)] = globaltimer_ns()
 
 __device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 
@@ -575,26 +578,22 @@ struct NNResult {
 };
 
 __device__ __forceinline__ void nn_reduce(double &best, int &bseq, V3 &bp) {
-    // lexicographic (distance, sequence) minimum across the warp, then fetch the winner's point
-    double d = best;
-    int sq = bseq;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const double od = __shfl_xor_sync(FULL, d, o);
-        const int os = __shfl_xor_sync(FULL, sq, o);
-        if (od < d || (od == d && os < sq)) {
-            d = od;
-            sq = os;
-        }
-    }
-    // every lane now holds the winning (d, seq); its owner is the unique lane with that seq
-    const unsigned who = __ballot_sync(FULL, bseq == sq && best == d);
+    // lexicographic (distance, sequence) minimum across the warp. Distances are non-negative
+    // doubles, so their bit patterns order like unsigned integers: three REDUX.MIN steps
+    // (high word, low word, sequence) replace a 5-round 64-bit shuffle tree.
+    const unsigned long long bits = static_cast<unsigned long long>(__double_as_longlong(best));
+    const unsigned hi = static_cast<unsigned>(bits >> 32), lo = static_cast<unsigned>(bits);
+    const unsigned mhi = __reduce_min_sync(FULL, hi);
+    const unsigned mlo = __reduce_min_sync(FULL, hi == mhi ? lo : 0xffffffffu);
+    const bool tie = (hi == mhi) && (lo == mlo);
+    const unsigned mseq = __reduce_min_sync(FULL, tie ? static_cast<unsigned>(bseq) : 0xffffffffu);
+    const unsigned who = __ballot_sync(FULL, tie && static_cast<unsigned>(bseq) == mseq);
     const int src = who ? (__ffs(who) - 1) : 0;
     bp.x = __shfl_sync(FULL, bp.x, src);
     bp.y = __shfl_sync(FULL, bp.y, src);
     bp.z = __shfl_sync(FULL, bp.z, src);
-    best = d;
-    bseq = sq;
+    best = __shfl_sync(FULL, best, src);
+    bseq = __shfl_sync(FULL, bseq, src);
 }
 
 // candidate update with the reference's comparison (first strict minimum of the sqrt'ed norm),
@@ -759,26 +758,28 @@ __device__ __forceinline__ double icp_term(int lane, const V3 &s, const V3 &t, d
     const double r2 = sqnorm(r);
     const double w = (kscale * kscale) / ((kscale + r2) * (kscale + r2));
     const double xw = s.x * w, yw = s.y * w, zw = s.z * w;
+    // all 16 terms are computed by every lane (a few dozen FP64 ops) and the lane's own one is
+    // selected with predicated moves: a 16-way divergent switch would serialise 16 branches
+    double t16[NACC];
+    t16[0] = w;
+    t16[1] = xw;
+    t16[2] = yw;
+    t16[3] = zw;
+    t16[4] = zw * s.z + yw * s.y;    // (3,3)
+    t16[5] = -(xw * s.y);            // (4,3)
+    t16[6] = zw * s.z + xw * s.x;    // (4,4)
+    t16[7] = -(xw * s.z);            // (5,3)
+    t16[8] = -(yw * s.z);            // (5,4)
+    t16[9] = yw * s.y + xw * s.x;    // (5,5)
+    t16[10] = w * r.x;
+    t16[11] = w * r.y;
+    t16[12] = w * r.z;
+    t16[13] = -(zw * r.y) + yw * r.z;
+    t16[14] = zw * r.x - xw * r.z;
+    t16[15] = -(yw * r.x) + xw * r.y;
     double v = 0.0;
-    switch (lane) {
-        case 0: v = w; break;
-        case 1: v = xw; break;
-        case 2: v = yw; break;
-        case 3: v = zw; break;
-        case 4: v = zw * s.z + yw * s.y; break;   // (3,3)
-        case 5: v = -(xw * s.y); break;           // (4,3)
-        case 6: v = zw * s.z + xw * s.x; break;   // (4,4)
-        case 7: v = -(xw * s.z); break;           // (5,3)
-        case 8: v = -(yw * s.z); break;           // (5,4)
-        case 9: v = yw * s.y + xw * s.x; break;   // (5,5)
-        case 10: v = w * r.x; break;
-        case 11: v = w * r.y; break;
-        case 12: v = w * r.z; break;
-        case 13: v = -(zw * r.y) + yw * r.z; break;
-        case 14: v = zw * r.x - xw * r.z; break;
-        case 15: v = -(yw * r.x) + xw * r.y; break;
-        default: break;
-    }
+#pragma unroll
+    for (int i = 0; i < NACC; ++i) v = (lane == i) ? t16[i] : v;
     return v;
 }
 
@@ -872,6 +873,7 @@ __device__ __noinline__ void icp_queries(const Scratch &sc, Shared &sh, const Ma
             sc.blk_d[(static_cast<size_t>(parity) * NPART + threadIdx.x / NWARPS) * gridDim.x + blockIdx.x] = v;
     }
     if (dbg_on && warp == 0) KB_DBG(sc, 3);
+    if (dbg_on) { KB_DBG_CTA(sc, 0); }
 }
 
 // per-iteration rendezvous. Every CTA posts its arrival with a release reduction (no return
@@ -1016,6 +1018,7 @@ __device__ __noinline__ void op_icp(Grid &g, const Scratch &sc, Shared &sh, cons
             if (threadIdx.x == 0) {
                 while (ld_relaxed_u32(&sc.bar[BAR_EPOCH]) < epoch) {
                 }
+                if (dbg_on) { KB_DBG_CTA(sc, 1); }
                 (void)ld_acquire_u32(&sc.bar[BAR_EPOCH]);
             }
             __syncwarp();
@@ -1028,6 +1031,7 @@ __device__ __noinline__ void op_icp(Grid &g, const Scratch &sc, Shared &sh, cons
                 sh.pending = SE3{{qx, qy, qz, qw}, {tx, ty, tz}};
                 sh.flag = dn != 0.0 ? 1 : 0;
                 if (dbg_on) KB_DBG(sc, 7);
+                if (dbg_on) { KB_DBG_CTA(sc, 2); }
             }
         }
         __syncthreads();

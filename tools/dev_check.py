@@ -97,7 +97,9 @@ for k in range(30):
     worst = max(worst, np.abs(g.last_pose - o.pose).max())
 import ctypes as C
 from kiss_icp_b200 import _native as N
-ns = np.zeros(16); N.check(N.lib().kb_pipeline_debug_stamps(g._h, N.ptr(ns), 16))
+ns = np.zeros(64 + 4 * 148); N.check(N.lib().kb_pipeline_debug_stamps(g._h, N.ptr(ns), len(ns)))
+cta = ns[64:].reshape(-1, 4)
+print('per-CTA: posted min/median/max [ns]', cta[:, 0].min(), np.median(cta[:, 0]), cta[:, 0].max(), 'argmax', cta[:, 0].argmax(), '| epoch seen min/median/max', cta[:, 1].min(), np.median(cta[:, 1]), cta[:, 1].max(), '| record loaded median/max', np.median(cta[:, 2]), cta[:, 2].max())
 print("icp iteration-4 stamps [ns]: start, queries done (warp0), block synced, partial posted | reducer: elected, reduced, solved+published | cta0 sees result:", ns[:8])
 b = C.c_double(0)
 for it in (1, 10, 100):
