@@ -1114,6 +1114,11 @@ int kb_debug_barrier_ns(int iters, double *ns_per_barrier) {
     *ns_per_barrier = static_cast<double>(t[1] - t[0]) / iters;
     return KB_OK;
 }
+int kb_pipeline_last_cache_stats(const kb_pipeline *p, double out[3]) {
+    if (!p || !out) return fail(KB_ERR_INVALID_ARG, "NULL argument");
+    for (int i = 0; i < 3; ++i) out[i] = p->last.cache_stats[i];
+    return KB_OK;
+}
 int kb_pipeline_last_icp_work(const kb_pipeline *p, double *queries, double *candidates) {
     if (!p) return fail(KB_ERR_INVALID_ARG, "p == NULL");
     if (queries) *queries = p->last.icp_queries;

@@ -32,7 +32,7 @@ constexpr unsigned FULL = 0xffffffffu;
 constexpr int BLOCK = 512;  // threads per CTA of every cooperative kernel
 constexpr int NWARPS = BLOCK / 32;
 constexpr int NACC = 16;  // unique accumulators of the 6x6 normal equations (see icp_accumulate)
-constexpr int NPART = NACC + 2;  // per-CTA partial: accumulators, #correspondences, #candidate points
+constexpr int NPART = NACC + 5;  // per-CTA partial: accumulators, #correspondences, #candidate points, cache hits/fills/overflows
 constexpr int BAR_ARRIVE = 32, BAR_EPOCH = 64, BAR_WORDS = 96;  // word offsets inside Scratch::bar
 constexpr int ICP_REC = 32;      // est(7) t_icp(7) final(7) conv cand_total query_total ...
 
@@ -312,6 +312,7 @@ struct Shared {
     int two[2];
     double warp_d[NWARPS][NPART];
     double warp_c[NWARPS];
+    double red[NPART];
     WarpNN wnn[NWARPS];
     double sys[NACC];
     double omega[6];
@@ -322,6 +323,7 @@ struct Shared {
     int iters;   // op_icp output
     double cand;     // candidate points examined by the last icp_pass (all CTAs)
     double cand_total, query_total;  // summed over the iterations of op_icp
+    double cache_stats[3];           // NN-cache hits / fills / overflows summed over the iterations
     int flag;
     int is_last;
 };
@@ -818,6 +820,7 @@ __device__ __noinline__ void icp_queries(const Scratch &sc, Shared &sh, const Ma
     double acc = 0.0;  // lane l < 16 owns accumulator l
     int corr = 0;
     double cand = 0.0;
+    int n_hit = 0, n_fill = 0, n_over = 0;
     int k = 0;
     for (int qi = gwarp; qi < n; qi += nwarps, ++k) {
         QCache *qc = (qcache != nullptr && k < QC_SLOTS) ? &qcache[warp * QC_SLOTS + k] : nullptr;
@@ -841,9 +844,12 @@ __device__ __noinline__ void icp_queries(const Scratch &sc, Shared &sh, const Ma
             const V3 moved = p - V3{qc->pf[0], qc->pf[1], qc->pf[2]};
             const int3 v = point_to_voxel(p.x, p.y, p.z, m.vdiv);
             if (qc->total >= 0 && qc->vx == v.x && qc->vy == v.y && qc->vz == v.z && sqnorm(moved) <= radius * radius)
-                r = nn_search_cached(*qc, p, lane);
-            else
+                r = nn_search_cached(*qc, p, lane), ++n_hit;
+            else {
                 r = nn_search_warp(m, p, lane, sh.wnn[warp], qc, radius);
+                ++n_fill;
+                n_over += (qc->total < 0 && r.d < DBL_MAX) ? 1 : 0;
+            }
         } else {
             if (lane == 0) {
                 work[3 * qi] = p.x;
@@ -862,14 +868,18 @@ __device__ __noinline__ void icp_queries(const Scratch &sc, Shared &sh, const Ma
     if (lane < NACC) sh.warp_d[warp][lane] = acc;
     if (lane == NACC) sh.warp_d[warp][NACC] = static_cast<double>(corr);
     if (lane == NACC + 1) sh.warp_d[warp][NACC + 1] = cand;
+    if (lane == NACC + 2) sh.warp_d[warp][NACC + 2] = static_cast<double>(n_hit);
+    if (lane == NACC + 3) sh.warp_d[warp][NACC + 3] = static_cast<double>(n_fill);
+    if (lane == NACC + 4) sh.warp_d[warp][NACC + 4] = static_cast<double>(n_over);
     __syncthreads();
     if (dbg_on && warp == 0) KB_DBG(sc, 2);
     // 16-warp tree per value: thread t -> value t/16, warp t%16 (NWARPS == 16)
-    if (threadIdx.x < NPART * NWARPS) {
-        double v = sh.warp_d[threadIdx.x & (NWARPS - 1)][threadIdx.x / NWARPS];
+    if (threadIdx.x < ((NPART * NWARPS + 31) / 32) * 32) {  // whole warps take part in the shuffles
+        const int val = min(static_cast<int>(threadIdx.x) / NWARPS, NPART - 1);
+        double v = sh.warp_d[threadIdx.x & (NWARPS - 1)][val];
 #pragma unroll
         for (int o = NWARPS / 2; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
-        if ((threadIdx.x & (NWARPS - 1)) == 0)
+        if ((threadIdx.x & (NWARPS - 1)) == 0 && threadIdx.x < NPART * NWARPS)
             sc.blk_d[(static_cast<size_t>(parity) * NPART + threadIdx.x / NWARPS) * gridDim.x + blockIdx.x] = v;
     }
     if (dbg_on && warp == 0) KB_DBG(sc, 3);
@@ -887,9 +897,10 @@ __device__ __forceinline__ bool icp_arrive(const Scratch &sc, Shared &sh, unsign
         asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(&sc.bar[BAR_ARRIVE]) : "memory");
         if (blockIdx.x == 0) {
             const unsigned want = epoch * gridDim.x;
+            // relaxed polling; the partials are then read with ld.global.cg (L2, the point of coherence),
+            // issued only after this loop exits (control dependency). An ld.acquire here costs ~1.3 us.
             while (ld_relaxed_u32(&sc.bar[BAR_ARRIVE]) < want) {
             }
-            (void)ld_acquire_u32(&sc.bar[BAR_ARRIVE]);
         }
     }
     if (blockIdx.x != 0) return false;
@@ -929,15 +940,14 @@ __device__ __forceinline__ void icp_reduce(const Scratch &sc, Shared &sh, int pa
         s1 += __shfl_xor_sync(FULL, s1, o);
     }
     if (lane == 0) {
-        if (e0 < NACC) sh.sys[e0] = s0;
-        if (two) {
-            if (e1 == NACC)
-                sh.two[0] = static_cast<int>(s1);
-            else if (e1 == NACC + 1)
-                sh.cand = s1;
-            else if (e1 < NACC)
-                sh.sys[e1] = s1;
-        }
+        sh.red[e0] = s0;
+        if (two) sh.red[e1] = s1;
+    }
+    __syncthreads();
+    if (threadIdx.x < NACC) sh.sys[threadIdx.x] = sh.red[threadIdx.x];
+    if (threadIdx.x == 0) {
+        sh.two[0] = static_cast<int>(sh.red[NACC]);
+        sh.cand = sh.red[NACC + 1];
     }
     __syncthreads();
 }
@@ -971,6 +981,7 @@ __device__ __noinline__ void op_icp(Grid &g, const Scratch &sc, Shared &sh, cons
             sh.iters = 0;
             sh.cand_total = 0.0;
             sh.query_total = 0.0;
+            sh.cache_stats[0] = sh.cache_stats[1] = sh.cache_stats[2] = 0.0;
         }
         __syncthreads();
         return;
@@ -996,9 +1007,13 @@ __device__ __noinline__ void op_icp(Grid &g, const Scratch &sc, Shared &sh, cons
                 icp_expand(sh.sys, JTJ, JTr);
 #pragma unroll
                 for (int i = 0; i < 6; ++i) rhs[i] = -JTr[i];
+                if (dbg_on) sc.dbg[8] = clock64();
                 ldlt6_solve_fast(JTJ, rhs, dx);                 // :156
+                if (dbg_on) sc.dbg[9] = clock64();
                 const SE3 est = se3_exp_fast(dx);               // :157
+                if (dbg_on) sc.dbg[10] = clock64();
                 const SE3 t_icp = se3_mul_fast(est, t_prev);    // :161
+                if (dbg_on) sc.dbg[11] = clock64();
                 double n2 = 0.0;
 #pragma unroll
                 for (int i = 0; i < 6; ++i) n2 += dx[i] * dx[i];
@@ -1008,6 +1023,7 @@ __device__ __noinline__ void op_icp(Grid &g, const Scratch &sc, Shared &sh, cons
                 if (done) rec_store_se3(rec + 14, se3_mul(t_icp, guess));  // :166
                 rec[21] = done ? 1.0 : 0.0;
                 rec[22] = cand_prev + sh.cand;
+                for (int i = 0; i < 3; ++i) rec[23 + i] = ((j == 0) ? 0.0 : __ldcg(prev + 23 + i)) + sh.red[NACC + 2 + i];
                 st_release_u32(&sc.bar[BAR_EPOCH], epoch);  // release: the record is visible before the epoch
                 if (dbg_on) sc.dbg[6] = globaltimer_ns();
             }
@@ -1019,7 +1035,6 @@ __device__ __noinline__ void op_icp(Grid &g, const Scratch &sc, Shared &sh, cons
                 while (ld_relaxed_u32(&sc.bar[BAR_EPOCH]) < epoch) {
                 }
                 if (dbg_on) { KB_DBG_CTA(sc, 1); }
-                (void)ld_acquire_u32(&sc.bar[BAR_EPOCH]);
             }
             __syncwarp();
             double v = 0.0;
@@ -1043,6 +1058,7 @@ __device__ __noinline__ void op_icp(Grid &g, const Scratch &sc, Shared &sh, cons
         sh.result = rec_load_se3(rec + 14);
         sh.iters = j + 1;
         sh.cand_total = __ldcg(rec + 22);
+        for (int i = 0; i < 3; ++i) sh.cache_stats[i] = __ldcg(rec + 23 + i);
         sh.query_total = static_cast<double>(n) * (j + 1);
     }
     __syncthreads();

@@ -28,6 +28,7 @@ struct FrameResult {
     int pad;
     double icp_candidates;  // map points examined by all ICP iterations of this frame
     double icp_queries;     // GetClosestNeighbor calls (iterations x source points)
+    double cache_stats[3];  // NN-cache hits / fills / overflows over all iterations
     unsigned long long t_ns[8];  // %globaltimer at phase boundaries (CTA 0): start, pre, ds1, ds2, icp, map, end
 };
 
@@ -115,6 +116,7 @@ __global__ void __launch_bounds__(BLOCK, 1) k_register_frame(const FrameParams P
     const SE3 new_pose = sh.result;
     const int iters = sh.iters;
     const double icp_cand = sh.cand_total, icp_q = sh.query_total;
+    const double cs0 = sh.cache_stats[0], cs1 = sh.cache_stats[1], cs2 = sh.cache_stats[2];
     KB_STAMP(4);
     // local_map_.Update(frame_downsample, new_pose) (KissICP.cpp:61)
     op_map_add(g, sh, P.m, P.ws.ds1, n_ds, true, new_pose, P.ws.tp, P.ws.next, P.ws.touched);
@@ -141,6 +143,9 @@ __global__ void __launch_bounds__(BLOCK, 1) k_register_frame(const FrameParams P
         r->iterations = iters;
         r->icp_candidates = icp_cand;
         r->icp_queries = icp_q;
+        r->cache_stats[0] = cs0;
+        r->cache_stats[1] = cs1;
+        r->cache_stats[2] = cs2;
         r->n_pre = n_pre;
         r->n_ds = n_ds;
         r->n_src = n_src;
