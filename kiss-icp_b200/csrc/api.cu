@@ -88,8 +88,10 @@ struct Exec {
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     int grid = 0;
-    Scratch sc{nullptr, nullptr, nullptr, nullptr, nullptr};
+    Scratch sc{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    unsigned tag_seq = 0;  // launch sequence number of the tagged ICP protocol
     unsigned long long launches = 0;
+    unsigned next_tag_base() { return (++tag_seq) << 13; }  // 8192 epochs per launch
 
     int init() {
         if (device_count() <= 0) return fail(KB_ERR_NO_DEVICE, "no CUDA device visible (this library has no CPU fallback)");
@@ -110,6 +112,10 @@ struct Exec {
         CK(cudaMalloc(&sc.blk_d, sizeof(double) * 2 * grid * NPART));
         CK(cudaMalloc(&sc.blk_i, sizeof(int) * 2 * grid));
         CK(cudaMalloc(&sc.icp_rec, sizeof(double) * 2 * ICP_REC));
+        CK(cudaMalloc(&sc.ll_part, sizeof(uint4) * NPART * grid));
+        CK(cudaMalloc(&sc.ll_res, sizeof(uint4) * LL_RES));
+        CK(cudaMemsetAsync(sc.ll_part, 0, sizeof(uint4) * NPART * grid, stream));
+        CK(cudaMemsetAsync(sc.ll_res, 0, sizeof(uint4) * LL_RES, stream));
         CK(cudaMalloc(&sc.dbg, sizeof(unsigned long long) * (64 + 4 * grid)));
         CK(cudaMemsetAsync(sc.dbg, 0, sizeof(unsigned long long) * (64 + 4 * grid), stream));
         return KB_OK;
@@ -119,6 +125,8 @@ struct Exec {
         if (sc.blk_d) cudaFree(sc.blk_d);
         if (sc.blk_i) cudaFree(sc.blk_i);
         if (sc.icp_rec) cudaFree(sc.icp_rec);
+        if (sc.ll_part) cudaFree(sc.ll_part);
+        if (sc.ll_res) cudaFree(sc.ll_res);
         if (sc.dbg) cudaFree(sc.dbg);
         if (own_stream && stream) cudaStreamDestroy(stream);
     }
@@ -653,6 +661,7 @@ int kb_registration_create(int max_num_iterations, double convergence_criterion,
                            kb_registration **out) {
     if (!out) return fail(KB_ERR_INVALID_ARG, "out == NULL");
     if (device_count() <= 0) return fail(KB_ERR_NO_DEVICE, "no CUDA device visible (this library has no CPU fallback)");
+    if (max_num_iterations > 8000) return fail(KB_ERR_INVALID_ARG, "max_num_iterations > 8000 is not supported");
     auto r = new kb_registration();
     r->max_iter = max_num_iterations;
     r->conv = convergence_criterion;
@@ -690,6 +699,7 @@ static int registration_run(kb_registration *reg, const double *xyz, size_t n, k
     P.out_sys = reg->out.p + 16;
     P.out_ncorr = reg->iout.p + 1;
     P.use_qcache = system_only ? 0 : 1;
+    P.tag_base = ex.next_tag_base();
     return ex.coop(k_icp, P, system_only ? 0 : QC_BYTES);
 }
 int kb_registration_align_points_to_map(kb_registration *reg, const double *xyz, size_t n, const kb_map *cmap,
@@ -886,6 +896,7 @@ static int pipeline_push_state(kb_pipeline *p, const SE3 &pose, const SE3 &delta
 
 int kb_pipeline_create(const kb_config *cfg, kb_pipeline **out) {
     if (!cfg || !out) return fail(KB_ERR_INVALID_ARG, "NULL argument");
+    if (cfg->max_num_iterations > 8000) return fail(KB_ERR_INVALID_ARG, "max_num_iterations > 8000 is not supported");
     auto p = std::make_unique<kb_pipeline>();
     RET(make_exec(&p->ex));
     p->cfg = *cfg;
@@ -936,6 +947,7 @@ static int pipeline_run(kb_pipeline *p, const double *d_xyz, size_t n, const dou
     P.conv = p->cfg.convergence_criterion;
     P.min_motion_th = p->cfg.min_motion_th;
     P.use_qcache = 1;
+    P.tag_base = ex.next_tag_base();
     RET(ex.coop(k_register_frame, P, QC_BYTES));
     CK(cudaMemcpyAsync(p->h_res, p->d_res, sizeof(FrameResult), cudaMemcpyDeviceToHost, ex.stream));
     RET(ex.sync());

@@ -34,7 +34,8 @@ constexpr int NWARPS = BLOCK / 32;
 constexpr int NACC = 16;  // unique accumulators of the 6x6 normal equations (see icp_accumulate)
 constexpr int NPART = NACC + 5;  // per-CTA partial: accumulators, #correspondences, #candidate points, cache hits/fills/overflows
 constexpr int BAR_ARRIVE = 32, BAR_EPOCH = 64, BAR_WORDS = 96;  // word offsets inside Scratch::bar
-constexpr int ICP_REC = 32;      // est(7) t_icp(7) final(7) conv cand_total query_total ...
+constexpr int ICP_REC = 32;
+constexpr int LL_RES = 16;        // est(7) + done flag, final pose(7), spare      // est(7) t_icp(7) final(7) conv cand_total query_total ...
 
 enum Counter { C_LIVE = 0, C_TOMB = 1, C_POINTS = 2, C_STATUS = 3, C_TOUCHED = 4, C_NCOUNTERS = 8 };
 enum StatusBit { ST_TABLE_FULL = 1 };
@@ -76,7 +77,9 @@ struct Scratch {
     unsigned *bar;  // [0] grid barrier counter, [BAR_ARRIVE] ICP arrivals, [BAR_EPOCH] ICP publish epoch: one 128-B
                     // line each (arrival atomics must not fight the epoch pollers); zeroed before each launch
     double *blk_d;  // [2][NPART][grid] doubles (ping-pong by ICP iteration parity; value-major so the reduce is coalesced)
-    double *icp_rec;  // [2][ICP_REC] solve results published by the reducing CTA (ping-pong)
+    double *icp_rec;  // (unused by the tagged protocol; kept for the debug tools)
+    uint4 *ll_part;   // [NPART][grid] epoch-tagged partial systems, one 16-B chunk per value and CTA
+    uint4 *ll_res;    // [LL_RES] epoch-tagged result record published by the coordinator
     int *blk_i;     // [grid] ints
     unsigned long long *dbg;  // [64] %globaltimer stamps of CTA 0 (profiling aid)
 };
@@ -103,8 +106,29 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 #define KB_DBG(sc, i) \
     if (blockIdx.x == 0 && (threadIdx.x & 31) == 0) (sc).dbg[i] = globaltimer_ns()
 // per-CTA timeline of the profiled ICP iteration: dbg[64 + 4*cta + k]
+#define KB_CYC(sc, i) \
+    if (blockIdx.x == 0 && threadIdx.x == 0) (sc).dbg[16 + (i)] = static_cast<unsigned long long>(clock64())
 #define KB_DBG_CTA(sc, k) \
     if (threadIdx.x == 0) (sc).dbg[64 + 4 * blockIdx.x + (k)] = globaltimer_ns()
+
+// ------------------------------------------------------------------------------------------
+// epoch-tagged 16-byte chunks (the NCCL "LL" idea): a double travels as {lo32, tag, hi32, tag};
+// each 8-byte half is a naturally atomic scalar write that validates itself, so a reader that
+// sees both tags equal to the tag it waits for has the value — no flag, no fence, no second
+// dependent load. Tags = launch sequence number * 8192 + iteration epoch.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void ll_store(uint4 *p, double v, unsigned tag) {
+    const unsigned long long b = static_cast<unsigned long long>(__double_as_longlong(v));
+    asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(static_cast<unsigned>(b)), "r"(tag),
+                 "r"(static_cast<unsigned>(b >> 32)), "r"(tag)
+                 : "memory");
+}
+__device__ __forceinline__ bool ll_load(const uint4 *p, unsigned tag, double *v) {
+    unsigned a, b, c, d;
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "l"(p) : "memory");
+    *v = __longlong_as_double(static_cast<long long>((static_cast<unsigned long long>(c) << 32) | a));
+    return b == tag && d == tag;
+}
 
 __device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 
@@ -289,7 +313,10 @@ struct WarpNN {
 // c' is in S; every candidate outside S is strictly farther than the minimum, so ties (resolved
 // by the stored reference sequence numbers) are unaffected. The cache is also tied to the
 // query's VOXEL: GetClosestNeighbor only looks at the 27 voxels around the current voxel, so a
-// query that crosses a voxel face sees a different candidate set and must be re-probed. The map is immutable during
+// query that crosses a voxel face sees a different candidate set and must be re-probed —
+// UNLESS d* + 3R < voxel_size: then every point within d* + 2R of p_f (the whole of S and any
+// would-be closer point) is less than one voxel away from both p_f and p, i.e. inside the
+// 27-voxel neighbourhood of either position, and the voxel does not matter. The map is immutable during
 // AlignPointsToMap and ICP steps shrink geometrically, so after the first iterations a query
 // costs no global memory traffic at all: ~30-cycle LDS instead of ~300-cycle L2 round trips,
 // and ~10-40 candidates instead of the 135-300 of the full 27-voxel neighbourhood.
@@ -302,6 +329,8 @@ struct QCache {
     double p[3];   // current query position, carried across iterations
     int total;     // cached candidates, -1 = invalid
     int full;      // candidates of the full neighbourhood (bookkeeping of algorithmic bytes)
+    int any_voxel; // 1: valid in whatever voxel the query is (d* + 3R < voxel_size, see below)
+    int pad2;
     double pts[QC_MAX][3];
     int seq[QC_MAX];  // reference order of each cached candidate (tie-breaking)
 };
@@ -735,6 +764,7 @@ __device__ __forceinline__ NNResult nn_search_warp(const MapView &m, const V3 &q
             fill->vz = v.z;
             fill->total = count;
             fill->full = total;
+            fill->any_voxel = (best < DBL_MAX && best + 3.0 * cache_radius < m.voxel_size) ? 1 : 0;
             fill->pf[0] = q.x;
             fill->pf[1] = q.y;
             fill->pf[2] = q.z;
@@ -812,10 +842,10 @@ __device__ __forceinline__ void icp_expand(const double a[NACC], double JTJ[36],
 // back to `work`, and the CTA's partial normal equations go to blk_d[parity][cta][NPART].
 // Reduction order is fixed: query-strided per warp -> 16-warp shuffle tree -> CTAs in order.
 __device__ __noinline__ void icp_queries(const Scratch &sc, Shared &sh, const MapView &m, const double *src, double *work, int n,
-                            const SE3 &pending, double max_dist, double kscale, int parity, bool dbg_on,
+                            const SE3 &pending, double max_dist, double kscale, unsigned tag, bool dbg_on,
                             QCache *qcache = nullptr, bool first = true) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (dbg_on && warp == 0) KB_DBG(sc, 0);
+    if (dbg_on) { KB_CYC(sc, 0); }
     const int gwarp = blockIdx.x * NWARPS + warp, nwarps = gridDim.x * NWARPS;
     double acc = 0.0;  // lane l < 16 owns accumulator l
     int corr = 0;
@@ -840,10 +870,11 @@ __device__ __noinline__ void icp_queries(const Scratch &sc, Shared &sh, const Ma
                 if (first) qc->total = -1;
             }
             __syncwarp();
-            const double radius = 0.25 * m.voxel_size;
+            const double radius = 0.2 * m.voxel_size;
             const V3 moved = p - V3{qc->pf[0], qc->pf[1], qc->pf[2]};
             const int3 v = point_to_voxel(p.x, p.y, p.z, m.vdiv);
-            if (qc->total >= 0 && qc->vx == v.x && qc->vy == v.y && qc->vz == v.z && sqnorm(moved) <= radius * radius)
+            if (qc->total >= 0 && sqnorm(moved) <= radius * radius &&
+                (qc->any_voxel || (qc->vx == v.x && qc->vy == v.y && qc->vz == v.z)))
                 r = nn_search_cached(*qc, p, lane), ++n_hit;
             else {
                 r = nn_search_warp(m, p, lane, sh.wnn[warp], qc, radius);
@@ -872,7 +903,7 @@ __device__ __noinline__ void icp_queries(const Scratch &sc, Shared &sh, const Ma
     if (lane == NACC + 3) sh.warp_d[warp][NACC + 3] = static_cast<double>(n_fill);
     if (lane == NACC + 4) sh.warp_d[warp][NACC + 4] = static_cast<double>(n_over);
     __syncthreads();
-    if (dbg_on && warp == 0) KB_DBG(sc, 2);
+    if (dbg_on) { KB_CYC(sc, 2); }
     // 16-warp tree per value: thread t -> value t/16, warp t%16 (NWARPS == 16)
     if (threadIdx.x < ((NPART * NWARPS + 31) / 32) * 32) {  // whole warps take part in the shuffles
         const int val = min(static_cast<int>(threadIdx.x) / NWARPS, NPART - 1);
@@ -880,53 +911,42 @@ __device__ __noinline__ void icp_queries(const Scratch &sc, Shared &sh, const Ma
 #pragma unroll
         for (int o = NWARPS / 2; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
         if ((threadIdx.x & (NWARPS - 1)) == 0 && threadIdx.x < NPART * NWARPS)
-            sc.blk_d[(static_cast<size_t>(parity) * NPART + threadIdx.x / NWARPS) * gridDim.x + blockIdx.x] = v;
+            ll_store(&sc.ll_part[static_cast<size_t>(threadIdx.x / NWARPS) * gridDim.x + blockIdx.x], v, tag);
     }
-    if (dbg_on && warp == 0) KB_DBG(sc, 3);
+    if (dbg_on) { KB_CYC(sc, 3); }
     if (dbg_on) { KB_DBG_CTA(sc, 0); }
 }
 
-// per-iteration rendezvous. Every CTA posts its arrival with a release reduction (no return
-// value -> nothing to wait for); CTA 0 is the fixed COORDINATOR: it waits until all CTAs of
-// this epoch have arrived, then reduces + solves + publishes. (A "last arriver does it" scheme
-// would run the large unrolled solve on a different SM every iteration — always instruction-
-// cache cold, measured 3x slower.)
-__device__ __forceinline__ bool icp_arrive(const Scratch &sc, Shared &sh, unsigned epoch) {
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(&sc.bar[BAR_ARRIVE]) : "memory");
-        if (blockIdx.x == 0) {
-            const unsigned want = epoch * gridDim.x;
-            // relaxed polling; the partials are then read with ld.global.cg (L2, the point of coherence),
-            // issued only after this loop exits (control dependency). An ld.acquire here costs ~1.3 us.
-            while (ld_relaxed_u32(&sc.bar[BAR_ARRIVE]) < want) {
-            }
-        }
-    }
-    if (blockIdx.x != 0) return false;
-    __syncthreads();
-    return true;
-}
-
-// the reducing CTA sums the partials of all CTAs in a fixed order -> sh.sys, sh.two[0], sh.cand.
-// All loads of a lane are issued before the first add (memory-level parallelism: one L2 round
-// trip instead of one per partial); grids larger than 32*RMAX CTAs take extra rounds.
-__device__ __forceinline__ void icp_reduce(const Scratch &sc, Shared &sh, int parity) {
+// The coordinator (CTA 0) gathers the tagged partials of all CTAs — polling IS the rendezvous —
+// and sums them in a fixed order -> sh.red[NPART]. Warp w owns values w and w + 16; lane l owns
+// CTAs l, l + 32, ...; all loads of a round are issued before any is examined.
+__device__ __forceinline__ void icp_gather(const Scratch &sc, Shared &sh, unsigned tag) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const double *all = sc.blk_d + static_cast<size_t>(parity) * gridDim.x * NPART;
     constexpr int RMAX = 8;
     const int nb = static_cast<int>(gridDim.x);
-    // warp w reduces value w, and (w < NPART - NWARPS) also value w + NWARPS, interleaved
     const int e0 = warp, e1 = warp + NWARPS;
     const bool two = e1 < NPART;
     double s0 = 0.0, s1 = 0.0;
     for (int base = 0; base < nb; base += 32 * RMAX) {
         double v0[RMAX], v1[RMAX];
+        unsigned pend = 0;  // bit r: value e0 of CTA base+32r+lane still missing; bit 16+r: same for e1
 #pragma unroll
         for (int r = 0; r < RMAX; ++r) {
-            const int b = base + r * 32 + lane;
-            v0[r] = (b < nb) ? __ldcg(&all[static_cast<size_t>(e0) * nb + b]) : 0.0;  // [value][cta]: coalesced
-            v1[r] = (two && b < nb) ? __ldcg(&all[static_cast<size_t>(e1) * nb + b]) : 0.0;
+            v0[r] = 0.0;
+            v1[r] = 0.0;
+            if (base + r * 32 + lane < nb) pend |= (1u << r) | (two ? (1u << (16 + r)) : 0u);
+        }
+        while (__any_sync(FULL, pend != 0)) {
+#pragma unroll
+            for (int r = 0; r < RMAX; ++r) {
+                const int b = base + r * 32 + lane;
+                if (pend & (1u << r)) {
+                    if (ll_load(&sc.ll_part[static_cast<size_t>(e0) * nb + b], tag, &v0[r])) pend &= ~(1u << r);
+                }
+                if (pend & (1u << (16 + r))) {
+                    if (ll_load(&sc.ll_part[static_cast<size_t>(e1) * nb + b], tag, &v1[r])) pend &= ~(1u << (16 + r));
+                }
+            }
         }
 #pragma unroll
         for (int r = 0; r < RMAX; ++r) {
@@ -944,35 +964,19 @@ __device__ __forceinline__ void icp_reduce(const Scratch &sc, Shared &sh, int pa
         if (two) sh.red[e1] = s1;
     }
     __syncthreads();
-    if (threadIdx.x < NACC) sh.sys[threadIdx.x] = sh.red[threadIdx.x];
-    if (threadIdx.x == 0) {
-        sh.two[0] = static_cast<int>(sh.red[NACC]);
-        sh.cand = sh.red[NACC + 1];
-    }
-    __syncthreads();
 }
 
 // ------------------------------------------------------------------------------------------
 // op_icp — Registration::AlignPointsToMap (core/Registration.cpp:138-167), device resident.
-//   Per iteration: every CTA runs its queries and posts a partial system + an arrival; CTA 0 (the
-//   coordinator) reduces the partials in fixed CTA order, solves the 6x6, updates T_icp and
-//   publishes {estimation, T_icp, converged} with a release store; everyone else spins on the
-//   publish epoch. One rendezvous per iteration, no host round trip, no 148-way re-read of the
-//   partials.
+//   Per iteration: every CTA runs its queries and posts its partial normal equations as
+//   epoch-tagged chunks; CTA 0 (the fixed coordinator, so the large unrolled solve stays warm in
+//   its instruction cache) gathers them in fixed CTA order, solves the 6x6, updates T_icp (kept
+//   in its shared memory) and publishes {estimation, converged} as tagged chunks; all CTAs poll
+//   that record. No flags, no fences, no host round trip: two L2 hops per iteration.
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void rec_store_se3(double *r, const SE3 &T) {
-    r[0] = T.q.x; r[1] = T.q.y; r[2] = T.q.z; r[3] = T.q.w; r[4] = T.t.x; r[5] = T.t.y; r[6] = T.t.z;
-}
-__device__ __forceinline__ SE3 rec_load_se3(const double *r) {
-    return SE3{{__ldcg(r), __ldcg(r + 1), __ldcg(r + 2), __ldcg(r + 3)}, {__ldcg(r + 4), __ldcg(r + 5), __ldcg(r + 6)}};
-}
-__device__ __forceinline__ void st_release_u32(unsigned *p, unsigned v) {
-    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-
 __device__ __noinline__ void op_icp(Grid &g, const Scratch &sc, Shared &sh, const MapView &m, const double *src, double *work,
                        int n, const SE3 &guess, double max_dist, double kscale, int max_iter, double conv,
-                       QCache *qcache) {
+                       QCache *qcache, unsigned tag_base) {
     (void)g;
     if (__ldcg(&m.counters[C_LIVE]) == 0 || max_iter <= 0) {  // voxel_map.Empty() -> initial_guess (:143)
         __syncthreads();
@@ -986,79 +990,100 @@ __device__ __noinline__ void op_icp(Grid &g, const Scratch &sc, Shared &sh, cons
         __syncthreads();
         return;
     }
+    if (threadIdx.x == 0) {
+        sh.t_icp = se3_identity();
+        sh.cand_total = 0.0;
+        sh.cache_stats[0] = sh.cache_stats[1] = sh.cache_stats[2] = 0.0;
+    }
     SE3 pending = guess;
     int j = 0;
     for (;; ++j) {
-        const int parity = j & 1;
         const bool dbg_on = (j == 4);
-        icp_queries(sc, sh, m, j == 0 ? src : work, work, n, pending, max_dist, kscale, parity, dbg_on, qcache, j == 0);
-        const unsigned epoch = static_cast<unsigned>(j) + 1u;
-        const bool last = icp_arrive(sc, sh, epoch);
-        double *rec = sc.icp_rec + parity * ICP_REC;
-        if (last) {
-            if (dbg_on && threadIdx.x == 0) sc.dbg[4] = globaltimer_ns();
-            icp_reduce(sc, sh, parity);
+        const unsigned tag = tag_base + static_cast<unsigned>(j) + 1u;
+        icp_queries(sc, sh, m, j == 0 ? src : work, work, n, pending, max_dist, kscale, tag, dbg_on, qcache, j == 0);
+        if (blockIdx.x == 0) {
+            if (dbg_on) { KB_CYC(sc, 4); }
+            icp_gather(sc, sh, tag);
             if (threadIdx.x == 0) {
-                if (dbg_on) sc.dbg[5] = globaltimer_ns();
-                const double *prev = sc.icp_rec + (parity ^ 1) * ICP_REC;
-                const SE3 t_prev = (j == 0) ? se3_identity() : rec_load_se3(prev + 7);
-                const double cand_prev = (j == 0) ? 0.0 : __ldcg(prev + 22);
+                if (dbg_on) { KB_CYC(sc, 5); }
+                double sys[NACC];
+#pragma unroll
+                for (int i = 0; i < NACC; ++i) sys[i] = sh.red[i];
                 double JTJ[36], JTr[6], rhs[6], dx[6];
-                icp_expand(sh.sys, JTJ, JTr);
+                icp_expand(sys, JTJ, JTr);
 #pragma unroll
                 for (int i = 0; i < 6; ++i) rhs[i] = -JTr[i];
-                if (dbg_on) sc.dbg[8] = clock64();
-                ldlt6_solve_fast(JTJ, rhs, dx);                 // :156
-                if (dbg_on) sc.dbg[9] = clock64();
-                const SE3 est = se3_exp_fast(dx);               // :157
-                if (dbg_on) sc.dbg[10] = clock64();
-                const SE3 t_icp = se3_mul_fast(est, t_prev);    // :161
-                if (dbg_on) sc.dbg[11] = clock64();
+                if (dbg_on) { KB_CYC(sc, 6); }
+                ldlt6_solve_fast(JTJ, rhs, dx);                   // :156
+                if (dbg_on) { KB_CYC(sc, 7); }
+                const SE3 est = se3_exp_fast(dx);                 // :157
+                if (dbg_on) { KB_CYC(sc, 8); }
+                const SE3 t_icp = se3_mul_fast(est, sh.t_icp);    // :161
+                if (dbg_on) { KB_CYC(sc, 9); }
                 double n2 = 0.0;
 #pragma unroll
                 for (int i = 0; i < 6; ++i) n2 += dx[i] * dx[i];
                 const bool done = (sqrt(n2) < conv) || (j + 1 >= max_iter);  // :163 / :151
-                rec_store_se3(rec, est);
-                rec_store_se3(rec + 7, t_icp);
-                if (done) rec_store_se3(rec + 14, se3_mul(t_icp, guess));  // :166
-                rec[21] = done ? 1.0 : 0.0;
-                rec[22] = cand_prev + sh.cand;
-                for (int i = 0; i < 3; ++i) rec[23 + i] = ((j == 0) ? 0.0 : __ldcg(prev + 23 + i)) + sh.red[NACC + 2 + i];
-                st_release_u32(&sc.bar[BAR_EPOCH], epoch);  // release: the record is visible before the epoch
-                if (dbg_on) sc.dbg[6] = globaltimer_ns();
+                ll_store(&sc.ll_res[0], est.q.x, tag);
+                ll_store(&sc.ll_res[1], est.q.y, tag);
+                ll_store(&sc.ll_res[2], est.q.z, tag);
+                ll_store(&sc.ll_res[3], est.q.w, tag);
+                ll_store(&sc.ll_res[4], est.t.x, tag);
+                ll_store(&sc.ll_res[5], est.t.y, tag);
+                ll_store(&sc.ll_res[6], est.t.z, tag);
+                if (done) {
+                    const SE3 fin = se3_mul(t_icp, guess);  // :166
+                    ll_store(&sc.ll_res[8], fin.q.x, tag);
+                    ll_store(&sc.ll_res[9], fin.q.y, tag);
+                    ll_store(&sc.ll_res[10], fin.q.z, tag);
+                    ll_store(&sc.ll_res[11], fin.q.w, tag);
+                    ll_store(&sc.ll_res[12], fin.t.x, tag);
+                    ll_store(&sc.ll_res[13], fin.t.y, tag);
+                    ll_store(&sc.ll_res[14], fin.t.z, tag);
+                }
+                ll_store(&sc.ll_res[7], done ? 1.0 : 0.0, tag);
+                if (dbg_on) { KB_CYC(sc, 10); }
+                sh.t_icp = t_icp;
+                sh.cand_total += sh.red[NACC + 1];
+                for (int i = 0; i < 3; ++i) sh.cache_stats[i] += sh.red[NACC + 2 + i];
             }
         }
         if (threadIdx.x < 32) {
-            // warp 0 polls the publish epoch (relaxed loads, one acquire at the end), then its lanes
-            // fetch the record in parallel
-            if (threadIdx.x == 0) {
-                while (ld_relaxed_u32(&sc.bar[BAR_EPOCH]) < epoch) {
-                }
-                if (dbg_on) { KB_DBG_CTA(sc, 1); }
-            }
-            __syncwarp();
+            // warp 0 of every CTA polls the tagged result record: lanes 0..7 = est(7) + done
+            const int l = threadIdx.x;
             double v = 0.0;
-            if (threadIdx.x < 7 || threadIdx.x == 21) v = __ldcg(rec + threadIdx.x);
+            bool ok = l >= 8;
+            while (!__all_sync(FULL, ok)) {
+                if (!ok) ok = ll_load(&sc.ll_res[l], tag, &v);
+            }
+            if (dbg_on) { KB_CYC(sc, 11); }
+            const double dn = __shfl_sync(FULL, v, 7);
+            if (dn != 0.0) {  // converged / out of iterations: the final pose rides in chunks 8..14
+                ok = l >= 7;
+                double f = 0.0;
+                while (!__all_sync(FULL, ok)) {
+                    if (!ok) ok = ll_load(&sc.ll_res[8 + l], tag, &f);
+                }
+                const double qx = __shfl_sync(FULL, f, 0), qy = __shfl_sync(FULL, f, 1), qz = __shfl_sync(FULL, f, 2);
+                const double qw = __shfl_sync(FULL, f, 3), tx = __shfl_sync(FULL, f, 4), ty = __shfl_sync(FULL, f, 5);
+                const double tz = __shfl_sync(FULL, f, 6);
+                if (l == 0) sh.result = SE3{{qx, qy, qz, qw}, {tx, ty, tz}};
+            }
             const double qx = __shfl_sync(FULL, v, 0), qy = __shfl_sync(FULL, v, 1), qz = __shfl_sync(FULL, v, 2);
             const double qw = __shfl_sync(FULL, v, 3), tx = __shfl_sync(FULL, v, 4), ty = __shfl_sync(FULL, v, 5);
-            const double tz = __shfl_sync(FULL, v, 6), dn = __shfl_sync(FULL, v, 21);
-            if (threadIdx.x == 0) {
+            const double tz = __shfl_sync(FULL, v, 6);
+            if (l == 0) {
                 sh.pending = SE3{{qx, qy, qz, qw}, {tx, ty, tz}};
                 sh.flag = dn != 0.0 ? 1 : 0;
-                if (dbg_on) KB_DBG(sc, 7);
-                if (dbg_on) { KB_DBG_CTA(sc, 2); }
+                if (dbg_on) { KB_CYC(sc, 12); }
             }
         }
         __syncthreads();
         pending = sh.pending;
         if (sh.flag) break;
     }
-    const double *rec = sc.icp_rec + (j & 1) * ICP_REC;
     if (threadIdx.x == 0) {
-        sh.result = rec_load_se3(rec + 14);
         sh.iters = j + 1;
-        sh.cand_total = __ldcg(rec + 22);
-        for (int i = 0; i < 3; ++i) sh.cache_stats[i] = __ldcg(rec + 23 + i);
         sh.query_total = static_cast<double>(n) * (j + 1);
     }
     __syncthreads();

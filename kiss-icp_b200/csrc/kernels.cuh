@@ -59,6 +59,7 @@ struct FrameParams {
     int max_iter;
     double conv, min_motion_th;
     int use_qcache;
+    unsigned tag_base;
 };
 
 __device__ __forceinline__ void threshold_update(const SE3 &dev, double min_motion_th, double max_range,
@@ -112,7 +113,7 @@ __global__ void __launch_bounds__(BLOCK, 1) k_register_frame(const FrameParams P
     const double sigma = sqrt(model_sse / num_samples);
     const SE3 guess = se3_mul(last_pose, last_delta);
     // ICP (KissICP.cpp:50-54)
-    op_icp(g, P.sc, sh, P.m, P.ws.src, P.ws.work, n_src, guess, 3.0 * sigma, sigma, P.max_iter, P.conv, qcache);
+    op_icp(g, P.sc, sh, P.m, P.ws.src, P.ws.work, n_src, guess, 3.0 * sigma, sigma, P.max_iter, P.conv, qcache, P.tag_base);
     const SE3 new_pose = sh.result;
     const int iters = sh.iters;
     const double icp_cand = sh.cand_total, icp_q = sh.query_total;
@@ -218,24 +219,25 @@ struct IcpParams {
     double *out_sys;
     int *out_ncorr;
     int use_qcache;
+    unsigned tag_base;
 };
 __global__ void __launch_bounds__(BLOCK, 1) k_icp(const IcpParams P) {
     __shared__ Shared sh;
     Grid g;
     g.init(P.sc.bar);
     if (P.system_only) {
-        icp_queries(P.sc, sh, P.m, P.src, P.work, P.n, se3_identity(), P.max_dist, P.kscale, 0, false);
-        if (icp_arrive(P.sc, sh, 1u)) {
-            icp_reduce(P.sc, sh, 0);
+        icp_queries(P.sc, sh, P.m, P.src, P.work, P.n, se3_identity(), P.max_dist, P.kscale, P.tag_base + 1u, false);
+        if (blockIdx.x == 0) {
+            icp_gather(P.sc, sh, P.tag_base + 1u);
             if (threadIdx.x == 0) {
-                for (int i = 0; i < NACC; ++i) P.out_sys[i] = sh.sys[i];
-                *P.out_ncorr = sh.two[0];
+                for (int i = 0; i < NACC; ++i) P.out_sys[i] = sh.red[i];
+                *P.out_ncorr = static_cast<int>(sh.red[NACC]);
             }
         }
         return;
     }
     op_icp(g, P.sc, sh, P.m, P.src, P.work, P.n, P.guess, P.max_dist, P.kscale, P.max_iter, P.conv,
-           P.use_qcache ? reinterpret_cast<QCache *>(kb_dyn_smem) : nullptr);
+           P.use_qcache ? reinterpret_cast<QCache *>(kb_dyn_smem) : nullptr, P.tag_base);
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         se3_to_matrix(sh.result, P.out_pose);
         *P.out_iters = sh.iters;

@@ -99,10 +99,11 @@ import ctypes as C
 from kiss_icp_b200 import _native as N
 ns = np.zeros(64 + 4 * 148); N.check(N.lib().kb_pipeline_debug_stamps(g._h, N.ptr(ns), len(ns)))
 cs = np.zeros(3); N.check(N.lib().kb_pipeline_last_cache_stats(g._h, N.ptr(cs))); print('NN cache hits/fills/overflows (last frame, all iterations):', cs, 'iters', g.last_iterations)
-print('solve cycles (ldlt, exp, mul):', ns[9] - ns[8], ns[10] - ns[9], ns[11] - ns[10])
+cyc = ns[16:29] - ns[16]
+names = ["start", "queries done", "block synced", "partial posted", "all arrived", "reduced", "rec loaded+expanded", "ldlt", "exp", "mul", "published", "epoch seen", "record in smem"]
+print("CTA0 iteration-4 timeline [us @1.965GHz]:", ", ".join("%s %.2f" % (n_, c / 1965.0) for n_, c in zip(names, cyc)))
 cta = ns[64:].reshape(-1, 4)
-print('per-CTA: posted min/median/max [ns]', cta[:, 0].min(), np.median(cta[:, 0]), cta[:, 0].max(), 'argmax', cta[:, 0].argmax(), '| epoch seen min/median/max', cta[:, 1].min(), np.median(cta[:, 1]), cta[:, 1].max(), '| record loaded median/max', np.median(cta[:, 2]), cta[:, 2].max())
-print("icp iteration-4 stamps [ns]: start, queries done (warp0), block synced, partial posted | reducer: elected, reduced, solved+published | cta0 sees result:", ns[:8])
+print('per-CTA posted (globaltimer, relative to the earliest) min/median/max [ns]', cta[:, 0].min() - cta[:, 0].min(), np.median(cta[:, 0]) - cta[:, 0].min(), cta[:, 0].max() - cta[:, 0].min(), 'argmax', cta[:, 0].argmax())
 b = C.c_double(0)
 for it in (1, 10, 100):
     N.check(N.lib().kb_debug_barrier_ns(it, C.byref(b))); print("grid barrier ns (avg over %d):" % it, b.value)
