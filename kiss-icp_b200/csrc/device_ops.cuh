@@ -119,13 +119,15 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void ll_store(uint4 *p, double v, unsigned tag) {
     const unsigned long long b = static_cast<unsigned long long>(__double_as_longlong(v));
-    asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(static_cast<unsigned>(b)), "r"(tag),
+    asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(static_cast<unsigned>(b)), "r"(tag),
                  "r"(static_cast<unsigned>(b >> 32)), "r"(tag)
                  : "memory");
 }
 __device__ __forceinline__ bool ll_load(const uint4 *p, unsigned tag, double *v) {
     unsigned a, b, c, d;
-    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "l"(p) : "memory");
+    // strong (relaxed.gpu) load: always served by the home L2 slice. A weak ld.global.cg is 2x cheaper per
+    // polling round but was measured to see the new value ~1.2 us later (B200 has two L2 partitions).
+    asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "l"(p) : "memory");
     *v = __longlong_as_double(static_cast<long long>((static_cast<unsigned long long>(c) << 32) | a));
     return b == tag && d == tag;
 }
@@ -657,6 +659,37 @@ __device__ __forceinline__ NNResult nn_search_cached(const QCache &qc, const V3 
     return NNResult{best, bp, qc.full};
 }
 
+// Same result as nn_search_cached with ONE square root per query instead of one per lane and
+// candidate: the minimum is taken on squared distances (sqrt is monotone), which can only differ
+// from the reference's comparison of rounded sqrt values if some other candidate's squared
+// distance lies within a few ulps above the minimum (two distinct squares rounding to the same
+// root). That near-tie is detected — every lane also tracks its second smallest square — and
+// then the exact routine above is used instead (in practice: never).
+__device__ __forceinline__ NNResult nn_search_cached_fast(const QCache &qc, const V3 &q, int lane) {
+    double b2 = DBL_MAX, s2 = DBL_MAX;
+    int bseq = INT_MAX;
+    V3 bp{0, 0, 0};
+    const int total = qc.total;
+    for (int k = lane; k < total; k += 32) {
+        const V3 c{qc.pts[k][0], qc.pts[k][1], qc.pts[k][2]};
+        const double d2 = sqnorm(c - q);
+        if (d2 < b2) {
+            s2 = b2;
+            b2 = d2;
+            bseq = qc.seq[k];
+            bp = c;
+        } else if (d2 > b2 && d2 < s2) {
+            s2 = d2;
+        }
+    }
+    const double mine = b2;
+    nn_reduce(b2, bseq, bp);  // b2 = warp minimum (exact ties: smallest reference sequence number)
+    const double lim = b2 * (1.0 + 8.8817841970012523e-16);
+    const bool near = (mine > b2 && mine <= lim) || (s2 <= lim);
+    if (__any_sync(FULL, near)) return nn_search_cached(qc, q, lane);
+    return NNResult{sqrt(b2), bp, qc.full};
+}
+
 __device__ __forceinline__ NNResult nn_search_warp(const MapView &m, const V3 &q, int lane, WarpNN &w,
                                                    QCache *fill = nullptr, double cache_radius = 0.0) {
     const int3 v = point_to_voxel(q.x, q.y, q.z, m.vdiv);
@@ -788,7 +821,7 @@ __device__ __forceinline__ NNResult nn_search_warp(const MapView &m, const V3 &q
 __device__ __forceinline__ double icp_term(int lane, const V3 &s, const V3 &t, double kscale) {
     const V3 r = s - t;
     const double r2 = sqnorm(r);
-    const double w = (kscale * kscale) / ((kscale + r2) * (kscale + r2));
+    const double w = (kscale * kscale) * fast_rcp((kscale + r2) * (kscale + r2));  // ~1 ulp from the reference's division
     const double xw = s.x * w, yw = s.y * w, zw = s.z * w;
     // all 16 terms are computed by every lane (a few dozen FP64 ops) and the lane's own one is
     // selected with predicated moves: a 16-way divergent switch would serialise 16 branches
@@ -846,7 +879,10 @@ __device__ __noinline__ void icp_queries(const Scratch &sc, Shared &sh, const Ma
                             QCache *qcache = nullptr, bool first = true) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (dbg_on) { KB_CYC(sc, 0); }
-    const int gwarp = blockIdx.x * NWARPS + warp, nwarps = gridDim.x * NWARPS;
+    if (dbg_on) { KB_DBG_CTA(sc, 3); }
+    // query qi -> CTA qi % G, warp (qi / G) % NWARPS: every CTA gets n/G (+1) queries, so the FP64-issue-bound
+    // query phase takes the same time on every SM
+    const int gwarp = blockIdx.x + gridDim.x * warp, nwarps = gridDim.x * NWARPS;
     double acc = 0.0;  // lane l < 16 owns accumulator l
     int corr = 0;
     double cand = 0.0;
@@ -875,7 +911,7 @@ __device__ __noinline__ void icp_queries(const Scratch &sc, Shared &sh, const Ma
             const int3 v = point_to_voxel(p.x, p.y, p.z, m.vdiv);
             if (qc->total >= 0 && sqnorm(moved) <= radius * radius &&
                 (qc->any_voxel || (qc->vx == v.x && qc->vy == v.y && qc->vz == v.z)))
-                r = nn_search_cached(*qc, p, lane), ++n_hit;
+                r = nn_search_cached_fast(*qc, p, lane), ++n_hit;
             else {
                 r = nn_search_warp(m, p, lane, sh.wnn[warp], qc, radius);
                 ++n_fill;
@@ -915,6 +951,7 @@ __device__ __noinline__ void icp_queries(const Scratch &sc, Shared &sh, const Ma
     }
     if (dbg_on) { KB_CYC(sc, 3); }
     if (dbg_on) { KB_DBG_CTA(sc, 0); }
+    if (dbg_on && threadIdx.x == 0) sc.dbg[64 + 4 * blockIdx.x + 2] = static_cast<unsigned long long>(sh.warp_d[0][NACC + 3] + sh.warp_d[1][NACC + 3] + sh.warp_d[2][NACC + 3] + sh.warp_d[3][NACC + 3] + sh.warp_d[4][NACC + 3] + sh.warp_d[5][NACC + 3] + sh.warp_d[6][NACC + 3] + sh.warp_d[7][NACC + 3] + sh.warp_d[8][NACC + 3] + sh.warp_d[9][NACC + 3] + sh.warp_d[10][NACC + 3] + sh.warp_d[11][NACC + 3] + sh.warp_d[12][NACC + 3] + sh.warp_d[13][NACC + 3] + sh.warp_d[14][NACC + 3] + sh.warp_d[15][NACC + 3]);
 }
 
 // The coordinator (CTA 0) gathers the tagged partials of all CTAs — polling IS the rendezvous —
@@ -936,18 +973,29 @@ __device__ __forceinline__ void icp_gather(const Scratch &sc, Shared &sh, unsign
             v1[r] = 0.0;
             if (base + r * 32 + lane < nb) pend |= (1u << r) | (two ? (1u << (16 + r)) : 0u);
         }
+        int rounds = 0;
         while (__any_sync(FULL, pend != 0)) {
+            ++rounds;
+            // issue every outstanding load of this round first (they are independent), examine afterwards
+            const unsigned snap = pend;
+            double t0[RMAX], t1[RMAX];
+            unsigned got = 0;
 #pragma unroll
             for (int r = 0; r < RMAX; ++r) {
                 const int b = base + r * 32 + lane;
-                if (pend & (1u << r)) {
-                    if (ll_load(&sc.ll_part[static_cast<size_t>(e0) * nb + b], tag, &v0[r])) pend &= ~(1u << r);
-                }
-                if (pend & (1u << (16 + r))) {
-                    if (ll_load(&sc.ll_part[static_cast<size_t>(e1) * nb + b], tag, &v1[r])) pend &= ~(1u << (16 + r));
-                }
+                if (snap & (1u << r))
+                    got |= ll_load(&sc.ll_part[static_cast<size_t>(e0) * nb + b], tag, &t0[r]) ? (1u << r) : 0u;
+                if (snap & (1u << (16 + r)))
+                    got |= ll_load(&sc.ll_part[static_cast<size_t>(e1) * nb + b], tag, &t1[r]) ? (1u << (16 + r)) : 0u;
             }
+#pragma unroll
+            for (int r = 0; r < RMAX; ++r) {
+                if (got & (1u << r)) v0[r] = t0[r];
+                if (got & (1u << (16 + r))) v1[r] = t1[r];
+            }
+            pend &= ~got;
         }
+        if (threadIdx.x == 0 && base == 0) sc.dbg[40] = sc.dbg[0] + static_cast<unsigned long long>(rounds);
 #pragma unroll
         for (int r = 0; r < RMAX; ++r) {
             s0 += v0[r];

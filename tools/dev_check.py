@@ -103,6 +103,10 @@ cyc = ns[16:29] - ns[16]
 names = ["start", "queries done", "block synced", "partial posted", "all arrived", "reduced", "rec loaded+expanded", "ldlt", "exp", "mul", "published", "epoch seen", "record in smem"]
 print("CTA0 iteration-4 timeline [us @1.965GHz]:", ", ".join("%s %.2f" % (n_, c / 1965.0) for n_, c in zip(names, cyc)))
 cta = ns[64:].reshape(-1, 4)
+print('gather rounds in the last ICP iteration of the last frame:', ns[40])
+dur = cta[:, 0] - cta[:, 3]
+order = np.argsort(-dur)[:12]
+print('slowest CTAs (cta, start->posted ns, fills this iteration):', [(int(i), float(dur[i]), float(cta[i, 2] + ns[0])) for i in order], 'median', np.median(dur), 'start spread', cta[:, 3].max() - cta[:, 3].min())
 print('per-CTA posted (globaltimer, relative to the earliest) min/median/max [ns]', cta[:, 0].min() - cta[:, 0].min(), np.median(cta[:, 0]) - cta[:, 0].min(), cta[:, 0].max() - cta[:, 0].min(), 'argmax', cta[:, 0].argmax())
 b = C.c_double(0)
 for it in (1, 10, 100):
