@@ -214,6 +214,8 @@ struct kb_map {
     int4 *slots = nullptr;
     double *points = nullptr;
     int *head = nullptr;
+    int *pcount = nullptr;
+    int *pending = nullptr;
     int *counters = nullptr;
     int h_counters[C_NCOUNTERS] = {0};
     Work ws;
@@ -226,6 +228,8 @@ struct kb_map {
         m.slots = slots;
         m.points = points;
         m.head = head;
+        m.pcount = pcount;
+        m.pending = pending;
         m.counters = counters;
         m.mask = static_cast<unsigned>(capacity - 1);
         m.cap = static_cast<int>(cap);
@@ -239,20 +243,26 @@ struct kb_map {
         if (slots) cudaFree(slots);
         if (points) cudaFree(points);
         if (head) cudaFree(head);
+        if (pcount) cudaFree(pcount);
+        if (pending) cudaFree(pending);
         slots = nullptr;
         points = nullptr;
         head = nullptr;
+        pcount = nullptr;
+        pending = nullptr;
     }
     ~kb_map() {
         if (ex) cudaSetDevice(ex->device);
         free_table();
         if (counters) cudaFree(counters);
     }
-    int alloc_table(size_t cap_slots, int4 **s, double **p, int **h) {
+    int alloc_table(size_t cap_slots, int4 **s, double **p, int **h, int **pc, int **pe) {
         CK(cudaMalloc(s, cap_slots * sizeof(int4)));
         CK(cudaMalloc(p, cap_slots * cap * 3 * sizeof(double)));
         CK(cudaMalloc(h, cap_slots * sizeof(int)));
-        k_map_fill<<<std::min<size_t>(4096, (cap_slots + 255) / 256), 256, 0, ex->stream>>>(*s, *h, cap_slots);
+        CK(cudaMalloc(pc, cap_slots * sizeof(int)));
+        CK(cudaMalloc(pe, cap_slots * PEND * sizeof(int)));
+        k_map_fill<<<std::min<size_t>(4096, (cap_slots + 255) / 256), 256, 0, ex->stream>>>(*s, *h, *pc, cap_slots);
         ++ex->launches;
         CK(cudaGetLastError());
         return KB_OK;
@@ -270,14 +280,16 @@ struct kb_map {
         if (want > (size_t(1) << 31)) return fail(KB_ERR_INVALID_ARG, "voxel table would exceed 2^31 slots");
         int4 *ns;
         double *np;
-        int *nh;
-        RET(alloc_table(want, &ns, &np, &nh));
+        int *nh, *npc, *npe;
+        RET(alloc_table(want, &ns, &np, &nh, &npc, &npe));
         if (capacity && live) {
             MapView from = view();
             MapView to = from;
             to.slots = ns;
             to.points = np;
             to.head = nh;
+            to.pcount = npc;
+            to.pending = npe;
             to.mask = static_cast<unsigned>(want - 1);
             int *nc;
             CK(cudaMalloc(&nc, sizeof(int) * C_NCOUNTERS));
@@ -299,6 +311,8 @@ struct kb_map {
         slots = ns;
         points = np;
         head = nh;
+        pcount = npc;
+        pending = npe;
         capacity = want;
         return KB_OK;
     }
@@ -477,7 +491,7 @@ int kb_map_clear(kb_map *map) {
     if (!map) return fail(KB_ERR_INVALID_ARG, "map == NULL");
     CK(cudaSetDevice(map->ex->device));
     k_map_fill<<<std::min<size_t>(4096, (map->capacity + 255) / 256), 256, 0, map->ex->stream>>>(map->slots, map->head,
-                                                                                             map->capacity);
+                                                                                             map->pcount, map->capacity);
     ++map->ex->launches;
     CK(cudaMemsetAsync(map->counters, 0, sizeof(int) * C_NCOUNTERS, map->ex->stream));
     std::memset(map->h_counters, 0, sizeof(map->h_counters));
@@ -1124,6 +1138,15 @@ int kb_debug_barrier_ns(int iters, double *ns_per_barrier) {
     CK(cudaMemcpyAsync(t, c->ex->sc.dbg + 8, sizeof(t), cudaMemcpyDeviceToHost, c->ex->stream));
     RET(c->ex->sync());
     *ns_per_barrier = static_cast<double>(t[1] - t[0]) / iters;
+    return KB_OK;
+}
+int kb_pipeline_last_map_profile(const kb_pipeline *p, double us[3]) {
+    if (!p || !us) return fail(KB_ERR_INVALID_ARG, "NULL argument");
+    const double t4 = static_cast<double>(p->last.t_ns[4]), a = static_cast<double>(p->last.t_ns[8]);
+    const double b = static_cast<double>(p->last.t_ns[9]), t5 = static_cast<double>(p->last.t_ns[5]);
+    us[0] = (a - t4) * 1e-3;  // transform + find-or-claim + pending lists
+    us[1] = (b - a) * 1e-3;   // per-voxel ordered insertion
+    us[2] = (t5 - b) * 1e-3;  // eviction scan
     return KB_OK;
 }
 int kb_pipeline_last_cache_stats(const kb_pipeline *p, double out[3]) {

@@ -62,7 +62,9 @@ __host__ __device__ __forceinline__ VoxelDiv make_voxel_div(double voxel_size) {
 struct MapView {
     int4 *slots;      // [capacity]
     double *points;   // [capacity][cap][3]
-    int *head;        // [capacity] pending-insert list head (-1 when idle)
+    int *head;        // [capacity] overflow list head of the pending-insert set (-1 when idle)
+    int *pcount;      // [capacity] size of the pending-insert set (0 when idle)
+    int *pending;     // [capacity][32] input indices of the pending-insert set
     int *counters;    // [C_NCOUNTERS]
     unsigned mask;    // capacity - 1 (capacity is a power of two)
     int cap;          // max_points_per_voxel
@@ -913,7 +915,9 @@ __device__ __noinline__ void icp_queries(const Scratch &sc, Shared &sh, const Ma
                 (qc->any_voxel || (qc->vx == v.x && qc->vy == v.y && qc->vz == v.z)))
                 r = nn_search_cached_fast(*qc, p, lane), ++n_hit;
             else {
-                r = nn_search_warp(m, p, lane, sh.wnn[warp], qc, radius);
+                // the first step of an alignment is the largest: caches filled before it are mostly
+                // invalid right after it, so the (two-pass) fill starts with iteration 1
+                r = nn_search_warp(m, p, lane, sh.wnn[warp], first ? nullptr : qc, radius);
                 ++n_fill;
                 n_over += (qc->total < 0 && r.d < DBL_MAX) ? 1 : 0;
             }
@@ -1145,8 +1149,18 @@ __device__ __noinline__ void op_icp(Grid &g, const Scratch &sc, Shared &sh, cons
 //   touched voxel replays its pending points in ascending input index (= reference order)
 //   with the reference's accept rule; phase C evicts by the first point of each voxel.
 // ------------------------------------------------------------------------------------------
+constexpr int PEND = 32;  // pending-insert indices kept per voxel in the coalesced array (more spill to a list)
+
+__device__ __forceinline__ bool map_close(const V3 &e, const V3 &p, double res, double res2_lo, double res2_hi) {
+    // (e - p).norm() < res  (VoxelHashMap.cpp:108): decided on the squared distance unless it is within a
+    // few ulps of res^2, where the rounded sqrt is evaluated like the reference does
+    const double d2 = sqnorm(e - p);
+    return (d2 < res2_lo) || (d2 <= res2_hi && sqrt(d2) < res);
+}
+
 __device__ __noinline__ void op_map_add(Grid &g, Shared &sh, const MapView &m, const double *pts, int n, bool has_pose,
-                           const SE3 &pose, double *tp, int *next, int *touched) {
+                           const SE3 &pose, double *tp, int *next, int *touched, unsigned long long *stamps = nullptr) {
+    // phase A: transform, find-or-claim the voxel, register the point on the voxel's pending set
     for (int i = blockIdx.x * BLOCK + threadIdx.x; i < n; i += gridDim.x * BLOCK) {
         V3 p{pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]};
         if (has_pose) p = se3_act(pose, p);  // VoxelHashMap.cpp:91-93
@@ -1155,51 +1169,94 @@ __device__ __noinline__ void op_map_add(Grid &g, Shared &sh, const MapView &m, c
         tp[3 * i + 2] = p.z;
         const int3 v = point_to_voxel(p.x, p.y, p.z, m.vdiv);
         const int s = map_find_or_claim(m, v.x, v.y, v.z);
-        if (s < 0) {
-            next[i] = -1;
-            continue;
+        if (s < 0) continue;
+        const int r = atomicAdd(&m.pcount[s], 1);
+        if (r < PEND) {
+            m.pending[static_cast<size_t>(s) * PEND + r] = i;
+        } else {  // rare (only when one voxel receives > 32 points in one call): overflow list
+            next[i] = atomicExch(&m.head[s], i);
         }
-        const int old = atomicExch(&m.head[s], i);
-        next[i] = old;
-        if (old == -1) touched[atomicAdd(&m.counters[C_TOUCHED], 1)] = s;
+        if (r == 0) touched[atomicAdd(&m.counters[C_TOUCHED], 1)] = s;
     }
     g.sync();
+    if (stamps && blockIdx.x == 0 && threadIdx.x == 0) stamps[0] = globaltimer_ns();
+    // phase B: one WARP per touched voxel replays that voxel's new points in ascending input index
+    // (= the reference's sequential order) with the reference's accept rule.
     const int n_touched = __ldcg(&m.counters[C_TOUCHED]);
     const int cap = m.cap;
-    for (int t = blockIdx.x * BLOCK + threadIdx.x; t < n_touched; t += gridDim.x * BLOCK) {
+    const double res = m.map_resolution;
+    const double res2_lo = res * res * (1.0 - 1e-14), res2_hi = res * res * (1.0 + 1e-14);
+    const int lane = threadIdx.x & 31;
+    const int gw = blockIdx.x + gridDim.x * (threadIdx.x >> 5), nw = gridDim.x * NWARPS;
+    for (int t = gw; t < n_touched; t += nw) {
         const int s = __ldcg(&touched[t]);
+        const int L = m.pcount[s];
         int cnt = m.slots[s].w;
         double *vp = m.points + static_cast<size_t>(s) * cap * 3;
-        const int first = m.head[s];
-        int last = -1, added = 0;
-        while (cnt < cap) {
-            int pick = INT_MAX;
-            for (int j = first; j != -1; j = next[j])
-                if (j > last && j < pick) pick = j;
-            if (pick == INT_MAX) break;
-            last = pick;
-            const V3 p{tp[3 * pick], tp[3 * pick + 1], tp[3 * pick + 2]};
-            bool reject = false;
-            for (int k = 0; k < cnt; ++k) {
-                const V3 e{vp[3 * k], vp[3 * k + 1], vp[3 * k + 2]};
-                if (norm(e - p) < m.map_resolution) {
-                    reject = true;
-                    break;
+        int added = 0;
+        if (L <= PEND && cap <= 32) {
+            // fast path: lane r holds new point #r of the pending set, lane k holds existing point k
+            const int idx = lane < L ? m.pending[static_cast<size_t>(s) * PEND + lane] : INT_MAX;
+            V3 np{0, 0, 0};
+            if (lane < L) np = V3{tp[3 * static_cast<size_t>(idx)], tp[3 * static_cast<size_t>(idx) + 1], tp[3 * static_cast<size_t>(idx) + 2]};
+            V3 ex{0, 0, 0};
+            if (lane < cnt) ex = V3{vp[3 * lane], vp[3 * lane + 1], vp[3 * lane + 2]};
+            int rank = 0;  // position of my index in ascending order
+            for (int j = 0; j < L; ++j) rank += (__shfl_sync(FULL, idx, j) < idx) ? 1 : 0;
+            for (int r = 0; r < L && cnt < cap; ++r) {
+                const unsigned who = __ballot_sync(FULL, lane < L && rank == r);
+                const int src = __ffs(who) - 1;
+                const V3 p{__shfl_sync(FULL, np.x, src), __shfl_sync(FULL, np.y, src), __shfl_sync(FULL, np.z, src)};
+                const bool close = lane < cnt && map_close(ex, p, res, res2_lo, res2_hi);
+                if (!__any_sync(FULL, close)) {
+                    if (lane == cnt) {
+                        ex = p;
+                        vp[3 * cnt] = p.x;
+                        vp[3 * cnt + 1] = p.y;
+                        vp[3 * cnt + 2] = p.z;
+                    }
+                    ++cnt;
+                    ++added;
                 }
             }
-            if (!reject) {
-                vp[3 * cnt] = p.x;
-                vp[3 * cnt + 1] = p.y;
-                vp[3 * cnt + 2] = p.z;
-                ++cnt;
-                ++added;
+        } else if (lane == 0) {
+            // general path (huge pending sets or max_points_per_voxel > 32): serial replay, sources = array + list
+            const int first = m.head[s];
+            int last = -1;
+            while (cnt < cap) {
+                int pick = INT_MAX;
+                for (int j = 0; j < min(L, PEND); ++j) {
+                    const int v = m.pending[static_cast<size_t>(s) * PEND + j];
+                    if (v > last && v < pick) pick = v;
+                }
+                for (int j = first; j != -1; j = next[j])
+                    if (j > last && j < pick) pick = j;
+                if (pick == INT_MAX) break;
+                last = pick;
+                const V3 p{tp[3 * static_cast<size_t>(pick)], tp[3 * static_cast<size_t>(pick) + 1], tp[3 * static_cast<size_t>(pick) + 2]};
+                bool reject = false;
+                for (int k = 0; k < cnt && !reject; ++k)
+                    reject = map_close(V3{vp[3 * k], vp[3 * k + 1], vp[3 * k + 2]}, p, res, res2_lo, res2_hi);
+                if (!reject) {
+                    vp[3 * cnt] = p.x;
+                    vp[3 * cnt + 1] = p.y;
+                    vp[3 * cnt + 2] = p.z;
+                    ++cnt;
+                    ++added;
+                }
             }
+            m.head[s] = -1;
         }
-        m.slots[s].w = cnt;
-        m.head[s] = -1;
-        if (added) atomicAdd(&m.counters[C_POINTS], added);
+        cnt = __shfl_sync(FULL, cnt, 0);
+        added = __shfl_sync(FULL, added, 0);
+        if (lane == 0) {
+            m.slots[s].w = cnt;
+            m.pcount[s] = 0;
+            if (added) atomicAdd(&m.counters[C_POINTS], added);
+        }
     }
     g.sync();
+    if (stamps && blockIdx.x == 0 && threadIdx.x == 0) stamps[1] = globaltimer_ns();
     if (blockIdx.x == 0 && threadIdx.x == 0) m.counters[C_TOUCHED] = 0;
     (void)sh;
 }

@@ -29,7 +29,7 @@ struct FrameResult {
     double icp_candidates;  // map points examined by all ICP iterations of this frame
     double icp_queries;     // GetClosestNeighbor calls (iterations x source points)
     double cache_stats[3];  // NN-cache hits / fills / overflows over all iterations
-    unsigned long long t_ns[8];  // %globaltimer at phase boundaries (CTA 0): start, pre, ds1, ds2, icp, map, end
+    unsigned long long t_ns[12];  // %globaltimer at phase boundaries (CTA 0): start, pre, ds1, ds2, icp, map, end
 };
 
 struct Workspace {
@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(BLOCK, 1) k_register_frame(const FrameParams P
     const double cs0 = sh.cache_stats[0], cs1 = sh.cache_stats[1], cs2 = sh.cache_stats[2];
     KB_STAMP(4);
     // local_map_.Update(frame_downsample, new_pose) (KissICP.cpp:61)
-    op_map_add(g, sh, P.m, P.ws.ds1, n_ds, true, new_pose, P.ws.tp, P.ws.next, P.ws.touched);
+    op_map_add(g, sh, P.m, P.ws.ds1, n_ds, true, new_pose, P.ws.tp, P.ws.next, P.ws.touched, &P.res->t_ns[8]);
     op_map_remove_far(P.m, new_pose.t);
     g.sync();
     KB_STAMP(5);
@@ -276,12 +276,13 @@ __global__ void __launch_bounds__(BLOCK, 1) k_barrier_bench(const Scratch sc, in
 }
 
 // table initialisation / clear
-__global__ void k_map_fill(int4 *slots, int *head, size_t capacity) {
+__global__ void k_map_fill(int4 *slots, int *head, int *pcount, size_t capacity) {
     const int4 empty = make_int4(-1, -1, -1, KB_EMPTY);
     for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < capacity;
          i += static_cast<size_t>(gridDim.x) * blockDim.x) {
         slots[i] = empty;
         head[i] = -1;
+        pcount[i] = 0;
     }
 }
 

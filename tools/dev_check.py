@@ -98,6 +98,7 @@ for k in range(30):
 import ctypes as C
 from kiss_icp_b200 import _native as N
 ns = np.zeros(64 + 4 * 148); N.check(N.lib().kb_pipeline_debug_stamps(g._h, N.ptr(ns), len(ns)))
+mp = np.zeros(3); N.check(N.lib().kb_pipeline_last_map_profile(g._h, N.ptr(mp))); print('map update split [us]: claim+lists, ordered insert, evict scan:', np.round(mp, 1))
 cs = np.zeros(3); N.check(N.lib().kb_pipeline_last_cache_stats(g._h, N.ptr(cs))); print('NN cache hits/fills/overflows (last frame, all iterations):', cs, 'iters', g.last_iterations)
 cyc = ns[16:29] - ns[16]
 names = ["start", "queries done", "block synced", "partial posted", "all arrived", "reduced", "rec loaded+expanded", "ldlt", "exp", "mul", "published", "epoch seen", "record in smem"]
