@@ -204,6 +204,8 @@ int kb_debug_icp_solve(const double A[36], const double b[6], double x_exact[6],
 /* work done by the ICP loop of the last RegisterFrame: GetClosestNeighbor calls (iterations x
  * source points) and map points examined — the inputs of the algorithmic-bytes formula */
 int kb_pipeline_last_icp_work(const kb_pipeline *p, double *queries, double *candidates);
+/* split of the two downsample phases of the last frame [us]: clear, dedupe, count, prefix+rank, replay+emit (x2) */
+int kb_pipeline_last_ds_profile(const kb_pipeline *p, double us[10]);
 /* split of the map-update phase of the last frame [us]: claim + pending lists, ordered insertion, eviction */
 int kb_pipeline_last_map_profile(const kb_pipeline *p, double us[3]);
 /* shared-memory NN cache of the ICP loop, last frame: {hits, fills, overflows} over all iterations */

@@ -136,6 +136,7 @@ SIGNATURES = {
     "kb_debug_ldlt6": (i32, [vp, vp, vp, vp]),
     "kb_debug_icp_solve": (i32, [vp, vp, vp, vp, vp, vp]),
     "kb_debug_barrier_ns": (i32, [i32, C.POINTER(dbl)]),
+    "kb_pipeline_last_ds_profile": (i32, [vp, vp]),
     "kb_pipeline_last_map_profile": (i32, [vp, vp]),
     "kb_pipeline_last_cache_stats": (i32, [vp, vp]),
     "kb_pipeline_last_icp_work": (i32, [vp, C.POINTER(dbl), C.POINTER(dbl)]),

@@ -615,7 +615,7 @@ static int nn_launch(kb_map *map, const double *d_q, size_t n, double *d_p, doub
     const size_t want = (n * 32 + threads - 1) / threads;
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, map->ex->device);
-    const unsigned blocks = static_cast<unsigned>(std::min<size_t>(want, static_cast<size_t>(sms) * 8 * 4));
+    const unsigned blocks = static_cast<unsigned>(std::min<size_t>(want, static_cast<size_t>(sms) * 4));  // 4 CTAs/SM resident, grid-stride
     if (d_cand)
         k_nn_query<true><<<blocks, threads, 0, map->ex->stream>>>(map->view(), d_q, n, d_p, d_d, d_cand);
     else
@@ -1138,6 +1138,18 @@ int kb_debug_barrier_ns(int iters, double *ns_per_barrier) {
     CK(cudaMemcpyAsync(t, c->ex->sc.dbg + 8, sizeof(t), cudaMemcpyDeviceToHost, c->ex->stream));
     RET(c->ex->sync());
     *ns_per_barrier = static_cast<double>(t[1] - t[0]) / iters;
+    return KB_OK;
+}
+int kb_pipeline_last_ds_profile(const kb_pipeline *p, double us[10]) {
+    if (!p || !us) return fail(KB_ERR_INVALID_ARG, "NULL argument");
+    const unsigned long long *t = p->last.t_ns;
+    // ds1: clear, dedupe, count, prefix+rank, replay+emit ; ds2: same
+    const unsigned long long a[6] = {t[1], t[12], t[13], t[14], t[15], t[2]};
+    const unsigned long long b[6] = {t[2], t[16], t[17], t[18], t[19], t[3]};
+    for (int i = 0; i < 5; ++i) {
+        us[i] = (static_cast<double>(a[i + 1]) - static_cast<double>(a[i])) * 1e-3;
+        us[5 + i] = (static_cast<double>(b[i + 1]) - static_cast<double>(b[i])) * 1e-3;
+    }
     return KB_OK;
 }
 int kb_pipeline_last_map_profile(const kb_pipeline *p, double us[3]) {

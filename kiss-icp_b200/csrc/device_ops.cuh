@@ -488,7 +488,7 @@ struct DsScratch {
 };
 
 __device__ __noinline__ void op_downsample(Grid &g, const Scratch &sc, Shared &sh, const double *in, int n, double voxel_size,
-                              const DsScratch &ds, double *out, int *out_n) {
+                              const DsScratch &ds, double *out, int *out_n, unsigned long long *stamps = nullptr) {
     const unsigned B = robin_bucket_count(n);
     if (B == 0) {
         if (blockIdx.x == 0 && threadIdx.x == 0) *out_n = 0;
@@ -502,6 +502,7 @@ __device__ __noinline__ void op_downsample(Grid &g, const Scratch &sc, Shared &s
         ds.sim[i] = make_int2(-1, 0);
     }
     g.sync();
+    if (stamps && blockIdx.x == 0 && threadIdx.x == 0) stamps[0] = globaltimer_ns();
     // (a) dedupe: first input index per voxel
     const VoxelDiv vd = make_voxel_div(voxel_size);
     for (int i = blockIdx.x * BLOCK + threadIdx.x; i < n; i += gridDim.x * BLOCK) {
@@ -519,6 +520,7 @@ __device__ __noinline__ void op_downsample(Grid &g, const Scratch &sc, Shared &s
         }
     }
     g.sync();
+    if (stamps && blockIdx.x == 0 && threadIdx.x == 0) stamps[1] = globaltimer_ns();
     // (b) occupancy prefix over buckets (two passes around a barrier)
     long long lo, hi;
     chunk_of(B, &lo, &hi);
@@ -527,6 +529,7 @@ __device__ __noinline__ void op_downsample(Grid &g, const Scratch &sc, Shared &s
     const int blk_cnt = block_sum(cnt, sh.warp_i);
     if (threadIdx.x == 0) sc.blk_i[blockIdx.x] = blk_cnt;
     g.sync();
+    if (stamps && blockIdx.x == 0 && threadIdx.x == 0) stamps[2] = globaltimer_ns();
     int offset, total;
     grid_offsets(sc.blk_i, &offset, &total, sh.two);
     if (blockIdx.x == 0 && threadIdx.x == 0) *out_n = total;
@@ -554,6 +557,7 @@ __device__ __noinline__ void op_downsample(Grid &g, const Scratch &sc, Shared &s
         ds.order[(s + rank) & mask] = static_cast<int>(h);
     }
     g.sync();
+    if (stamps && blockIdx.x == 0 && threadIdx.x == 0) stamps[3] = globaltimer_ns();
     // (c2) replay tsl::robin_map::insert for every run, in first-index order, then emit
     for (unsigned s = blockIdx.x * BLOCK + threadIdx.x; s < B; s += gridDim.x * BLOCK) {
         if (ds_slots[s].w == KB_EMPTY || ds_slots[(s - 1) & mask].w != KB_EMPTY) continue;  // not a run start
@@ -1050,6 +1054,7 @@ __device__ __noinline__ void op_icp(Grid &g, const Scratch &sc, Shared &sh, cons
     SE3 pending = guess;
     int j = 0;
     for (;; ++j) {
+        if (blockIdx.x == 0 && threadIdx.x == 0 && j < 20) sc.dbg[41 + j] = globaltimer_ns();
         const bool dbg_on = (j == 4);
         const unsigned tag = tag_base + static_cast<unsigned>(j) + 1u;
         icp_queries(sc, sh, m, j == 0 ? src : work, work, n, pending, max_dist, kscale, tag, dbg_on, qcache, j == 0);

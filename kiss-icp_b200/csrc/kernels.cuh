@@ -29,7 +29,7 @@ struct FrameResult {
     double icp_candidates;  // map points examined by all ICP iterations of this frame
     double icp_queries;     // GetClosestNeighbor calls (iterations x source points)
     double cache_stats[3];  // NN-cache hits / fills / overflows over all iterations
-    unsigned long long t_ns[12];  // %globaltimer at phase boundaries (CTA 0): start, pre, ds1, ds2, icp, map, end
+    unsigned long long t_ns[20];  // %globaltimer at phase boundaries (CTA 0): start, pre, ds1, ds2, icp, map, end
 };
 
 struct Workspace {
@@ -100,12 +100,12 @@ __global__ void __launch_bounds__(BLOCK, 1) k_register_frame(const FrameParams P
     const int n_pre = __ldcg(&P.ws.cnt[0]);
     // Voxelize (KissICP.cpp:70-75)
     op_downsample(g, P.sc, sh, P.ws.pre, n_pre, P.voxel_size * 0.5, P.ws.ds, P.ws.ds1,
-                  &P.ws.cnt[1]);
+                  &P.ws.cnt[1], &P.res->t_ns[12]);
     g.sync();
     KB_STAMP(2);
     const int n_ds = __ldcg(&P.ws.cnt[1]);
     op_downsample(g, P.sc, sh, P.ws.ds1, n_ds, P.voxel_size * 1.5, P.ws.ds, P.ws.src,
-                  &P.ws.cnt[2]);
+                  &P.ws.cnt[2], &P.res->t_ns[16]);
     g.sync();
     KB_STAMP(3);
     const int n_src = __ldcg(&P.ws.cnt[2]);
@@ -309,19 +309,118 @@ __global__ void k_map_rehash(const MapView from, const MapView to) {
     }
 }
 
-// batched GetClosestNeighbor (VoxelHashMap.cpp:46-70): one warp per query, grid-stride
+// batched GetClosestNeighbor (VoxelHashMap.cpp:46-70): one warp per query, grid-stride.
+// Bandwidth-bound at scale (BASELINE config 5): every query is three dependent DRAM round trips
+// (query, 27 slot probes, candidate blocks), so the kernel is built for memory-level parallelism:
+// <= 64 registers (4 CTAs of 256 threads = 32 warps per SM) and the NEXT query's point and first
+// probe are issued before the current query's candidates are reduced.
+struct NNProbe {
+    V3 q;
+    int3 v;
+    unsigned h;  // first bucket of this lane's neighbour voxel
+    int4 s;      // that bucket
+};
+
+__device__ __forceinline__ void nn_issue(const MapView &m, const double *__restrict__ q, size_t i, int lane, NNProbe &pr) {
+    pr.q = V3{q[3 * i], q[3 * i + 1], q[3 * i + 2]};
+    pr.v = point_to_voxel(pr.q.x, pr.q.y, pr.q.z, m.vdiv);
+    if (lane < 27) {
+        pr.h = mix_hash(pr.v.x + c_shifts[lane][0], pr.v.y + c_shifts[lane][1], pr.v.z + c_shifts[lane][2]) & m.mask;
+        pr.s = m.slots[pr.h];
+    }
+}
+
+// finish the probe started by nn_issue (collision chain), then gather + reduce exactly like nn_search_warp
+__device__ __forceinline__ NNResult nn_finish(const MapView &m, const NNProbe &pr, int lane, WarpNN &w) {
+    int cnt = 0, slot = -1;
+    if (lane < 27) {
+        const int x = pr.v.x + c_shifts[lane][0], y = pr.v.y + c_shifts[lane][1], z = pr.v.z + c_shifts[lane][2];
+        unsigned h = pr.h;
+        int4 s = pr.s;
+        for (unsigned probes = 0; probes <= m.mask; ++probes) {
+            if (s.w == KB_EMPTY) break;
+            if (s.w != KB_TOMB && s.x == x && s.y == y && s.z == z) {
+                cnt = s.w;
+                slot = static_cast<int>(h);
+                break;
+            }
+            h = (h + 1) & m.mask;
+            s = m.slots[h];
+        }
+    }
+    const V3 q = pr.q;
+    double best = DBL_MAX, best_d2 = DBL_MAX;
+    int bseq = INT_MAX;
+    V3 bp{0, 0, 0};
+    const int cap = m.cap;
+    int total;
+    if (cap <= NN_FLAT_CAP) {
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(FULL, incl, o);
+            if (lane >= o) incl += t;
+        }
+        const int start = incl - cnt;
+        total = __shfl_sync(FULL, incl, 31);
+        __syncwarp();
+        if (lane < 27) {
+            w.slot[lane] = slot;
+            w.start[lane] = start;
+            for (int k = 0; k < cnt; ++k) w.owner[start + k] = static_cast<unsigned char>(lane);
+        }
+        __syncwarp();
+        constexpr int U = 2;
+        for (int base = 0; base < total; base += 32 * U) {
+            V3 c[U];
+            bool ok[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int j = base + u * 32 + lane;
+                ok[u] = j < total;
+                if (ok[u]) {
+                    const int vi = w.owner[j];
+                    const double *pp = m.points + (static_cast<size_t>(w.slot[vi]) * cap + (j - w.start[vi])) * 3;
+                    c[u] = V3{pp[0], pp[1], pp[2]};
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (ok[u]) nn_consider(c[u], q, base + u * 32 + lane, best, best_d2, bseq, bp);
+        }
+    } else {
+        unsigned occ = __ballot_sync(FULL, cnt > 0);
+        total = 0;
+        while (occ) {
+            const int vi = __ffs(occ) - 1;
+            occ &= occ - 1;
+            const int c = __shfl_sync(FULL, cnt, vi);
+            const int sidx = __shfl_sync(FULL, slot, vi);
+            total += c;
+            const double *blk = m.points + static_cast<size_t>(sidx) * cap * 3;
+            for (int k = lane; k < c; k += 32)
+                nn_consider(V3{blk[3 * k], blk[3 * k + 1], blk[3 * k + 2]}, q, vi * 1024 + k, best, best_d2, bseq, bp);
+        }
+    }
+    nn_reduce(best, bseq, bp);
+    return NNResult{best, bp, total};
+}
+
 template <bool COUNT>
-__global__ void __launch_bounds__(256) k_nn_query(const MapView m, const double *__restrict__ q, size_t n,
-                                                  double *__restrict__ out_p, double *__restrict__ out_d,
-                                                  unsigned long long *cand_total) {
+__global__ void __launch_bounds__(256, 4) k_nn_query(const MapView m, const double *__restrict__ q, size_t n,
+                                                     double *__restrict__ out_p, double *__restrict__ out_d,
+                                                     unsigned long long *cand_total) {
     __shared__ WarpNN wnn[8];  // blockDim.x == 256
     const int lane = threadIdx.x & 31;
     const size_t gw = (blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x) >> 5;
     const size_t nw = (static_cast<size_t>(gridDim.x) * blockDim.x) >> 5;
     unsigned long long cand = 0;
+    NNProbe cur, nxt;
+    if (gw < n) nn_issue(m, q, gw, lane, cur);
     for (size_t i = gw; i < n; i += nw) {
-        const V3 p{q[3 * i], q[3 * i + 1], q[3 * i + 2]};
-        const NNResult r = nn_search_warp(m, p, lane, wnn[threadIdx.x >> 5]);
+        const bool more = i + nw < n;
+        if (more) nn_issue(m, q, i + nw, lane, nxt);  // next query's loads fly while this one is reduced
+        const NNResult r = nn_finish(m, cur, lane, wnn[threadIdx.x >> 5]);
         if (lane == 0) {
             out_p[3 * i] = r.p.x;
             out_p[3 * i + 1] = r.p.y;
@@ -329,6 +428,7 @@ __global__ void __launch_bounds__(256) k_nn_query(const MapView m, const double 
             out_d[i] = r.d;
         }
         if (COUNT) cand += r.candidates;
+        if (more) cur = nxt;
     }
     if (COUNT && lane == 0 && cand) atomicAdd(cand_total, cand);
 }

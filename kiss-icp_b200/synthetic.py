@@ -208,3 +208,24 @@ def ouster128_shape(seed=0, device="cpu", **kw):
 def small_shape(seed=0, beams=16, cols=256, stamps="none", device="cpu", **kw):
     """Reduced scan for CPU-speed tests."""
     return SyntheticLidar(seed=seed, beams=beams, cols=cols, elev_deg=(-24.8, 2.0), stamps=stamps, device=device, **kw)
+
+
+def surface_cloud(n_raw: int, seed: int = 0, density: float = 14.0, wall_spacing: float = 25.0, wall_height: float = 6.0):
+    """Dense map-like cloud for the NN-query sweep (BASELINE config 5): points on a ground sheet and on
+    vertical wall sheets at ``density`` points per m^2, so that a 1 m voxel map built from it holds ~8-10
+    points per voxel (real KISS-ICP maps: ~8) instead of the ~2 of uniform 3-D noise. Returns (n_raw, 3)."""
+    rng = np.random.default_rng(seed)
+    n_g = n_raw // 2
+    n_w = n_raw - n_g
+    side = math.sqrt(n_g / density)
+    ground = np.stack([rng.uniform(-side / 2, side / 2, n_g), rng.uniform(-side / 2, side / 2, n_g),
+                       rng.normal(0.0, 0.03, n_g)], 1)
+    n_planes = max(1, int(side // wall_spacing))
+    along = rng.uniform(-side / 2, side / 2, n_w)
+    plane = (rng.integers(0, n_planes, n_w) - n_planes / 2 + 0.5) * wall_spacing + rng.normal(0.0, 0.03, n_w)
+    z = rng.uniform(0.0, wall_height, n_w)
+    flip = rng.random(n_w) < 0.5
+    walls = np.stack([np.where(flip, plane, along), np.where(flip, along, plane), z], 1)
+    pts = np.concatenate([ground, walls])
+    rng.shuffle(pts)
+    return pts

@@ -98,12 +98,23 @@ for k in range(30):
 import ctypes as C
 from kiss_icp_b200 import _native as N
 ns = np.zeros(64 + 4 * 148); N.check(N.lib().kb_pipeline_debug_stamps(g._h, N.ptr(ns), len(ns)))
+dp = np.zeros(10); N.check(N.lib().kb_pipeline_last_ds_profile(g._h, N.ptr(dp))); print('downsample split [us] (clear, dedupe, count, prefix+rank, replay+emit) ds1:', np.round(dp[:5], 1), 'ds2:', np.round(dp[5:], 1))
 mp = np.zeros(3); N.check(N.lib().kb_pipeline_last_map_profile(g._h, N.ptr(mp))); print('map update split [us]: claim+lists, ordered insert, evict scan:', np.round(mp, 1))
 cs = np.zeros(3); N.check(N.lib().kb_pipeline_last_cache_stats(g._h, N.ptr(cs))); print('NN cache hits/fills/overflows (last frame, all iterations):', cs, 'iters', g.last_iterations)
 cyc = ns[16:29] - ns[16]
 names = ["start", "queries done", "block synced", "partial posted", "all arrived", "reduced", "rec loaded+expanded", "ldlt", "exp", "mul", "published", "epoch seen", "record in smem"]
 print("CTA0 iteration-4 timeline [us @1.965GHz]:", ", ".join("%s %.2f" % (n_, c / 1965.0) for n_, c in zip(names, cyc)))
 cta = ns[64:].reshape(-1, 4)
+it = ns[41:41 + min(g.last_iterations, 20)]; print('ICP iteration durations [us]:', np.round(np.diff(it) * 1e-3, 1))
+# experiment: the same alignment twice through the stand-alone API (second call: map data L2-warm, same kernel)
+reg2 = K.Registration(500, 1e-4, 0)
+src2 = O.voxel_down_sample(O.voxel_down_sample(p, 0.5), 1.5)
+guess2 = g.last_pose @ O.se3_exp([0.4, 0.05, 0.0, 0.0, 0.0, 0.01])
+for rep in range(3):
+    reg2.align_points_to_map(src2, g.local_map, guess2, 3.0, 1.0)
+    N.check(N.lib().kb_pipeline_debug_stamps(g._h, N.ptr(ns), len(ns)))
+    it = ns[41:41 + min(reg2.last_iterations, 20)]
+    print('  stand-alone align rep', rep, 'n_src', len(src2), 'iters', reg2.last_iterations, 'iteration durations [us]:', np.round(np.diff(it) * 1e-3, 1))
 print('gather rounds in the last ICP iteration of the last frame:', ns[40])
 dur = cta[:, 0] - cta[:, 3]
 order = np.argsort(-dur)[:12]
