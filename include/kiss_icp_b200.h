@@ -93,6 +93,9 @@ int kb_map_closest_neighbors(const kb_map *map, const double *queries, size_t n,
                              double *out_dist);
 int kb_map_closest_neighbors_dev(const kb_map *map, const double *d_queries, size_t n, double *d_out_points,
                                  double *d_out_dist);
+/* rebuild the table at load factor <= 0.5 without tombstones (smallest power-of-two capacity): shrinks the
+ * address range the point blocks are scattered over — for query-heavy phases on a static map */
+int kb_map_compact(kb_map *map);
 /* public data members voxel_size_, max_distance_, max_points_per_voxel_ VoxelHashMap.hpp:53-55 */
 int kb_map_params(const kb_map *map, double *voxel_size, double *max_distance, unsigned *max_points_per_voxel);
 /* ALGORITHMIC bytes of kb_map_closest_neighbors_dev for these n queries on this map: sum over

@@ -102,6 +102,7 @@ SIGNATURES = {
     "kb_map_dump": (i32, [vp, vp, vp, vp, sz, sz, C.POINTER(sz), C.POINTER(sz)]),
     "kb_map_closest_neighbors": (i32, [vp, vp, sz, vp, vp]),
     "kb_map_closest_neighbors_dev": (i32, [vp, vp, sz, vp, vp]),
+    "kb_map_compact": (i32, [vp]),
     "kb_map_params": (i32, [vp, C.POINTER(dbl), C.POINTER(dbl), C.POINTER(u32)]),
     "kb_map_query_bytes_dev": (i32, [vp, vp, sz, C.POINTER(dbl)]),
     "kb_map_sync": (i32, [vp]),

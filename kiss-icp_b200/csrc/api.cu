@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <numeric>
@@ -268,15 +269,15 @@ struct kb_map {
         return KB_OK;
     }
     // make room for `extra` more voxels at load factor <= 0.5 (tombstones count as load)
-    int ensure_capacity(size_t extra) {
+    int ensure_capacity(size_t extra, size_t force_want = 0) {
         CK(cudaSetDevice(ex->device));
         if (!counters) {
             CK(cudaMalloc(&counters, sizeof(int) * C_NCOUNTERS));
             CK(cudaMemsetAsync(counters, 0, sizeof(int) * C_NCOUNTERS, ex->stream));
         }
         const size_t live = static_cast<size_t>(h_counters[C_LIVE]), tomb = static_cast<size_t>(h_counters[C_TOMB]);
-        if (capacity && (live + tomb + extra) * 2 <= capacity) return KB_OK;
-        const size_t want = std::max<size_t>(pow2_at_least(4 * (live + extra)), size_t(1) << 14);
+        if (!force_want && capacity && (live + tomb + extra) * 2 <= capacity) return KB_OK;
+        const size_t want = force_want ? force_want : std::max<size_t>(pow2_at_least(4 * (live + extra)), size_t(1) << 14);
         if (want > (size_t(1) << 31)) return fail(KB_ERR_INVALID_ARG, "voxel table would exceed 2^31 slots");
         int4 *ns;
         double *np;
@@ -520,6 +521,14 @@ int kb_map_remove_far(kb_map *map, const double origin[3]) {
     if (!map || !origin) return fail(KB_ERR_INVALID_ARG, "NULL argument");
     return map->update_host(nullptr, 0, false, se3_identity(), false, true, V3{origin[0], origin[1], origin[2]});
 }
+int kb_map_compact(kb_map *map) {
+    if (!map) return fail(KB_ERR_INVALID_ARG, "map == NULL");
+    const size_t live = static_cast<size_t>(map->h_counters[C_LIVE]);
+    const size_t want = std::max<size_t>(pow2_at_least(2 * live + 2), size_t(1) << 14);
+    if (want >= map->capacity && map->h_counters[C_TOMB] == 0) return KB_OK;
+    RET(map->ensure_capacity(0, want));
+    return map->ex->sync();
+}
 int kb_map_num_points(const kb_map *map, size_t *out) {
     if (!map || !out) return fail(KB_ERR_INVALID_ARG, "NULL argument");
     *out = static_cast<size_t>(map->h_counters[C_POINTS]);
@@ -611,11 +620,11 @@ int kb_map_pointcloud(const kb_map *map, double *out_xyz, size_t capacity, size_
 
 static int nn_launch(kb_map *map, const double *d_q, size_t n, double *d_p, double *d_d, unsigned long long *d_cand) {
     if (n == 0) return KB_OK;
-    const int threads = 256;
-    const size_t want = (n * 32 + threads - 1) / threads;
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, map->ex->device);
-    const unsigned blocks = static_cast<unsigned>(std::min<size_t>(want, static_cast<size_t>(sms) * 4));  // 4 CTAs/SM resident, grid-stride
+    const int threads = 256;
+    const size_t want = (n * 32 + threads - 1) / threads;
+    const unsigned blocks = static_cast<unsigned>(std::min<size_t>(want, static_cast<size_t>(sms) * 4));  // 4 CTAs/SM, grid-stride
     if (d_cand)
         k_nn_query<true><<<blocks, threads, 0, map->ex->stream>>>(map->view(), d_q, n, d_p, d_d, d_cand);
     else

@@ -72,6 +72,10 @@ class VoxelHashMap:
         return out
 
     # -- extras (no reference counterpart in Python; C++ has GetClosestNeighbor) ----------------
+    def compact(self):
+        """rebuild the table at the smallest capacity (load <= 0.5, no tombstones)"""
+        N.check(N.lib().kb_map_compact(self._h))
+
     def num_points(self) -> int:
         n = N.sz(0)
         N.check(N.lib().kb_map_num_points(self._h, C.byref(n)))
