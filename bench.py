@@ -271,7 +271,10 @@ def main():
     kern_us = prof.sum(1)  # %globaltimer span of the kernel (CTA 0), live, per launch
     achieved = float(bytes_per_launch.mean() / (kern_us.mean() * 1e-6) / 1e9)
     roofline = {"kernel": "k_register_frame (persistent cooperative, 1 launch/scan)", "bound": "hbm",
-                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "algorithmic_bytes_per_launch": float(bytes_per_launch.mean()), "kernel_us": float(kern_us.mean()),
+                "traffic": profiled_traffic("r1_register_frame"),
+                "traffic_source": "profiles/r1_register_frame_ncu_raw_selected.csv (ncu --set full, bytes per launch)",
                 "peak_source": peak_src,
                 "note": "latency-bound: ~%.0f ICP iterations x %.0f queries per launch, working set L2-resident; "
                         "kernel time from in-kernel %%globaltimer stamps; see nn_kernel for the bandwidth-bound NN query"
@@ -302,6 +305,21 @@ def main():
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def profiled_traffic(tag):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full summary
+    (profiles/<tag>_ncu_raw_selected.csv, produced by tools/summarize_profiles.py); None when absent."""
+    import csv
+    path = os.path.join(ROOT, "profiles", f"{tag}_ncu_raw_selected.csv")
+    if not os.path.exists(path):
+        return None
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    per_launch = {}
+    for r in csv.DictReader(open(path)):
+        if r["metric"] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            per_launch[r["launch"]] = per_launch.get(r["launch"], 0.0) + float(r["value"]) * scale.get(r["unit"], 1.0)
+    return float(np.mean(list(per_launch.values()))) if per_launch else None
 
 
 def nn_leg(K, N, L, torch, dev, peak):
@@ -336,7 +354,8 @@ def nn_leg(K, N, L, torch, dev, peak):
     ach = b.value / (ms * 1e-3) / 1e9
     return {"kernel": "k_nn_query", "map_points": int(stored.shape[0]), "map_voxels": m.num_voxels(), "queries": n_q, "points_per_voxel": float(stored.shape[0]) / max(m.num_voxels(), 1),
             "algorithmic_bytes": b.value, "bytes_per_query": b.value / n_q, "ms": ms, "achieved": ach, "peak": peak,
-            "unit": "GB/s", "frac": ach / peak, "l2": "flushed (256 MiB write) before every timed launch", "reps": len(times)}
+            "unit": "GB/s", "frac": ach / peak, "traffic": profiled_traffic("r1_nn_query"),
+            "l2": "flushed (256 MiB write) before every timed launch", "reps": len(times)}
 
 
 def cpu_leg(args, lidar):

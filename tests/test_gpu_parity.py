@@ -340,3 +340,35 @@ def test_pipeline_errors_and_state_accessors(K, O):
         icp.last_delta = np.diag([1.0, 2.0, 1.0, 1.0])
     icp.register_frame(np.empty((0, 3)), np.empty(0))  # empty frame: pose = last_pose * last_delta
     assert np.allclose(icp.last_pose, T, atol=1e-12)
+
+
+def test_pipeline_ouster128_shape_full_size(K, O):
+    """BASELINE config-3 shape: 128 x 1024 rays, voxel 0.3 m, per-column stamps (deskew on), a few scans"""
+    import torch
+    from kiss_icp_b200 import synthetic
+    L = synthetic.ouster128_shape(seed=2, device="cuda" if torch.cuda.is_available() else "cpu")
+    g, o = K.KissICP(K.load_config(voxel_size=0.3)), O.KissICP(voxel_size=0.3)
+    for k in range(5):
+        p, t = L.scan(k)
+        assert len(p) > 60000 and len(t) == len(p)
+        g.register_frame(p, t, return_clouds=False)
+        o.register_frame(p, t, want_clouds=False)
+        dt, dr = pose_error(g.last_pose, o.pose)
+        assert dt < 1e-4 and dr < 1e-4  # BASELINE bar
+        assert dt < 1e-6 and dr < 1e-6  # expected ~1e-14 (device sin/cos in the deskew differ in the last ulps)
+    assert abs(g.local_map.num_points() - o.local_map.num_points()) <= 2
+
+
+def test_map_compact_keeps_content(K, O):
+    pts = rng.normal(size=(40000, 3)) * 8
+    g, o = K.VoxelHashMap(1.0, 20.0, 20), O.VoxelHashMap(1.0, 20.0, 20)
+    g.add_points(pts)
+    o.add_points(pts)
+    g.remove_far_away_points([3.0, 0.0, 0.0])
+    o.remove_far_away_points([3.0, 0.0, 0.0])
+    g.compact()
+    assert_maps_equal(g, o)
+    q = pts[::7] + 0.1
+    ap, ad = g.closest_neighbors(q)
+    bp, bd = o.closest_neighbors(q)
+    assert np.array_equal(ap, bp) and np.array_equal(ad, bd)
