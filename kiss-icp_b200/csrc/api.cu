@@ -173,9 +173,9 @@ int make_exec(std::shared_ptr<Exec> *out) {
 // per-call workspace sized by the largest cloud seen
 struct Work {
     DBuf<double> in, ts, tmp, pre, ds1, src, work, tp;
-    DBuf<int> next, touched, ds_prefix, ds_order, cnt;
-    DBuf<int4> ds_slots;
-    DBuf<int2> ds_sim;
+    DBuf<int> next, touched, ds_chunk, ds_order, ds2_chunk, ds2_order, cnt;
+    DBuf<int4> ds_slots, ds2_slots;
+    DBuf<int2> ds_sim, ds2_sim;
     int ensure(size_t n) {
         n = std::max<size_t>(n, 1);
         RET(in.ensure(3 * n));
@@ -190,15 +190,20 @@ struct Work {
         RET(touched.ensure(n));
         const size_t b = pow2_at_least(2 * n);
         RET(ds_slots.ensure(b));
-        RET(ds_prefix.ensure(b));
+        RET(ds_chunk.ensure(DS_MAX_CHUNKS));
         RET(ds_order.ensure(b));
         RET(ds_sim.ensure(b));
+        RET(ds2_slots.ensure(b));
+        RET(ds2_chunk.ensure(DS_MAX_CHUNKS));
+        RET(ds2_order.ensure(b));
+        RET(ds2_sim.ensure(b));
         RET(cnt.ensure(8));
         return KB_OK;
     }
-    DsScratch ds_view() { return DsScratch{ds_slots.p, ds_prefix.p, ds_order.p, ds_sim.p}; }
+    DsScratch ds_view() { return DsScratch{ds_slots.p, ds_chunk.p, ds_order.p, ds_sim.p}; }
+    DsScratch ds2_view() { return DsScratch{ds2_slots.p, ds2_chunk.p, ds2_order.p, ds2_sim.p}; }
     Workspace view() {
-        return Workspace{tmp.p, pre.p, ds1.p, src.p, work.p, tp.p, next.p, touched.p, ds_view(), cnt.p};
+        return Workspace{tmp.p, pre.p, ds1.p, src.p, work.p, tp.p, next.p, touched.p, ds_view(), ds2_view(), cnt.p};
     }
 };
 

@@ -33,6 +33,7 @@ constexpr int BLOCK = 512;  // threads per CTA of every cooperative kernel
 constexpr int NWARPS = BLOCK / 32;
 constexpr int NACC = 16;  // unique accumulators of the 6x6 normal equations (see icp_accumulate)
 constexpr int NPART = NACC + 5;  // per-CTA partial: accumulators, #correspondences, #candidate points, cache hits/fills/overflows
+constexpr int DS_MAX_CHUNKS = 4096;  // downsample: 32-bucket chunks up to 131072 buckets (a 65k-point scan), coarser beyond
 constexpr int BAR_ARRIVE = 32, BAR_EPOCH = 64, BAR_WORDS = 96;  // word offsets inside Scratch::bar
 constexpr int ICP_REC = 32;
 constexpr int LL_RES = 16;        // est(7) + done flag, final pose(7), spare      // est(7) t_icp(7) final(7) conv cand_total query_total ...
@@ -343,6 +344,7 @@ constexpr size_t QC_BYTES = sizeof(QCache) * QC_SLOTS * NWARPS;
 struct Shared {
     int warp_i[NWARPS + 1];
     int two[2];
+    int chunk_pref[DS_MAX_CHUNKS];  // exclusive prefix of the downsample chunk counts
     double warp_d[NWARPS][NPART];
     double warp_c[NWARPS];
     double red[NPART];
@@ -465,10 +467,11 @@ __device__ __noinline__ void op_preprocess(Grid &g, const Scratch &sc, Shared &s
 //   maximal occupied runs of the final table never interacted (the empty bucket between them
 //   was always empty); (3) inside a run the layout DOES depend on history (a displaced entry
 //   leapfrogs residents of equal probe distance), so each run is replayed exactly.
-//   Phases: (a) fill a scratch table by linear probing from the reference's home bucket with a
-//   128-bit CAS + atomicMin(first index); (b) prefix-count occupied buckets; (c1) every entry
-//   ranks itself by first index inside its run; (c2) one thread per run replays the robin-hood
-//   inserts of that run in index order and emits the points at prefix[bucket].
+//   Phases: [clear] | dedupe: linear probing from the reference's home bucket with a 128-bit CAS +
+//   atomicMin(first index), counting claimed buckets per chunk | one warp per chunk: exclusive
+//   chunk prefix, singleton runs emitted per lane, longer runs replayed IN REGISTERS (lane =
+//   bucket of the run, robin-hood swap chain via ballots) and emitted at their bucket's rank.
+//   Two grid barriers per call (one when the caller pre-cleared the scratch tables).
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned robin_bucket_count(int n) {
     if (n <= 0) return 0;
@@ -481,14 +484,67 @@ __device__ __forceinline__ unsigned robin_bucket_count(int n) {
 }
 
 struct DsScratch {
-    int4 *slots;   // [B] {voxel, first index}
-    int *prefix;   // [B] occupied buckets before this one
-    int *order;    // [B] run-local insertion order: order[s + k] = bucket of the k-th inserted entry
-    int2 *sim;     // [B] replayed robin-hood layout {first index (-1 empty), home offset in run}
+    int4 *slots;     // [B] {voxel, first index}
+    int *chunk_cnt;  // [DS_MAX_CHUNKS] claimed buckets per chunk of the table
+    int *order;      // [B] general path only: run-local insertion order
+    int2 *sim;       // [B] general path only: replayed layout {first index (-1 empty), home offset in run}
 };
 
+// chunk geometry: at most DS_MAX_CHUNKS chunks of at least 32 buckets (one warp-wide group): small tables
+// still spread over hundreds of warps and the per-chunk counters see little atomic contention
+__device__ __forceinline__ unsigned ds_chunk_shift(unsigned B) {
+    unsigned sh = 5;
+    while ((B >> sh) > static_cast<unsigned>(DS_MAX_CHUNKS)) ++sh;
+    return sh;
+}
+
+// clear the scratch for a table of n inputs (grid-stride; the caller provides the barrier)
+__device__ __forceinline__ void ds_clear(const DsScratch &ds, int n_upper) {
+    const unsigned B = robin_bucket_count(n_upper);
+    const int4 empty = make_int4(-1, -1, -1, KB_EMPTY);
+    for (unsigned i = blockIdx.x * BLOCK + threadIdx.x; i < B; i += gridDim.x * BLOCK) ds.slots[i] = empty;
+    for (unsigned i = blockIdx.x * BLOCK + threadIdx.x; i < static_cast<unsigned>(DS_MAX_CHUNKS); i += gridDim.x * BLOCK)
+        ds.chunk_cnt[i] = 0;
+}
+
+// general (slow, rare) replay of one run longer than a warp: lane 0, global scratch
+__device__ __noinline__ void ds_replay_long_run(const DsScratch &ds, unsigned s, unsigned L, unsigned mask) {
+    // insertion order by first index: order[s + rank]
+    for (unsigned k = 0; k < L; ++k) {
+        const int my = ds.slots[(s + k) & mask].w;
+        unsigned rank = 0;
+        for (unsigned j = 0; j < L; ++j) rank += (ds.slots[(s + j) & mask].w < my) ? 1u : 0u;
+        ds.order[(s + rank) & mask] = static_cast<int>((s + k) & mask);
+        ds.sim[(s + k) & mask] = make_int2(-1, 0);
+    }
+    for (unsigned k = 0; k < L; ++k) {
+        const int4 e = ds.slots[ds.order[(s + k) & mask]];
+        int ci = e.w;
+        int ch = static_cast<int>(((ref_hash(e.x, e.y, e.z) & mask) - s) & mask);
+        int r = ch;
+        while (true) {  // insert_impl search: stop at the first bucket whose resident is "richer"
+            const int2 t = ds.sim[(s + r) & mask];
+            if (t.x < 0 || (r - ch) > (r - t.y)) break;
+            ++r;
+        }
+        while (true) {  // insert_value: robin-hood swap chain until an empty bucket
+            const int2 t = ds.sim[(s + r) & mask];
+            if (t.x < 0) break;
+            if ((r - ch) > (r - t.y)) {
+                ds.sim[(s + r) & mask] = make_int2(ci, ch);
+                ci = t.x;
+                ch = t.y;
+            }
+            ++r;
+        }
+        ds.sim[(s + r) & mask] = make_int2(ci, ch);
+    }
+}
+
 __device__ __noinline__ void op_downsample(Grid &g, const Scratch &sc, Shared &sh, const double *in, int n, double voxel_size,
-                              const DsScratch &ds, double *out, int *out_n, unsigned long long *stamps = nullptr) {
+                              const DsScratch &ds, double *out, int *out_n, unsigned long long *stamps = nullptr,
+                              bool precleared = false) {
+    (void)sc;
     const unsigned B = robin_bucket_count(n);
     if (B == 0) {
         if (blockIdx.x == 0 && threadIdx.x == 0) *out_n = 0;
@@ -497,13 +553,15 @@ __device__ __noinline__ void op_downsample(Grid &g, const Scratch &sc, Shared &s
     const unsigned mask = B - 1;
     int4 *ds_slots = ds.slots;
     const int4 empty = make_int4(-1, -1, -1, KB_EMPTY);
-    for (unsigned i = blockIdx.x * BLOCK + threadIdx.x; i < B; i += gridDim.x * BLOCK) {
-        ds_slots[i] = empty;
-        ds.sim[i] = make_int2(-1, 0);
+    const unsigned csh = ds_chunk_shift(B);
+    const unsigned CH = 1u << csh;
+    const unsigned nchunks = (B + CH - 1) >> csh;
+    if (!precleared) {
+        ds_clear(ds, n);
+        g.sync();
     }
-    g.sync();
     if (stamps && blockIdx.x == 0 && threadIdx.x == 0) stamps[0] = globaltimer_ns();
-    // (a) dedupe: first input index per voxel
+    // (a) dedupe: first input index per voxel; claimed buckets are counted per chunk
     const VoxelDiv vd = make_voxel_div(voxel_size);
     for (int i = blockIdx.x * BLOCK + threadIdx.x; i < n; i += gridDim.x * BLOCK) {
         const int3 v = point_to_voxel(in[3 * i], in[3 * i + 1], in[3 * i + 2], vd);
@@ -511,7 +569,10 @@ __device__ __noinline__ void op_downsample(Grid &g, const Scratch &sc, Shared &s
         while (true) {
             int4 s = ds_slots[h];
             if (s.w == KB_EMPTY) s = cas_slot(&ds_slots[h], empty, make_int4(v.x, v.y, v.z, i));
-            if (s.w == KB_EMPTY) break;  // claimed with our index
+            if (s.w == KB_EMPTY) {  // claimed with our index
+                atomicAdd(&ds.chunk_cnt[h >> csh], 1);
+                break;
+            }
             if (s.x == v.x && s.y == v.y && s.z == v.z) {
                 atomicMin(&ds_slots[h].w, i);
                 break;
@@ -520,78 +581,135 @@ __device__ __noinline__ void op_downsample(Grid &g, const Scratch &sc, Shared &s
         }
     }
     g.sync();
-    if (stamps && blockIdx.x == 0 && threadIdx.x == 0) stamps[1] = globaltimer_ns();
-    // (b) occupancy prefix over buckets (two passes around a barrier)
-    long long lo, hi;
-    chunk_of(B, &lo, &hi);
-    int cnt = 0;
-    for (long long i = lo + threadIdx.x; i < hi; i += BLOCK) cnt += (ds_slots[i].w != KB_EMPTY) ? 1 : 0;
-    const int blk_cnt = block_sum(cnt, sh.warp_i);
-    if (threadIdx.x == 0) sc.blk_i[blockIdx.x] = blk_cnt;
-    g.sync();
-    if (stamps && blockIdx.x == 0 && threadIdx.x == 0) stamps[2] = globaltimer_ns();
-    int offset, total;
-    grid_offsets(sc.blk_i, &offset, &total, sh.two);
-    if (blockIdx.x == 0 && threadIdx.x == 0) *out_n = total;
-    int run = offset;
-    for (long long base = lo; base < hi; base += BLOCK) {
-        const long long i = base + threadIdx.x;
-        const int occ = (i < hi && ds_slots[i].w != KB_EMPTY) ? 1 : 0;
-        int tile_total;
-        const int rank = block_rank(occ, &tile_total, sh.warp_i);
-        if (i < hi) ds.prefix[i] = run + rank;
-        run += tile_total;
-    }
-    // (c1) insertion order inside every run (no barrier needed between (b) and (c1): disjoint data)
-    for (unsigned h = blockIdx.x * BLOCK + threadIdx.x; h < B; h += gridDim.x * BLOCK) {
-        const int my = ds_slots[h].w;
-        if (my == KB_EMPTY) continue;
-        unsigned s = h;  // start of the occupied run containing h
-        while (ds_slots[(s - 1) & mask].w != KB_EMPTY) s = (s - 1) & mask;
-        unsigned rank = 0;
-        for (unsigned p = s;; p = (p + 1) & mask) {
-            const int w = ds_slots[p].w;
-            if (w == KB_EMPTY) break;
-            rank += (w < my) ? 1u : 0u;
+    if (stamps && blockIdx.x == 0 && threadIdx.x == 0) stamps[1] = stamps[2] = stamps[3] = globaltimer_ns();
+    // (b) exclusive prefix of the chunk counts (every CTA, in shared memory): DS_MAX_CHUNKS / BLOCK chunks per thread
+    {
+        constexpr int PER = DS_MAX_CHUNKS / BLOCK;
+        const int t = threadIdx.x;
+        int cv[PER];
+        int v = 0;
+#pragma unroll
+        for (int k = 0; k < PER; ++k) {
+            cv[k] = (PER * t + k < static_cast<int>(nchunks)) ? __ldcg(&ds.chunk_cnt[PER * t + k]) : 0;
+            v += cv[k];
         }
-        ds.order[(s + rank) & mask] = static_cast<int>(h);
+        const int mine = v;
+        const int lane = t & 31, warp = t >> 5;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int u = __shfl_up_sync(FULL, v, o);
+            if (lane >= o) v += u;
+        }
+        __syncthreads();
+        if (lane == 31) sh.warp_i[warp] = v;
+        __syncthreads();
+        int before = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < NWARPS; ++w) {
+            const int c = sh.warp_i[w];
+            if (w < warp) before += c;
+            total += c;
+        }
+        int excl = before + v - mine;
+#pragma unroll
+        for (int k = 0; k < PER; ++k) {
+            sh.chunk_pref[PER * t + k] = excl;
+            excl += cv[k];
+        }
+        if (blockIdx.x == 0 && t == 0) *out_n = total;
+        __syncthreads();
     }
-    g.sync();
-    if (stamps && blockIdx.x == 0 && threadIdx.x == 0) stamps[3] = globaltimer_ns();
-    // (c2) replay tsl::robin_map::insert for every run, in first-index order, then emit
-    for (unsigned s = blockIdx.x * BLOCK + threadIdx.x; s < B; s += gridDim.x * BLOCK) {
-        if (ds_slots[s].w == KB_EMPTY || ds_slots[(s - 1) & mask].w != KB_EMPTY) continue;  // not a run start
-        unsigned L = 0;
-        for (; ds_slots[(s + L) & mask].w != KB_EMPTY; ++L) {
-            const int4 e = ds_slots[ds.order[(s + L) & mask]];
-            int ci = e.w;                                                               // entry being carried
-            int ch = static_cast<int>(((ref_hash(e.x, e.y, e.z) & mask) - s) & mask);   // its home, run-relative
-            int r = ch;
-            // insert_impl search: stop at the first bucket whose resident is "richer"
-            while (true) {
-                const int2 t = ds.sim[(s + r) & mask];
-                if (t.x < 0 || (r - ch) > (r - t.y)) break;
-                ++r;
+    // (c) one warp per chunk: singleton runs per lane, longer runs replayed in registers
+    const int lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
+    for (unsigned c = blockIdx.x + gridDim.x * (threadIdx.x >> 5); c < nchunks; c += gridDim.x * NWARPS) {
+        const unsigned cbase = c << csh;
+        const unsigned cend = min(cbase + CH, B);
+        int before = sh.chunk_pref[c];  // occupied buckets before the current group
+        unsigned prev_occ = (ds_slots[(cbase - 1) & mask].w != KB_EMPTY) ? 1u : 0u;  // bucket before the group
+        for (unsigned gb = cbase; gb < cend; gb += 32) {
+            const unsigned b = gb + lane;
+            const int4 e = (b < cend) ? ds_slots[b] : empty;
+            const unsigned occ = __ballot_sync(FULL, e.w != KB_EMPTY);
+            const unsigned left = (occ << 1) | prev_occ;                     // bit l: bucket l-1 occupied
+            const unsigned nvalid = min(32u, cend - gb);                     // < 32 only for tables smaller than a warp
+            const unsigned next_occ_bit = (ds_slots[(gb + nvalid) & mask].w != KB_EMPTY) ? 1u : 0u;  // wraps at the table end
+            const unsigned right = (occ >> 1) | (next_occ_bit << (nvalid - 1));  // bit l: bucket l+1 occupied
+            const unsigned starts = occ & ~left;                             // run starts in this group
+            const unsigned single = starts & ~right;                         // runs of length 1
+            if ((single >> lane) & 1u) {
+                const long long o = before + __popc(occ & lt);
+                const long long src = e.w;
+                out[3 * o] = in[3 * src];
+                out[3 * o + 1] = in[3 * src + 1];
+                out[3 * o + 2] = in[3 * src + 2];
             }
-            // insert_value: robin-hood swap chain until an empty bucket
-            while (true) {
-                const int2 t = ds.sim[(s + r) & mask];
-                if (t.x < 0) break;
-                if ((r - ch) > (r - t.y)) {
-                    ds.sim[(s + r) & mask] = make_int2(ci, ch);
-                    ci = t.x;
-                    ch = t.y;
+            unsigned multi = starts & ~single;
+            while (multi) {
+                const int sb = __ffs(multi) - 1;
+                multi &= multi - 1;
+                const unsigned s = gb + sb;                                  // first bucket of the run
+                const int o_run = before + __popc(occ & ((1u << sb) - 1u));  // its rank among occupied buckets
+                // run length (may leave the group / chunk / wrap around the table end)
+                unsigned L = 0;
+                while (true) {
+                    const unsigned o2 = __ballot_sync(FULL, ds_slots[(s + L + lane) & mask].w != KB_EMPTY);
+                    if (o2 != FULL) {
+                        L += __ffs(~o2) - 1;
+                        break;
+                    }
+                    L += 32;
                 }
-                ++r;
+                if (L <= 32) {
+                    // lane k <-> entry found in bucket s+k; replay the inserts in first-index order
+                    const int4 f = (static_cast<unsigned>(lane) < L) ? ds_slots[(s + lane) & mask] : empty;
+                    const int idx = (static_cast<unsigned>(lane) < L) ? f.w : INT_MAX;
+                    const int home = static_cast<int>(((ref_hash(f.x, f.y, f.z) & mask) - s) & mask);
+                    int rank = 0;
+                    for (unsigned j = 0; j < L; ++j) rank += (__shfl_sync(FULL, idx, j) < idx) ? 1 : 0;
+                    int sim_idx = -1, sim_home = 0;  // lane r = bucket s+r of the replayed table
+                    for (unsigned t = 0; t < L; ++t) {
+                        const unsigned who = __ballot_sync(FULL, static_cast<unsigned>(lane) < L && rank == static_cast<int>(t));
+                        const int srcl = __ffs(who) - 1;
+                        int ci = __shfl_sync(FULL, idx, srcl), ch = __shfl_sync(FULL, home, srcl);
+                        int from = ch;  // insert_impl + insert_value: next bucket >= from that is empty or "richer"
+                        while (true) {
+                            const unsigned cand = __ballot_sync(FULL, lane >= from && (sim_idx < 0 || sim_home > ch));
+                            const int p = __ffs(cand) - 1;
+                            const int di = __shfl_sync(FULL, sim_idx, p), dh = __shfl_sync(FULL, sim_home, p);
+                            if (lane == p) {
+                                sim_idx = ci;
+                                sim_home = ch;
+                            }
+                            if (di < 0) break;  // landed in an empty bucket
+                            ci = di;            // displaced resident carries on
+                            ch = dh;
+                            from = p + 1;
+                        }
+                    }
+                    if (static_cast<unsigned>(lane) < L) {
+                        const unsigned bk = s + lane;
+                        const long long o = (bk >= B) ? static_cast<long long>(bk - B) : static_cast<long long>(o_run) + lane;
+                        const long long src = sim_idx;
+                        out[3 * o] = in[3 * src];
+                        out[3 * o + 1] = in[3 * src + 1];
+                        out[3 * o + 2] = in[3 * src + 2];
+                    }
+                } else {
+                    if (lane == 0) ds_replay_long_run(ds, s, L, mask);
+                    __syncwarp();
+                    for (unsigned r = lane; r < L; r += 32) {
+                        const unsigned bk = s + r;
+                        const long long o = (bk >= B) ? static_cast<long long>(bk - B) : static_cast<long long>(o_run) + r;
+                        const long long src = ds.sim[bk & mask].x;
+                        out[3 * o] = in[3 * src];
+                        out[3 * o + 1] = in[3 * src + 1];
+                        out[3 * o + 2] = in[3 * src + 2];
+                    }
+                }
             }
-            ds.sim[(s + r) & mask] = make_int2(ci, ch);
-        }
-        for (unsigned r = 0; r < L; ++r) {
-            const long long src = ds.sim[(s + r) & mask].x;
-            const long long o = ds.prefix[(s + r) & mask];
-            out[3 * o] = in[3 * src];
-            out[3 * o + 1] = in[3 * src + 1];
-            out[3 * o + 2] = in[3 * src + 2];
+            before += __popc(occ);
+            prev_occ = occ >> 31;
         }
     }
 }

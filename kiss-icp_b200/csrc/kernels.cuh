@@ -41,7 +41,8 @@ struct Workspace {
     double *tp;     // [n][3] points being inserted, map frame
     int *next;      // [n] pending-list links
     int *touched;   // [n] voxels touched by the current AddPoints
-    DsScratch ds;    // [pow2 >= 2n] downsample scratch tables
+    DsScratch ds;    // [pow2 >= 2n] downsample scratch tables (0.5 v pass)
+    DsScratch ds2;   // second set for the 1.5 v pass (both are cleared during preprocessing)
     int *cnt;        // [8] device-side counts (n_pre, n_ds, n_src, ...)
 };
 
@@ -92,6 +93,9 @@ __global__ void __launch_bounds__(BLOCK, 1) k_register_frame(const FrameParams P
     const double model_sse = P.st->model_sse;
     const int num_samples = P.st->num_samples;
 
+    // the downsample scratch tables of both passes are cleared here, under the preprocess barriers
+    ds_clear(P.ws.ds, P.n);
+    ds_clear(P.ws.ds2, P.n);
     // Preprocess (KissICP.cpp:38)
     op_preprocess(g, P.sc, sh, P.in, P.n, P.ts, P.n_ts, P.deskew != 0, last_delta, P.max_range, P.min_range,
                   P.ws.tmp, P.ws.pre, &P.ws.cnt[0]);
@@ -100,12 +104,12 @@ __global__ void __launch_bounds__(BLOCK, 1) k_register_frame(const FrameParams P
     const int n_pre = __ldcg(&P.ws.cnt[0]);
     // Voxelize (KissICP.cpp:70-75)
     op_downsample(g, P.sc, sh, P.ws.pre, n_pre, P.voxel_size * 0.5, P.ws.ds, P.ws.ds1,
-                  &P.ws.cnt[1], &P.res->t_ns[12]);
+                  &P.ws.cnt[1], &P.res->t_ns[12], true);
     g.sync();
     KB_STAMP(2);
     const int n_ds = __ldcg(&P.ws.cnt[1]);
-    op_downsample(g, P.sc, sh, P.ws.ds1, n_ds, P.voxel_size * 1.5, P.ws.ds, P.ws.src,
-                  &P.ws.cnt[2], &P.res->t_ns[16]);
+    op_downsample(g, P.sc, sh, P.ws.ds1, n_ds, P.voxel_size * 1.5, P.ws.ds2, P.ws.src,
+                  &P.ws.cnt[2], &P.res->t_ns[16], true);
     g.sync();
     KB_STAMP(3);
     const int n_src = __ldcg(&P.ws.cnt[2]);
