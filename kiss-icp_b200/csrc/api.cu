@@ -282,7 +282,12 @@ struct kb_map {
         }
         const size_t live = static_cast<size_t>(h_counters[C_LIVE]), tomb = static_cast<size_t>(h_counters[C_TOMB]);
         if (!force_want && capacity && (live + tomb + extra) * 2 <= capacity) return KB_OK;
-        const size_t want = force_want ? force_want : std::max<size_t>(pow2_at_least(4 * (live + extra)), size_t(1) << 14);
+        // grow/rebuild target: load factor <= 1/3 right after the rebuild (tombstones then accumulate up to 1/2)
+        static const size_t cap_factor = [] {
+            const char *e = std::getenv("KB_MAP_CAP_FACTOR");  // tuning aid: slots per expected voxel after a rebuild
+            return (e && std::atoi(e) >= 2) ? static_cast<size_t>(std::atoi(e)) : size_t(3);
+        }();
+        const size_t want = force_want ? force_want : std::max<size_t>(pow2_at_least(cap_factor * (live + extra)), size_t(1) << 14);
         if (want > (size_t(1) << 31)) return fail(KB_ERR_INVALID_ARG, "voxel table would exceed 2^31 slots");
         int4 *ns;
         double *np;
@@ -404,6 +409,7 @@ struct kb_pipeline {
     FrameResult *h_res = nullptr;  // pinned
     FrameResult last{};
     bool has_last = false;
+    unsigned long long grow_retries = 0;
     std::vector<kb_frame_stats> history;
     size_t history_cap = 0;
     ~kb_pipeline() {
@@ -954,9 +960,26 @@ int kb_pipeline_destroy(kb_pipeline *p) {
     return KB_OK;
 }
 
+static int pipeline_run_once(kb_pipeline *p, const double *d_xyz, size_t n, const double *d_ts, size_t n_ts, size_t extra);
+
 static int pipeline_run(kb_pipeline *p, const double *d_xyz, size_t n, const double *d_ts, size_t n_ts) {
+    // expected new voxels: at most one per downsampled point; the 0.5-voxel downsample keeps ~1/9 of a scan, so
+    // size for max(n/4, 2x the last frame's count) and let the kernel veto the frame if that was too optimistic
+    size_t extra = std::max<size_t>(n / 4, 2 * static_cast<size_t>(p->has_last ? p->last.n_ds : 0) + 1024);
+    extra = std::min(extra, n);
+    for (int attempt = 0; attempt < 3; ++attempt) {
+        RET(pipeline_run_once(p, d_xyz, n, d_ts, n_ts, extra));
+        if (!(p->last.map_status & ST_NEED_GROW)) return KB_OK;
+        ++p->grow_retries;
+        extra = std::max<size_t>(static_cast<size_t>(p->last.n_ds), extra) + 1;  // exact bound now known
+        p->map->h_counters[C_STATUS] = 0;
+    }
+    return fail(KB_ERR_CUDA, "voxel table could not be grown (internal capacity bug)");
+}
+
+static int pipeline_run_once(kb_pipeline *p, const double *d_xyz, size_t n, const double *d_ts, size_t n_ts, size_t extra) {
     Exec &ex = *p->ex;
-    RET(p->map->ensure_capacity(n));
+    RET(p->map->ensure_capacity(extra));
     FrameParams P;
     P.m = p->map->view();
     P.sc = ex.sc;
@@ -979,6 +1002,11 @@ static int pipeline_run(kb_pipeline *p, const double *d_xyz, size_t n, const dou
     RET(ex.coop(k_register_frame, P, QC_BYTES));
     CK(cudaMemcpyAsync(p->h_res, p->d_res, sizeof(FrameResult), cudaMemcpyDeviceToHost, ex.stream));
     RET(ex.sync());
+    if (p->h_res->map_status & ST_NEED_GROW) {  // vetoed: no state was modified; only remember why
+        p->last.map_status = p->h_res->map_status;
+        p->last.n_ds = p->h_res->n_ds;
+        return KB_OK;
+    }
     p->last = *p->h_res;
     p->has_last = true;
     p->map->h_counters[C_LIVE] = p->last.map_live;

@@ -39,7 +39,7 @@ constexpr int ICP_REC = 32;
 constexpr int LL_RES = 16;        // est(7) + done flag, final pose(7), spare      // est(7) t_icp(7) final(7) conv cand_total query_total ...
 
 enum Counter { C_LIVE = 0, C_TOMB = 1, C_POINTS = 2, C_STATUS = 3, C_TOUCHED = 4, C_NCOUNTERS = 8 };
-enum StatusBit { ST_TABLE_FULL = 1 };
+enum StatusBit { ST_TABLE_FULL = 1, ST_NEED_GROW = 2 };
 
 // core/VoxelUtils.hpp:33-37 — FP64 DIVISION then floor then int cast (bit-exact with the CPU).
 // A DDIV costs ~131 cycles on B200; when voxel_size is an exact power of two (1.0, 0.5, 2.0 ...:

@@ -108,6 +108,19 @@ __global__ void __launch_bounds__(BLOCK, 1) k_register_frame(const FrameParams P
     g.sync();
     KB_STAMP(2);
     const int n_ds = __ldcg(&P.ws.cnt[1]);
+    // optimistic table capacity: the host sized the voxel table for the EXPECTED number of new voxels. If this
+    // frame could push the load factor beyond 0.5, nothing has been modified yet: report and let the host grow
+    // the table and replay the frame (rare; first frames of a sequence).
+    {
+        const long long need = static_cast<long long>(__ldcg(&P.m.counters[C_LIVE])) + __ldcg(&P.m.counters[C_TOMB]) + n_ds;
+        if (need * 2 > static_cast<long long>(P.m.mask) + 1) {
+            if (blockIdx.x == 0 && threadIdx.x == 0) {
+                P.res->map_status = ST_NEED_GROW;
+                P.res->n_ds = n_ds;
+            }
+            return;  // uniform across the grid
+        }
+    }
     op_downsample(g, P.sc, sh, P.ws.ds1, n_ds, P.voxel_size * 1.5, P.ws.ds2, P.ws.src,
                   &P.ws.cnt[2], &P.res->t_ns[16], true);
     g.sync();
