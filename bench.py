@@ -71,9 +71,19 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
+    def wait_ready(self, timeout=20.0):
+        """nvidia-smi's NVML start-up stalls the GPU for hundreds of ms: never let it land in a timed region"""
+        t0 = time.perf_counter()
+        while self.proc and not self.rows and time.perf_counter() - t0 < timeout:
+            time.sleep(0.05)
+
+    def mark(self):
+        self.first = len(self.rows)
+
     def stop(self):
         if self.proc:
             self.proc.terminate()
+        self.rows = self.rows[getattr(self, "first", 0):]
         sm = [float(r[1]) for r in self.rows if len(r) > 8 and r[1].replace(".", "").isdigit()]
         mx = [float(r[2]) for r in self.rows if len(r) > 8 and r[2].replace(".", "").isdigit()]
         reasons = set()
@@ -184,6 +194,10 @@ def main():
     torch.cuda.set_stream(stream)
     N.check(N.lib().kb_set_stream(C.c_void_p(stream.cuda_stream)))
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()  # started long before the timed regions; samples before mark() are dropped
+
     seq = sharding.sequences_of_rank(rank, world, world)[0]
     lidar = synthetic.kitti_shape(seed=seq, device=dev)
     n_total = args.prime + args.warmup + args.steps
@@ -211,9 +225,9 @@ def main():
     icp = make_pipeline()
     for t in scans_dev[:args.prime + args.warmup]:
         reg_dev(icp, t)
-    sampler = ClockSampler(local)
     if rank == 0:
-        sampler.start()
+        sampler.wait_ready()
+        sampler.mark()
     timed = scans_dev[args.prime + args.warmup:]
     l0 = launches(icp)
     prof = np.zeros((len(timed), 6))

@@ -89,7 +89,7 @@ struct Exec {
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     int grid = 0;
-    Scratch sc{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    Scratch sc{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     unsigned tag_seq = 0;  // launch sequence number of the tagged ICP protocol
     unsigned long long launches = 0;
     unsigned next_tag_base() { return (++tag_seq) << 13; }  // 8192 epochs per launch
@@ -109,12 +109,15 @@ struct Exec {
         CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device));
         if (!coop) return fail(KB_ERR_CUDA, "device does not support cooperative launch");
         grid = tl_grid_blocks > 0 ? std::min(tl_grid_blocks, sms) : sms;
+        grid = std::min(grid, 256);  // the two-level gather tree of the ICP loop handles up to 16 x 16 CTAs
         CK(cudaMalloc(&sc.bar, BAR_WORDS * sizeof(unsigned)));
         CK(cudaMalloc(&sc.blk_d, sizeof(double) * 2 * grid * NPART));
         CK(cudaMalloc(&sc.blk_i, sizeof(int) * 2 * grid));
         CK(cudaMalloc(&sc.icp_rec, sizeof(double) * 2 * ICP_REC));
         CK(cudaMalloc(&sc.ll_part, sizeof(uint4) * NPART * grid));
         CK(cudaMalloc(&sc.ll_res, sizeof(uint4) * LL_RES));
+        CK(cudaMalloc(&sc.ll_group, sizeof(uint4) * NPART * 16));
+        CK(cudaMemsetAsync(sc.ll_group, 0, sizeof(uint4) * NPART * 16, stream));
         CK(cudaMemsetAsync(sc.ll_part, 0, sizeof(uint4) * NPART * grid, stream));
         CK(cudaMemsetAsync(sc.ll_res, 0, sizeof(uint4) * LL_RES, stream));
         CK(cudaMalloc(&sc.dbg, sizeof(unsigned long long) * (64 + 4 * grid)));
@@ -128,6 +131,7 @@ struct Exec {
         if (sc.icp_rec) cudaFree(sc.icp_rec);
         if (sc.ll_part) cudaFree(sc.ll_part);
         if (sc.ll_res) cudaFree(sc.ll_res);
+        if (sc.ll_group) cudaFree(sc.ll_group);
         if (sc.dbg) cudaFree(sc.dbg);
         if (own_stream && stream) cudaStreamDestroy(stream);
     }

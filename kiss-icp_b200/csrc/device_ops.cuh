@@ -83,6 +83,7 @@ struct Scratch {
     double *icp_rec;  // (unused by the tagged protocol; kept for the debug tools)
     uint4 *ll_part;   // [NPART][grid] epoch-tagged partial systems, one 16-B chunk per value and CTA
     uint4 *ll_res;    // [LL_RES] epoch-tagged result record published by the coordinator
+    uint4 *ll_group;  // [NPART][16] epoch-tagged group partials (second level of the gather tree)
     int *blk_i;     // [grid] ints
     unsigned long long *dbg;  // [64] %globaltimer stamps of CTA 0 (profiling aid)
 };
@@ -1080,64 +1081,51 @@ __device__ __noinline__ void icp_queries(const Scratch &sc, Shared &sh, const Ma
     if (dbg_on && threadIdx.x == 0) sc.dbg[64 + 4 * blockIdx.x + 2] = static_cast<unsigned long long>(sh.warp_d[0][NACC + 3] + sh.warp_d[1][NACC + 3] + sh.warp_d[2][NACC + 3] + sh.warp_d[3][NACC + 3] + sh.warp_d[4][NACC + 3] + sh.warp_d[5][NACC + 3] + sh.warp_d[6][NACC + 3] + sh.warp_d[7][NACC + 3] + sh.warp_d[8][NACC + 3] + sh.warp_d[9][NACC + 3] + sh.warp_d[10][NACC + 3] + sh.warp_d[11][NACC + 3] + sh.warp_d[12][NACC + 3] + sh.warp_d[13][NACC + 3] + sh.warp_d[14][NACC + 3] + sh.warp_d[15][NACC + 3]);
 }
 
-// The coordinator (CTA 0) gathers the tagged partials of all CTAs — polling IS the rendezvous —
-// and sums them in a fixed order -> sh.red[NPART]. Warp w owns values w and w + 16; lane l owns
-// CTAs l, l + 32, ...; all loads of a round are issued before any is examined.
+// Two-level gather of the tagged partials (polling IS the rendezvous). The grid is cut into
+// groups of GS = ceil(sqrt(G)) consecutive CTAs; the first CTA of a group (its leader) polls the
+// <= 16 partials of its members — one 16-byte chunk per thread, so a gather is ONE load round —
+// reduces them with a 16-lane shuffle tree (fixed order) and re-posts the group partial; CTA 0
+// then gathers the <= 16 group partials the same way. Two short hops (~0.4 us each) instead of
+// one CTA reading 148 x 21 chunks (~2 us).
+__device__ __forceinline__ int icp_group_size() {
+    int gs = 1;
+    while (gs * gs < static_cast<int>(gridDim.x)) ++gs;
+    return gs;
+}
+
+// thread t = (value e = t / 16, member m = t % 16); returns the sum over `count` chunks in lanes with m == 0
+__device__ __forceinline__ double ll_gather16(const uint4 *base, int stride, int first, int count, unsigned tag) {
+    const int e = threadIdx.x >> 4, m = threadIdx.x & 15;
+    const bool active = e < NPART && m < count;
+    double v = 0.0;
+    bool ok = !active;
+    while (!__all_sync(FULL, ok)) {
+        if (!ok) ok = ll_load(&base[static_cast<size_t>(e) * stride + first + m], tag, &v);
+    }
+    if (!active) v = 0.0;
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    return v;
+}
+
 __device__ __forceinline__ void icp_gather(const Scratch &sc, Shared &sh, unsigned tag) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    constexpr int RMAX = 8;
-    const int nb = static_cast<int>(gridDim.x);
-    const int e0 = warp, e1 = warp + NWARPS;
-    const bool two = e1 < NPART;
-    double s0 = 0.0, s1 = 0.0;
-    for (int base = 0; base < nb; base += 32 * RMAX) {
-        double v0[RMAX], v1[RMAX];
-        unsigned pend = 0;  // bit r: value e0 of CTA base+32r+lane still missing; bit 16+r: same for e1
-#pragma unroll
-        for (int r = 0; r < RMAX; ++r) {
-            v0[r] = 0.0;
-            v1[r] = 0.0;
-            if (base + r * 32 + lane < nb) pend |= (1u << r) | (two ? (1u << (16 + r)) : 0u);
-        }
-        int rounds = 0;
-        while (__any_sync(FULL, pend != 0)) {
-            ++rounds;
-            // issue every outstanding load of this round first (they are independent), examine afterwards
-            const unsigned snap = pend;
-            double t0[RMAX], t1[RMAX];
-            unsigned got = 0;
-#pragma unroll
-            for (int r = 0; r < RMAX; ++r) {
-                const int b = base + r * 32 + lane;
-                if (snap & (1u << r))
-                    got |= ll_load(&sc.ll_part[static_cast<size_t>(e0) * nb + b], tag, &t0[r]) ? (1u << r) : 0u;
-                if (snap & (1u << (16 + r)))
-                    got |= ll_load(&sc.ll_part[static_cast<size_t>(e1) * nb + b], tag, &t1[r]) ? (1u << (16 + r)) : 0u;
-            }
-#pragma unroll
-            for (int r = 0; r < RMAX; ++r) {
-                if (got & (1u << r)) v0[r] = t0[r];
-                if (got & (1u << (16 + r))) v1[r] = t1[r];
-            }
-            pend &= ~got;
-        }
-        if (threadIdx.x == 0 && base == 0) sc.dbg[40] = sc.dbg[0] + static_cast<unsigned long long>(rounds);
-#pragma unroll
-        for (int r = 0; r < RMAX; ++r) {
-            s0 += v0[r];
-            s1 += v1[r];
-        }
+    const int G = static_cast<int>(gridDim.x);
+    const int gs = icp_group_size();
+    const int ngroups = (G + gs - 1) / gs;
+    const int cta = static_cast<int>(blockIdx.x);
+    const bool in_tree = threadIdx.x < ((NPART * 16 + 31) / 32) * 32;  // whole warps
+    if (cta % gs == 0 && in_tree) {  // group leader
+        const int gid = cta / gs, first = gid * gs;
+        const double v = ll_gather16(sc.ll_part, G, first, min(gs, G - first), tag);
+        if ((threadIdx.x & 15) == 0 && (threadIdx.x >> 4) < NPART) ll_store(&sc.ll_group[(threadIdx.x >> 4) * 16 + gid], v, tag);
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        s0 += __shfl_xor_sync(FULL, s0, o);
-        s1 += __shfl_xor_sync(FULL, s1, o);
+    if (cta == 0) {  // coordinator
+        if (in_tree) {
+            const double v = ll_gather16(sc.ll_group, 16, 0, ngroups, tag);
+            if ((threadIdx.x & 15) == 0 && (threadIdx.x >> 4) < NPART) sh.red[threadIdx.x >> 4] = v;
+        }
+        __syncthreads();
     }
-    if (lane == 0) {
-        sh.red[e0] = s0;
-        if (two) sh.red[e1] = s1;
-    }
-    __syncthreads();
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1176,9 +1164,9 @@ __device__ __noinline__ void op_icp(Grid &g, const Scratch &sc, Shared &sh, cons
         const bool dbg_on = (j == 4);
         const unsigned tag = tag_base + static_cast<unsigned>(j) + 1u;
         icp_queries(sc, sh, m, j == 0 ? src : work, work, n, pending, max_dist, kscale, tag, dbg_on, qcache, j == 0);
+        if (dbg_on) { KB_CYC(sc, 4); }
+        icp_gather(sc, sh, tag);  // group leaders and the coordinator work, everybody else falls through
         if (blockIdx.x == 0) {
-            if (dbg_on) { KB_CYC(sc, 4); }
-            icp_gather(sc, sh, tag);
             if (threadIdx.x == 0) {
                 if (dbg_on) { KB_CYC(sc, 5); }
                 double sys[NACC];

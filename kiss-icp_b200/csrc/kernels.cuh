@@ -244,8 +244,8 @@ __global__ void __launch_bounds__(BLOCK, 1) k_icp(const IcpParams P) {
     g.init(P.sc.bar);
     if (P.system_only) {
         icp_queries(P.sc, sh, P.m, P.src, P.work, P.n, se3_identity(), P.max_dist, P.kscale, P.tag_base + 1u, false);
+        icp_gather(P.sc, sh, P.tag_base + 1u);
         if (blockIdx.x == 0) {
-            icp_gather(P.sc, sh, P.tag_base + 1u);
             if (threadIdx.x == 0) {
                 for (int i = 0; i < NACC; ++i) P.out_sys[i] = sh.red[i];
                 *P.out_ncorr = static_cast<int>(sh.red[NACC]);
