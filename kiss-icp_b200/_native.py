@@ -16,7 +16,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(_HERE)
-LIB_PATH = os.path.join(_HERE, "libkiss_icp_b200.so")
+LIB_PATH = os.environ.get("KB_LIB") or os.path.join(_HERE, "libkiss_icp_b200.so")  # KB_LIB: A/B builds side by side
 CSRC = os.path.join(_HERE, "csrc")
 HEADER = os.path.join(ROOT, "include", "kiss_icp_b200.h")
 

@@ -372,3 +372,36 @@ def test_map_compact_keeps_content(K, O):
     ap, ad = g.closest_neighbors(q)
     bp, bd = o.closest_neighbors(q)
     assert np.array_equal(ap, bp) and np.array_equal(ad, bd)
+
+
+def test_pipeline_long_stream_with_table_rebuilds(K, O):
+    """300 free-running scans: eviction tombstones accumulate and the voxel table is rebuilt several times"""
+    from kiss_icp_b200 import synthetic
+    L = synthetic.small_shape(seed=21, beams=32, cols=512)
+    g, o = K.KissICP(K.load_config(max_range=40.0)), O.KissICP(max_range=40.0, voxel_size=0.4)
+    worst = 0.0
+    for k in range(300):
+        p, t = L.scan(k)
+        g.register_frame(p, t, return_clouds=False)
+        o.register_frame(p, t, want_clouds=False)
+        dt, dr = pose_error(g.last_pose, o.pose)
+        worst = max(worst, dt, dr)
+        assert dt < 1e-4 and dr < 1e-4, (k, dt, dr)
+    assert worst < 1e-6
+    assert g.local_map.num_points() == o.local_map.num_points() and g.local_map.num_voxels() == o.local_map.num_voxels()
+    gv, gc, gp = g.local_map.dump()
+    ov, oc, op = canon_map(*o.local_map.dump())
+    assert np.array_equal(gv, ov) and np.array_equal(gc, oc) and np.allclose(gp, op, atol=1e-9)
+
+
+def test_pipeline_capacity_veto_and_retry(K, O):
+    """frames whose downsampled size exceeds the optimistic table sizing (every point its own voxel): the kernel
+    vetoes the frame before touching any state, the host grows the table and replays it"""
+    g, o = K.KissICP(K.load_config(max_range=300.0, voxel_size=1.0)), O.KissICP(max_range=300.0, voxel_size=1.0)
+    for k in range(4):
+        pts = rng.uniform(-150, 150, size=(30000, 3)) * [1.0, 1.0, 0.2]
+        g.register_frame(pts, np.empty(0), return_clouds=False)
+        o.register_frame(pts, np.empty(0), want_clouds=False)
+        dt, dr = pose_error(g.last_pose, o.pose)
+        assert dt < 1e-6 and dr < 1e-6
+        assert g.local_map.num_points() == o.local_map.num_points()
