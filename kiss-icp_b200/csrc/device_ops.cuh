@@ -816,6 +816,84 @@ __device__ __forceinline__ NNResult nn_search_cached_fast(const QCache &qc, cons
     return NNResult{sqrt(b2), bp, qc.full};
 }
 
+// 24-byte point record -> one 16-byte + one 8-byte load (records are 8-byte aligned, every other one 16-byte)
+__device__ __forceinline__ V3 ld_point24(const double *rec) {
+    const char *pp = reinterpret_cast<const char *>(rec);
+    const bool even = ((reinterpret_cast<size_t>(pp) & 15) == 0);
+    const double2 wide = *reinterpret_cast<const double2 *>(pp + (even ? 0 : 8));
+    const double lone = *reinterpret_cast<const double *>(pp + (even ? 16 : 0));
+    return even ? V3{wide.x, wide.y, lone} : V3{lone, wide.x, wide.y};
+}
+
+// FLAT GATHER over the probed neighbourhood (per-lane cnt/slot of lanes 0..26): candidate j (reference order:
+// voxel_shifts order, then insertion order) goes to lane j % 32, so all loads of a round are independent — one
+// L2 round trip instead of one per occupied voxel. The minimum is taken on SQUARED distances (one sqrt per
+// query); if another candidate's square lies within a few ulps above the minimum (two squares that could round
+// to the same root) the search is redone comparing rounded roots exactly like the reference.
+__device__ __forceinline__ NNResult nn_flat_search(const MapView &m, const V3 &q, int lane, WarpNN &w, int cnt, int slot) {
+    const int cap = m.cap;
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(FULL, incl, o);
+        if (lane >= o) incl += t;
+    }
+    const int start = incl - cnt;
+    const int total = __shfl_sync(FULL, incl, 31);
+    __syncwarp();
+    if (lane < 27) {
+        w.slot[lane] = slot;
+        w.start[lane] = start;
+        for (int k = 0; k < cnt; ++k) w.owner[start + k] = static_cast<unsigned char>(lane);
+    }
+    __syncwarp();
+    double b2 = DBL_MAX, s2 = DBL_MAX;
+    int bseq = INT_MAX;
+    V3 bp{0, 0, 0};
+    constexpr int U = 2;
+    for (int base = 0; base < total; base += 32 * U) {
+        V3 c[U];
+        bool ok[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int j = base + u * 32 + lane;
+            ok[u] = j < total;
+            if (ok[u]) {
+                const int vi = w.owner[j];
+                c[u] = ld_point24(m.points + (static_cast<size_t>(w.slot[vi]) * cap + (j - w.start[vi])) * 3);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (ok[u]) {
+                const double d2 = sqnorm(c[u] - q);
+                if (d2 < b2) {
+                    s2 = b2;
+                    b2 = d2;
+                    bseq = base + u * 32 + lane;
+                    bp = c[u];
+                } else if (d2 > b2 && d2 < s2) {
+                    s2 = d2;
+                }
+            }
+    }
+    const double mine = b2;
+    nn_reduce(b2, bseq, bp);
+    const double lim = b2 * (1.0 + 8.8817841970012523e-16);
+    const bool near = (mine > b2 && mine <= lim) || (s2 <= lim);
+    if (!__any_sync(FULL, near)) return NNResult{total > 0 ? sqrt(b2) : DBL_MAX, bp, total};
+    double best = DBL_MAX, best_d2 = DBL_MAX;
+    bseq = INT_MAX;
+    bp = V3{0, 0, 0};
+    for (int j = lane; j < total; j += 32) {
+        const int vi = w.owner[j];
+        const double *pp = m.points + (static_cast<size_t>(w.slot[vi]) * cap + (j - w.start[vi])) * 3;
+        nn_consider(V3{pp[0], pp[1], pp[2]}, q, j, best, best_d2, bseq, bp);
+    }
+    nn_reduce(best, bseq, bp);
+    return NNResult{best, bp, total};
+}
+
 __device__ __forceinline__ NNResult nn_search_warp(const MapView &m, const V3 &q, int lane, WarpNN &w,
                                                    QCache *fill = nullptr, double cache_radius = 0.0) {
     const int3 v = point_to_voxel(q.x, q.y, q.z, m.vdiv);
@@ -824,52 +902,14 @@ __device__ __forceinline__ NNResult nn_search_warp(const MapView &m, const V3 &q
         slot = map_find(m, v.x + c_shifts[lane][0], v.y + c_shifts[lane][1], v.z + c_shifts[lane][2], &cnt);
         if (slot < 0) cnt = 0;
     }
-    double best = DBL_MAX, best_d2 = DBL_MAX;
-    int bseq = INT_MAX;
-    V3 bp{0, 0, 0};
     const int cap = m.cap;
-    int total;
-    if (cap <= NN_FLAT_CAP) {
-        // FLAT GATHER: candidate j (in reference order: voxel_shifts order, then insertion order)
-        // goes to lane j % 32; all loads of a round are independent -> one L2 round trip instead
-        // of one per occupied voxel.
-        int incl = cnt;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int t = __shfl_up_sync(FULL, incl, o);
-            if (lane >= o) incl += t;
-        }
-        const int start = incl - cnt;
-        total = __shfl_sync(FULL, incl, 31);
-        __syncwarp();
-        if (lane < 27) {
-            w.slot[lane] = slot;
-            w.start[lane] = start;
-            for (int k = 0; k < cnt; ++k) w.owner[start + k] = static_cast<unsigned char>(lane);
-        }
-        __syncwarp();
-        constexpr int U = 4;
-        for (int base = 0; base < total; base += 32 * U) {
-            V3 c[U];
-            bool ok[U];
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int j = base + u * 32 + lane;
-                ok[u] = j < total;
-                if (ok[u]) {
-                    const int vi = w.owner[j];
-                    const double *pp = m.points + (static_cast<size_t>(w.slot[vi]) * cap + (j - w.start[vi])) * 3;
-                    c[u] = V3{pp[0], pp[1], pp[2]};
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < U; ++u)
-                if (ok[u]) nn_consider(c[u], q, base + u * 32 + lane, best, best_d2, bseq, bp);
-        }
-    } else {
-        // general path: walk the occupied voxels one after the other
+    if (cap > NN_FLAT_CAP) {
+        // general path (max_points_per_voxel > 32): walk the occupied voxels one after the other
+        double best = DBL_MAX, best_d2 = DBL_MAX;
+        int bseq = INT_MAX;
+        V3 bp{0, 0, 0};
         unsigned occ = __ballot_sync(FULL, cnt > 0);
-        total = 0;
+        int total = 0;
         while (occ) {
             const int vi = __ffs(occ) - 1;
             occ &= occ - 1;
@@ -881,9 +921,12 @@ __device__ __forceinline__ NNResult nn_search_warp(const MapView &m, const V3 &q
                 nn_consider(V3{blk[3 * k], blk[3 * k + 1], blk[3 * k + 2]}, q, vi * 1024 + k, best, best_d2, bseq, bp);
         }
         if (fill != nullptr && lane == 0) fill->total = -1;
-        fill = nullptr;
+        nn_reduce(best, bseq, bp);
+        return NNResult{best, bp, total};
     }
-    nn_reduce(best, bseq, bp);
+    const NNResult r = nn_flat_search(m, q, lane, w, cnt, slot);
+    const double best = r.d;
+    const int total = r.candidates;
     if (fill != nullptr) {
         // second pass (L1-hot): keep the candidates within d* + 2R of the query, in reference order
         int count = -1;
@@ -900,8 +943,7 @@ __device__ __forceinline__ NNResult nn_search_warp(const MapView &m, const V3 &q
                     V3 c{0, 0, 0};
                     if (j < total) {
                         const int vi = w.owner[j];
-                        const double *pp = m.points + (static_cast<size_t>(w.slot[vi]) * cap + (j - w.start[vi])) * 3;
-                        c = V3{pp[0], pp[1], pp[2]};
+                        c = ld_point24(m.points + (static_cast<size_t>(w.slot[vi]) * cap + (j - w.start[vi])) * 3);
                         keep = sqnorm(c - q) <= thr2;
                     }
                     const unsigned mask = __ballot_sync(FULL, keep);
@@ -930,7 +972,7 @@ __device__ __forceinline__ NNResult nn_search_warp(const MapView &m, const V3 &q
         }
         __syncwarp();
     }
-    return NNResult{best, bp, total};
+    return r;
 }
 
 // ------------------------------------------------------------------------------------------

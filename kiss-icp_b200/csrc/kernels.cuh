@@ -367,83 +367,13 @@ __device__ __forceinline__ NNResult nn_finish(const MapView &m, const NNProbe &p
     }
     const V3 q = pr.q;
     const int cap = m.cap;
-    int total;
-    if (cap <= NN_FLAT_CAP) {
-        int incl = cnt;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int t = __shfl_up_sync(FULL, incl, o);
-            if (lane >= o) incl += t;
-        }
-        const int start = incl - cnt;
-        total = __shfl_sync(FULL, incl, 31);
-        __syncwarp();
-        if (lane < 27) {
-            w.slot[lane] = slot;
-            w.start[lane] = start;
-            for (int k = 0; k < cnt; ++k) w.owner[start + k] = static_cast<unsigned char>(lane);
-        }
-        __syncwarp();
-        // pass 1: minimum of the SQUARED distances (one sqrt per query at the end). Each 24-byte point is
-        // fetched with one 16-byte and one 8-byte load (records are 8-byte aligned, every other one 16-byte).
-        double b2 = DBL_MAX, s2 = DBL_MAX;
-        int bseq = INT_MAX;
-        V3 bp{0, 0, 0};
-        constexpr int U = 2;
-        for (int base = 0; base < total; base += 32 * U) {
-            V3 c[U];
-            bool ok[U];
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int j = base + u * 32 + lane;
-                ok[u] = j < total;
-                if (ok[u]) {
-                    const int vi = w.owner[j];
-                    const int k = j - w.start[vi];
-                    const char *pp = reinterpret_cast<const char *>(m.points + (static_cast<size_t>(w.slot[vi]) * cap + k) * 3);
-                    const bool even = ((reinterpret_cast<size_t>(pp) & 15) == 0);
-                    const double2 wide = *reinterpret_cast<const double2 *>(pp + (even ? 0 : 8));
-                    const double lone = *reinterpret_cast<const double *>(pp + (even ? 16 : 0));
-                    c[u] = even ? V3{wide.x, wide.y, lone} : V3{lone, wide.x, wide.y};
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < U; ++u)
-                if (ok[u]) {
-                    const double d2 = sqnorm(c[u] - q);
-                    if (d2 < b2) {
-                        s2 = b2;
-                        b2 = d2;
-                        bseq = base + u * 32 + lane;
-                        bp = c[u];
-                    } else if (d2 > b2 && d2 < s2) {
-                        s2 = d2;
-                    }
-                }
-        }
-        const double mine = b2;
-        nn_reduce(b2, bseq, bp);
-        const double lim = b2 * (1.0 + 8.8817841970012523e-16);
-        const bool near = (mine > b2 && mine <= lim) || (s2 <= lim);
-        if (!__any_sync(FULL, near)) return NNResult{total > 0 ? sqrt(b2) : DBL_MAX, bp, total};
-        // near-tie of squared distances (two squares that may round to the same root): redo it the reference's way
-        double best = DBL_MAX, best_d2 = DBL_MAX;
-        bseq = INT_MAX;
-        bp = V3{0, 0, 0};
-        for (int j = lane; j < total; j += 32) {
-            const int vi = w.owner[j];
-            const double *pp = m.points + (static_cast<size_t>(w.slot[vi]) * cap + (j - w.start[vi])) * 3;
-            nn_consider(V3{pp[0], pp[1], pp[2]}, q, j, best, best_d2, bseq, bp);
-        }
-        nn_reduce(best, bseq, bp);
-        return NNResult{best, bp, total};
-    }
+    if (cap <= NN_FLAT_CAP) return nn_flat_search(m, q, lane, w, cnt, slot);
     double best = DBL_MAX, best_d2 = DBL_MAX;
     int bseq = INT_MAX;
     V3 bp{0, 0, 0};
+    int total = 0;
     {
         unsigned occ = __ballot_sync(FULL, cnt > 0);
-        total = 0;
         while (occ) {
             const int vi = __ffs(occ) - 1;
             occ &= occ - 1;
