@@ -173,6 +173,11 @@ int kb_pipeline_destroy(kb_pipeline *p);
  * ros/src/OdometryServer.cpp:168-172). */
 int kb_pipeline_register_frame(kb_pipeline *p, const double *xyz, size_t n, const double *timestamps,
                                size_t n_timestamps);
+/* same with a float32 frame float[n][3] (KITTI .bin / PointCloud2 payloads are float32 and the reference widens
+ * them on the host: python/kiss_icp/datasets/kitti.py:66, ros/src/Utils.hpp:198-208). Half the H2D bytes; the
+ * exact float->double widening happens on the device, so results equal the f64 call on the widened array. */
+int kb_pipeline_register_frame_f32(kb_pipeline *p, const float *xyz, size_t n, const double *timestamps,
+                                   size_t n_timestamps);
 /* same, frame (and stamps) already resident in HBM on the pipeline's device */
 int kb_pipeline_register_frame_dev(kb_pipeline *p, const double *d_xyz, size_t n, const double *d_timestamps,
                                    size_t n_timestamps);

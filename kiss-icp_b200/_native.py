@@ -123,6 +123,7 @@ SIGNATURES = {
     "kb_pipeline_create": (i32, [C.POINTER(Config), C.POINTER(vp)]),
     "kb_pipeline_destroy": (i32, [vp]),
     "kb_pipeline_register_frame": (i32, [vp, vp, sz, vp, sz]),
+    "kb_pipeline_register_frame_f32": (i32, [vp, vp, sz, vp, sz]),
     "kb_pipeline_register_frame_dev": (i32, [vp, vp, sz, vp, sz]),
     "kb_pipeline_last_cloud_sizes": (i32, [vp, C.POINTER(sz), C.POINTER(sz)]),
     "kb_pipeline_last_clouds": (i32, [vp, vp, sz, vp, sz]),

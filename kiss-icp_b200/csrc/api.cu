@@ -964,15 +964,16 @@ int kb_pipeline_destroy(kb_pipeline *p) {
     return KB_OK;
 }
 
-static int pipeline_run_once(kb_pipeline *p, const double *d_xyz, size_t n, const double *d_ts, size_t n_ts, size_t extra);
+static int pipeline_run_once(kb_pipeline *p, const double *d_xyz, size_t n, const double *d_ts, size_t n_ts, size_t extra,
+                             bool in_f32);
 
-static int pipeline_run(kb_pipeline *p, const double *d_xyz, size_t n, const double *d_ts, size_t n_ts) {
+static int pipeline_run(kb_pipeline *p, const double *d_xyz, size_t n, const double *d_ts, size_t n_ts, bool in_f32 = false) {
     // expected new voxels: at most one per downsampled point; the 0.5-voxel downsample keeps ~1/9 of a scan, so
     // size for max(n/4, 2x the last frame's count) and let the kernel veto the frame if that was too optimistic
     size_t extra = std::max<size_t>(n / 4, 2 * static_cast<size_t>(p->has_last ? p->last.n_ds : 0) + 1024);
     extra = std::min(extra, n);
     for (int attempt = 0; attempt < 3; ++attempt) {
-        RET(pipeline_run_once(p, d_xyz, n, d_ts, n_ts, extra));
+        RET(pipeline_run_once(p, d_xyz, n, d_ts, n_ts, extra, in_f32));
         if (!(p->last.map_status & ST_NEED_GROW)) return KB_OK;
         ++p->grow_retries;
         extra = std::max<size_t>(static_cast<size_t>(p->last.n_ds), extra) + 1;  // exact bound now known
@@ -981,7 +982,8 @@ static int pipeline_run(kb_pipeline *p, const double *d_xyz, size_t n, const dou
     return fail(KB_ERR_CUDA, "voxel table could not be grown (internal capacity bug)");
 }
 
-static int pipeline_run_once(kb_pipeline *p, const double *d_xyz, size_t n, const double *d_ts, size_t n_ts, size_t extra) {
+static int pipeline_run_once(kb_pipeline *p, const double *d_xyz, size_t n, const double *d_ts, size_t n_ts, size_t extra,
+                             bool in_f32) {
     Exec &ex = *p->ex;
     RET(p->map->ensure_capacity(extra));
     FrameParams P;
@@ -1003,6 +1005,7 @@ static int pipeline_run_once(kb_pipeline *p, const double *d_xyz, size_t n, cons
     P.min_motion_th = p->cfg.min_motion_th;
     P.use_qcache = 1;
     P.tag_base = ex.next_tag_base();
+    P.in_f32 = in_f32 ? 1 : 0;
     RET(ex.coop(k_register_frame, P, QC_BYTES));
     CK(cudaMemcpyAsync(p->h_res, p->d_res, sizeof(FrameResult), cudaMemcpyDeviceToHost, ex.stream));
     RET(ex.sync());
@@ -1057,6 +1060,16 @@ int kb_pipeline_register_frame(kb_pipeline *p, const double *xyz, size_t n, cons
     if (n) CK(cudaMemcpyAsync(p->ws.in.p, xyz, n * 24, cudaMemcpyHostToDevice, ex.stream));
     if (use_ts) CK(cudaMemcpyAsync(p->ws.ts.p, timestamps, n_timestamps * 8, cudaMemcpyHostToDevice, ex.stream));
     return pipeline_run(p, p->ws.in.p, n, p->ws.ts.p, use_ts ? n_timestamps : 0);
+}
+int kb_pipeline_register_frame_f32(kb_pipeline *p, const float *xyz, size_t n, const double *timestamps, size_t n_timestamps) {
+    bool use_ts;
+    RET(pipeline_check(p, xyz, n, timestamps, n_timestamps, &use_ts));
+    Exec &ex = *p->ex;
+    CK(cudaSetDevice(ex.device));
+    RET(p->ws.ensure(std::max(n, use_ts ? n_timestamps : 0)));
+    if (n) CK(cudaMemcpyAsync(p->ws.in.p, xyz, n * 12, cudaMemcpyHostToDevice, ex.stream));  // half the bytes of the f64 path
+    if (use_ts) CK(cudaMemcpyAsync(p->ws.ts.p, timestamps, n_timestamps * 8, cudaMemcpyHostToDevice, ex.stream));
+    return pipeline_run(p, p->ws.in.p, n, p->ws.ts.p, use_ts ? n_timestamps : 0, true);
 }
 int kb_pipeline_register_frame_dev(kb_pipeline *p, const double *d_xyz, size_t n, const double *d_timestamps,
                                    size_t n_timestamps) {

@@ -364,9 +364,20 @@ struct Shared {
     int is_last;
 };
 
+// `in` is double[n][3], or float[n][3] when in_f32 (KITTI .bin / PointCloud2 payloads are float32; the reference
+// widens them on the host — python/kiss_icp/datasets/kitti.py:66, ros/src/Utils.hpp:198-208 — here the H2D copy
+// is half the size and the exact float->double widening happens on the device)
+__device__ __forceinline__ V3 pre_load(const double *in, long long i, bool in_f32) {
+    if (in_f32) {
+        const float *f = reinterpret_cast<const float *>(in);
+        return V3{static_cast<double>(f[3 * i]), static_cast<double>(f[3 * i + 1]), static_cast<double>(f[3 * i + 2])};
+    }
+    return V3{in[3 * i], in[3 * i + 1], in[3 * i + 2]};
+}
+
 __device__ __noinline__ void op_preprocess(Grid &g, const Scratch &sc, Shared &sh, const double *in, int n, const double *ts,
                               int n_ts, bool deskew, const SE3 &motion, double max_range, double min_range,
-                              double *tmp, double *out, int *out_n) {
+                              double *tmp, double *out, int *out_n, bool in_f32 = false) {
     const bool do_deskew = deskew && n_ts > 0;
     if (do_deskew) {
         // std::minmax_element over ALL stamps (Preprocessing.cpp:62-64)
@@ -413,7 +424,7 @@ __device__ __noinline__ void op_preprocess(Grid &g, const Scratch &sc, Shared &s
     for (long long base = lo; base < hi; base += BLOCK) {
         const long long i = base + threadIdx.x;
         if (i < hi) {
-            V3 p{in[3 * i], in[3 * i + 1], in[3 * i + 2]};
+            V3 p = pre_load(in, i, in_f32);
             if (do_deskew) {
                 const double stamp = (ts[i] - sh.mm[0]) / (sh.mm[1] - sh.mm[0]);
                 double a[6];
@@ -436,13 +447,14 @@ __device__ __noinline__ void op_preprocess(Grid &g, const Scratch &sc, Shared &s
     if (blockIdx.x == 0 && threadIdx.x == 0) *out_n = total;
     // pass 2: ordered compaction
     const double *src = do_deskew ? tmp : in;
+    const bool src_f32 = in_f32 && !do_deskew;
     int run = offset;
     for (long long base = lo; base < hi; base += BLOCK) {
         const long long i = base + threadIdx.x;
         V3 p{0, 0, 0};
         int keep = 0;
         if (i < hi) {
-            p = V3{src[3 * i], src[3 * i + 1], src[3 * i + 2]};
+            p = pre_load(src, i, src_f32);
             const double r = norm(p);
             keep = (r < max_range && r > min_range) ? 1 : 0;
         }

@@ -61,6 +61,7 @@ struct FrameParams {
     double conv, min_motion_th;
     int use_qcache;
     unsigned tag_base;
+    int in_f32;  // the frame is float[n][3] instead of double[n][3]
 };
 
 __device__ __forceinline__ void threshold_update(const SE3 &dev, double min_motion_th, double max_range,
@@ -98,7 +99,7 @@ __global__ void __launch_bounds__(BLOCK, 1) k_register_frame(const FrameParams P
     ds_clear(P.ws.ds2, P.n);
     // Preprocess (KissICP.cpp:38)
     op_preprocess(g, P.sc, sh, P.in, P.n, P.ts, P.n_ts, P.deskew != 0, last_delta, P.max_range, P.min_range,
-                  P.ws.tmp, P.ws.pre, &P.ws.cnt[0]);
+                  P.ws.tmp, P.ws.pre, &P.ws.cnt[0], P.in_f32 != 0);
     g.sync();
     KB_STAMP(1);
     const int n_pre = __ldcg(&P.ws.cnt[0]);

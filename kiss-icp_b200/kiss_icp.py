@@ -146,9 +146,16 @@ class KissICP:
         two device-to-host cloud copies (the pose is available as ``last_pose`` either way)."""
         if not self.fused:
             return self._register_frame_modular(frame, timestamps)
-        pts = N.points_arg(frame)
         ts = np.ascontiguousarray(np.asarray(timestamps).ravel(), dtype=np.float64)
-        N.check(N.lib().kb_pipeline_register_frame(self._h, N.ptr(pts), len(pts), N.ptr(ts), len(ts)))
+        f = np.asarray(frame)
+        if f.dtype == np.float32 and f.ndim == 2 and f.shape[1] == 3:
+            # float32 clouds (KITTI .bin, PointCloud2) go to the device as they are: half the H2D bytes,
+            # widened exactly on the device (the reference does .astype(np.float64) on the host)
+            pts = np.ascontiguousarray(f)
+            N.check(N.lib().kb_pipeline_register_frame_f32(self._h, N.ptr(pts), len(pts), N.ptr(ts), len(ts)))
+        else:
+            pts = N.points_arg(frame)
+            N.check(N.lib().kb_pipeline_register_frame(self._h, N.ptr(pts), len(pts), N.ptr(ts), len(ts)))
         if not return_clouds:
             return None, None
         a, b = N.sz(0), N.sz(0)

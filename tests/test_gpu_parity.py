@@ -405,3 +405,20 @@ def test_pipeline_capacity_veto_and_retry(K, O):
         dt, dr = pose_error(g.last_pose, o.pose)
         assert dt < 1e-6 and dr < 1e-6
         assert g.local_map.num_points() == o.local_map.num_points()
+
+
+def test_pipeline_float32_ingestion_equals_float64(K):
+    """kb_pipeline_register_frame_f32: float32 frames widened on the device give the same trajectory as the
+    float64 call on the host-widened array"""
+    from kiss_icp_b200 import synthetic
+    for stamps in ("none", "column"):
+        L = synthetic.small_shape(seed=13, beams=32, cols=512, stamps=stamps)
+        a, b = K.KissICP(K.load_config()), K.KissICP(K.load_config())
+        for k in range(8):
+            p, t = L.scan(k)
+            p32 = p.astype(np.float32)
+            assert np.array_equal(p32.astype(np.float64), p)  # synthetic scans are fp32-representable like KITTI
+            pa, sa = a.register_frame(p32, t)
+            pb, sb = b.register_frame(p, t)
+            assert np.array_equal(a.last_pose, b.last_pose)
+            assert np.array_equal(pa, pb) and np.array_equal(sa, sb)
