@@ -1188,6 +1188,24 @@ int kb_debug_icp_solve(const double A[36], const double b[6], double x_exact[6],
     se3_to_matrix(se3_mul_fast(se3_exp_fast(x_fast), base), T_fast);
     return KB_OK;
 }
+int kb_debug_icp_schur(const double acc[16], double x_schur[6], double x_ldlt[6], int *used_schur) {
+    // host evaluation: the structured Schur solve vs the pivoted LDL^T on the same 16 accumulators
+    if (!acc || !x_schur || !x_ldlt || !used_schur) return fail(KB_ERR_INVALID_ARG, "NULL argument");
+    double JTJ[36], JTr[6], rhs[6];
+    for (int i = 0; i < 36; ++i) JTJ[i] = 0.0;
+    JTJ[0] = JTJ[7] = JTJ[14] = acc[0];
+    JTJ[6 * 3 + 1] = -acc[3]; JTJ[6 * 3 + 2] = acc[2]; JTJ[6 * 4 + 0] = acc[3]; JTJ[6 * 4 + 2] = -acc[1];
+    JTJ[6 * 5 + 0] = -acc[2]; JTJ[6 * 5 + 1] = acc[1];
+    JTJ[6 * 3 + 3] = acc[4]; JTJ[6 * 4 + 3] = acc[5]; JTJ[6 * 4 + 4] = acc[6];
+    JTJ[6 * 5 + 3] = acc[7]; JTJ[6 * 5 + 4] = acc[8]; JTJ[6 * 5 + 5] = acc[9];
+    for (int i = 0; i < 6; ++i)
+        for (int j = i + 1; j < 6; ++j) JTJ[6 * i + j] = JTJ[6 * j + i];
+    for (int i = 0; i < 6; ++i) { JTr[i] = acc[10 + i]; rhs[i] = -JTr[i]; }
+    ldlt6_solve_reg(JTJ, rhs, x_ldlt);
+    *used_schur = icp_solve_schur(acc, x_schur) ? 1 : 0;
+    if (!*used_schur) for (int i = 0; i < 6; ++i) x_schur[i] = x_ldlt[i];
+    return KB_OK;
+}
 int kb_debug_barrier_ns(int iters, double *ns_per_barrier) {
     if (!ns_per_barrier || iters < 1) return fail(KB_ERR_INVALID_ARG, "bad argument");
     DefaultCtx *c;

@@ -1229,12 +1229,15 @@ __device__ __noinline__ void op_icp(Grid &g, const Scratch &sc, Shared &sh, cons
                 double sys[NACC];
 #pragma unroll
                 for (int i = 0; i < NACC; ++i) sys[i] = sh.red[i];
-                double JTJ[36], JTr[6], rhs[6], dx[6];
-                icp_expand(sys, JTJ, JTr);
-#pragma unroll
-                for (int i = 0; i < 6; ++i) rhs[i] = -JTr[i];
+                double dx[6];
                 if (dbg_on) { KB_CYC(sc, 6); }
-                ldlt6_solve_fast(JTJ, rhs, dx);                   // :156
+                if (!icp_solve_schur(sys, dx)) {                  // :156 — structured 3x3 Schur solve; degenerate
+                    double JTJ[36], JTr[6], rhs[6];               // systems take the pivoted LDL^T with Eigen's zero-pivot rule
+                    icp_expand(sys, JTJ, JTr);
+#pragma unroll
+                    for (int i = 0; i < 6; ++i) rhs[i] = -JTr[i];
+                    ldlt6_solve_fast(JTJ, rhs, dx);
+                }
                 if (dbg_on) { KB_CYC(sc, 7); }
                 const SE3 est = se3_exp_fast(dx);                 // :157
                 if (dbg_on) { KB_CYC(sc, 8); }

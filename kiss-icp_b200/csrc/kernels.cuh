@@ -137,13 +137,11 @@ __global__ void __launch_bounds__(BLOCK, 1) k_register_frame(const FrameParams P
     const double icp_cand = sh.cand_total, icp_q = sh.query_total;
     const double cs0 = sh.cache_stats[0], cs1 = sh.cache_stats[1], cs2 = sh.cache_stats[2];
     KB_STAMP(4);
-    // local_map_.Update(frame_downsample, new_pose) (KissICP.cpp:61)
-    op_map_add(g, sh, P.m, P.ws.ds1, n_ds, true, new_pose, P.ws.tp, P.ws.next, P.ws.touched, &P.res->t_ns[8]);
-    op_map_remove_far(P.m, new_pose.t);
-    g.sync();
-    KB_STAMP(5);
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        // model deviation, threshold, delta, pose (KissICP.cpp:57-63)
+    // Bookkeeping (KissICP.cpp:57-63: model deviation, threshold, delta, pose) is ~6 us of single-thread FP64
+    // math; it only needs new_pose, so one thread of the LAST CTA does it now, hidden behind the map update's
+    // first phase (that thread owns no insert work), instead of serially after the map update.
+    const bool book = (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0);
+    if (book) {
         const SE3 dev = se3_mul(se3_inverse(guess), new_pose);
         double sse = model_sse;
         int ns = num_samples;
@@ -168,6 +166,14 @@ __global__ void __launch_bounds__(BLOCK, 1) k_register_frame(const FrameParams P
         r->n_pre = n_pre;
         r->n_ds = n_ds;
         r->n_src = n_src;
+    }
+    // local_map_.Update(frame_downsample, new_pose) (KissICP.cpp:61)
+    op_map_add(g, sh, P.m, P.ws.ds1, n_ds, true, new_pose, P.ws.tp, P.ws.next, P.ws.touched, &P.res->t_ns[8]);
+    op_map_remove_far(P.m, new_pose.t);
+    g.sync();
+    KB_STAMP(5);
+    if (book) {
+        FrameResult *r = P.res;
         r->map_live = P.m.counters[C_LIVE];
         r->map_tomb = P.m.counters[C_TOMB];
         r->map_points = P.m.counters[C_POINTS];

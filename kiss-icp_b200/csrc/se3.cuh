@@ -665,4 +665,53 @@ KB_HD SE3 se3_mul_fast(const SE3 &a, const SE3 &b) {
     return r;
 }
 
+// ---- structured solve of the ICP normal equations ------------------------------------------
+// With J = [I | -hat(s)] the 6x6 system is  [ a I   B^T ] [x1]   [r1]      a = sum w,  B = hat(m), m = sum w s,
+//                                           [ B     C   ] [x2] = [r2]      C = sum w hat(s)^T hat(s)
+// so x2 solves the 3x3 Schur complement  S x2 = r2 - (m x r1)/a,  S = C + (m m^T - |m|^2 I)/a,  and
+// x1 = (r1 + m x x2)/a. ~90 flops and two reciprocals instead of a pivoted 6x6 LDL^T (~3100 cycles of
+// dependent FP64 work on B200): the same linear system, a different rounding path (like the reference's own
+// nondeterministic summation order). Returns false (caller falls back to the LDL^T) when the system is
+// degenerate: no correspondences, or a Schur complement that is not safely invertible.
+KB_HD bool icp_solve_schur(const double acc[16], double dx[6]) {
+    const double a = acc[0];
+    if (!(a > 1e-300)) return false;
+    const double inv_a = fast_rcp(a);
+    const V3 m{acc[1], acc[2], acc[3]};
+    // rhs = -JTr
+    const V3 r1{-acc[10], -acc[11], -acc[12]};
+    const V3 r2{-acc[13], -acc[14], -acc[15]};
+    // C (symmetric): (3,3) (4,3) (4,4) (5,3) (5,4) (5,5) = acc[4..9]
+    const double mm = sqnorm(m);
+    const double s00 = acc[4] + (m.x * m.x - mm) * inv_a;
+    const double s10 = acc[5] + (m.y * m.x) * inv_a;
+    const double s11 = acc[6] + (m.y * m.y - mm) * inv_a;
+    const double s20 = acc[7] + (m.z * m.x) * inv_a;
+    const double s21 = acc[8] + (m.z * m.y) * inv_a;
+    const double s22 = acc[9] + (m.z * m.z - mm) * inv_a;
+    const V3 mxr1 = cross(m, r1);
+    const V3 b{r2.x - mxr1.x * inv_a, r2.y - mxr1.y * inv_a, r2.z - mxr1.z * inv_a};
+    // adjugate of the symmetric 3x3
+    const double c00 = s11 * s22 - s21 * s21;
+    const double c01 = s20 * s21 - s10 * s22;
+    const double c02 = s10 * s21 - s20 * s11;
+    const double c11 = s00 * s22 - s20 * s20;
+    const double c12 = s10 * s20 - s00 * s21;
+    const double c22 = s00 * s11 - s10 * s10;
+    const double det = s00 * c00 + s10 * c01 + s20 * c02;
+    const double scale = (fabs(s00) + fabs(s11) + fabs(s22)) * (1.0 / 3.0);
+    if (!(fabs(det) > 1e-9 * scale * scale * scale) || !(scale > 0.0)) return false;
+    const double inv_det = fast_rcp(det);
+    const V3 x2{(c00 * b.x + c01 * b.y + c02 * b.z) * inv_det, (c01 * b.x + c11 * b.y + c12 * b.z) * inv_det,
+                (c02 * b.x + c12 * b.y + c22 * b.z) * inv_det};
+    const V3 mxx2 = cross(m, x2);
+    dx[0] = (r1.x + mxx2.x) * inv_a;
+    dx[1] = (r1.y + mxx2.y) * inv_a;
+    dx[2] = (r1.z + mxx2.z) * inv_a;
+    dx[3] = x2.x;
+    dx[4] = x2.y;
+    dx[5] = x2.z;
+    return true;
+}
+
 }  // namespace kb

@@ -130,3 +130,40 @@ def test_fast_icp_solve_variants_stay_within_ulps_of_exact():
     xe, xf, Te, Tf = np.empty(6), np.empty(6), np.empty((4, 4)), np.empty((4, 4))
     N.check(N.lib().kb_debug_icp_solve(N.ptr(A), N.ptr(b), N.ptr(xe), N.ptr(xf), N.ptr(Te), N.ptr(Tf)))
     assert not xe.any() and not xf.any()
+
+
+def test_structured_schur_solve_matches_ldlt():
+    """the ICP loop solves the normal equations through their structure (3x3 Schur complement); on systems
+    assembled from real correspondences it must agree with the pivoted 6x6 LDL^T, and it must decline
+    degenerate systems (which then take the LDL^T path with Eigen's zero-pivot rule)"""
+    from kiss_icp_b200 import _native as N
+    rng = np.random.default_rng(10)
+
+    def accumulate(S, R, W):
+        acc = np.zeros(16)
+        for s, r, w in zip(S, R, W):
+            x, y, z = s
+            acc[0] += w; acc[1] += w * x; acc[2] += w * y; acc[3] += w * z
+            acc[4] += w * (z * z + y * y); acc[5] += -w * x * y; acc[6] += w * (z * z + x * x)
+            acc[7] += -w * x * z; acc[8] += -w * y * z; acc[9] += w * (y * y + x * x)
+            acc[10:13] += w * r
+            acc[13] += w * (-z * r[1] + y * r[2]); acc[14] += w * (z * r[0] - x * r[2]); acc[15] += w * (-y * r[0] + x * r[1])
+        return acc
+
+    for scale in (1.0, 30.0, 100.0):
+        for _ in range(25):
+            n = int(rng.integers(6, 400))
+            S = rng.normal(size=(n, 3)) * scale + rng.normal(size=3) * scale
+            R = rng.normal(size=(n, 3)) * 0.1
+            W = rng.random(n) + 0.01
+            acc = np.ascontiguousarray(accumulate(S, R, W))
+            xs, xl, used = np.empty(6), np.empty(6), N.i32(0)
+            N.check(N.lib().kb_debug_icp_schur(N.ptr(acc), N.ptr(xs), N.ptr(xl), C.byref(used)))
+            assert used.value == 1
+            assert np.allclose(xs, xl, rtol=1e-8, atol=1e-11 * max(1.0, np.abs(xl).max()))
+    # degenerate: nothing accumulated / all source points on one line through the origin
+    for acc in (np.zeros(16), accumulate(np.outer(np.arange(1, 8.0), [1.0, 2.0, 3.0]), rng.normal(size=(7, 3)), np.ones(7))):
+        acc = np.ascontiguousarray(acc)
+        xs, xl, used = np.empty(6), np.empty(6), N.i32(0)
+        N.check(N.lib().kb_debug_icp_schur(N.ptr(acc), N.ptr(xs), N.ptr(xl), C.byref(used)))
+        assert used.value == 0 and np.array_equal(xs, xl) and np.all(np.isfinite(xl))
