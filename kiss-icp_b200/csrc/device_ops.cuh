@@ -1056,7 +1056,7 @@ __device__ __forceinline__ void icp_expand(const double a[NACC], double JTJ[36],
 // Reduction order is fixed: query-strided per warp -> 16-warp shuffle tree -> CTAs in order.
 __device__ __noinline__ void icp_queries(const Scratch &sc, Shared &sh, const MapView &m, const double *src, double *work, int n,
                             const SE3 &pending, double max_dist, double kscale, unsigned tag, bool dbg_on,
-                            QCache *qcache = nullptr, bool first = true) {
+                            QCache *qcache = nullptr, bool first = true, bool fill_first = false) {
     // (copying sc / m / pending into locals was measured: -0.6 us on the query phase but slower overall, the
     // extra live registers spill in the search code)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -1095,9 +1095,10 @@ __device__ __noinline__ void icp_queries(const Scratch &sc, Shared &sh, const Ma
                 (qc->any_voxel || (qc->vx == v.x && qc->vy == v.y && qc->vz == v.z)))
                 r = nn_search_cached_fast(*qc, p, lane), ++n_hit;
             else {
-                // the first step of an alignment is the largest: caches filled before it are mostly
-                // invalid right after it, so the (two-pass) fill starts with iteration 1
-                r = nn_search_warp(m, p, lane, sh.wnn[warp], first ? nullptr : qc, radius);
+                // whether filling already pays off on the first iteration depends on the size of the first step:
+                // with a good constant-velocity prediction (steady driving) most caches survive it (measured
+                // -4 us/scan), after a poor one they are refilled on iteration 1 anyway (fill_first = false)
+                r = nn_search_warp(m, p, lane, sh.wnn[warp], (first && !fill_first) ? nullptr : qc, radius);
                 ++n_fill;
                 n_over += (qc->total < 0 && r.d < DBL_MAX) ? 1 : 0;
             }
@@ -1195,7 +1196,7 @@ __device__ __forceinline__ void icp_gather(const Scratch &sc, Shared &sh, unsign
 // ------------------------------------------------------------------------------------------
 __device__ __noinline__ void op_icp(Grid &g, const Scratch &sc, Shared &sh, const MapView &m, const double *src, double *work,
                        int n, const SE3 &guess, double max_dist, double kscale, int max_iter, double conv,
-                       QCache *qcache, unsigned tag_base) {
+                       QCache *qcache, unsigned tag_base, bool fill_first = true) {
     (void)g;
     if (__ldcg(&m.counters[C_LIVE]) == 0 || max_iter <= 0) {  // voxel_map.Empty() -> initial_guess (:143)
         __syncthreads();
@@ -1220,7 +1221,7 @@ __device__ __noinline__ void op_icp(Grid &g, const Scratch &sc, Shared &sh, cons
         if (blockIdx.x == 0 && threadIdx.x == 0 && j < 20) sc.dbg[41 + j] = globaltimer_ns();
         const bool dbg_on = (j == 4);
         const unsigned tag = tag_base + static_cast<unsigned>(j) + 1u;
-        icp_queries(sc, sh, m, j == 0 ? src : work, work, n, pending, max_dist, kscale, tag, dbg_on, qcache, j == 0);
+        icp_queries(sc, sh, m, j == 0 ? src : work, work, n, pending, max_dist, kscale, tag, dbg_on, qcache, j == 0, fill_first);
         if (dbg_on) { KB_CYC(sc, 4); }
         icp_gather(sc, sh, tag);  // group leaders and the coordinator work, everybody else falls through
         if (blockIdx.x == 0) {
