@@ -227,6 +227,9 @@ int kb_pipeline_threshold(const kb_pipeline *p, double *out_sigma);
 /* device-side duration [us] of the phases of the last RegisterFrame, from %globaltimer stamps
  * inside the kernel: preprocess, downsample(0.5v), downsample(1.5v), ICP, map update, epilogue */
 int kb_pipeline_last_profile(const kb_pipeline *p, double *us, int n);
+/* in-kernel phase timestamps (kb_pipeline_last_profile & co.) are OFF by default: every %globaltimer read costs
+ * ~1 us on the kernel's critical path. Enable them for profiling runs only. */
+int kb_pipeline_set_profiling(kb_pipeline *p, int enabled);
 /* per-frame statistics, recorded on the host after every RegisterFrame when enabled (so a
  * benchmark can read them AFTER its timed region): kb_pipeline_set_history(p, capacity) starts
  * a fresh log of up to `capacity` frames */

@@ -146,6 +146,7 @@ SIGNATURES = {
     "kb_pipeline_threshold": (i32, [vp, C.POINTER(dbl)]),
     "kb_pipeline_last_iterations": (i32, [vp, C.POINTER(i32)]),
     "kb_pipeline_last_profile": (i32, [vp, vp, i32]),
+    "kb_pipeline_set_profiling": (i32, [vp, i32]),
     "kb_pipeline_set_history": (i32, [vp, sz]),
     "kb_pipeline_get_history": (i32, [vp, vp, sz, C.POINTER(sz)]),
     "kb_pipeline_launch_count": (i32, [vp, C.POINTER(C.c_ulonglong)]),

@@ -89,7 +89,7 @@ struct Exec {
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     int grid = 0;
-    Scratch sc{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    Scratch sc{};  // all pointers null, profiling off
     unsigned tag_seq = 0;  // launch sequence number of the tagged ICP protocol
     unsigned long long launches = 0;
     unsigned next_tag_base() { return (++tag_seq) << 13; }  // 8192 epochs per launch
@@ -1262,6 +1262,12 @@ int kb_pipeline_last_iterations(const kb_pipeline *p, int *out) {
 int kb_pipeline_last_profile(const kb_pipeline *p, double *us, int n) {
     if (!p || !us) return fail(KB_ERR_INVALID_ARG, "NULL argument");
     for (int i = 0; i < n && i < 6; ++i) us[i] = (static_cast<double>(p->last.t_ns[i + 1]) - static_cast<double>(p->last.t_ns[i])) * 1e-3;
+    return KB_OK;
+}
+int kb_pipeline_set_profiling(kb_pipeline *p, int enabled) {
+    if (!p) return fail(KB_ERR_INVALID_ARG, "p == NULL");
+    p->ex->sc.profile = enabled ? 1 : 0;
+    std::memset(p->last.t_ns, 0, sizeof(p->last.t_ns));
     return KB_OK;
 }
 int kb_pipeline_set_history(kb_pipeline *p, size_t capacity) {

@@ -85,7 +85,8 @@ struct Scratch {
     uint4 *ll_res;    // [LL_RES] epoch-tagged result record published by the coordinator
     uint4 *ll_group;  // [NPART][16] epoch-tagged group partials (second level of the gather tree)
     int *blk_i;     // [grid] ints
-    unsigned long long *dbg;  // [64] %globaltimer stamps of CTA 0 (profiling aid)
+    unsigned long long *dbg;  // [64 + 4*grid] timestamps (profiling aid)
+    int profile;              // 0: no in-kernel timestamps at all (%globaltimer reads cost ~1 us each on the critical path)
 };
 
 // ------------------------------------------------------------------------------------------
@@ -1218,8 +1219,8 @@ __device__ __noinline__ void op_icp(Grid &g, const Scratch &sc, Shared &sh, cons
     SE3 pending = guess;
     int j = 0;
     for (;; ++j) {
-        if (blockIdx.x == 0 && threadIdx.x == 0 && j < 20) sc.dbg[41 + j] = globaltimer_ns();
-        const bool dbg_on = (j == 4);
+        if (sc.profile && blockIdx.x == 0 && threadIdx.x == 0 && j < 20) sc.dbg[41 + j] = globaltimer_ns();
+        const bool dbg_on = sc.profile && (j == 4);
         const unsigned tag = tag_base + static_cast<unsigned>(j) + 1u;
         icp_queries(sc, sh, m, j == 0 ? src : work, work, n, pending, max_dist, kscale, tag, dbg_on, qcache, j == 0, fill_first);
         if (dbg_on) { KB_CYC(sc, 4); }

@@ -79,7 +79,7 @@ __device__ __forceinline__ void threshold_update(const SE3 &dev, double min_moti
 
 // ---- KissICP::RegisterFrame (pipeline/KissICP.cpp:35-68) as ONE persistent kernel ----------
 #define KB_STAMP(i) \
-    if (blockIdx.x == 0 && threadIdx.x == 0) P.res->t_ns[i] = globaltimer_ns()
+    if (P.sc.profile && blockIdx.x == 0 && threadIdx.x == 0) P.res->t_ns[i] = globaltimer_ns()
 
 extern __shared__ __align__(16) unsigned char kb_dyn_smem[];  // QCache[NWARPS][QC_SLOTS] when launched with QC_BYTES
 
@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(BLOCK, 1) k_register_frame(const FrameParams P
     const int n_pre = __ldcg(&P.ws.cnt[0]);
     // Voxelize (KissICP.cpp:70-75)
     op_downsample(g, P.sc, sh, P.ws.pre, n_pre, P.voxel_size * 0.5, P.ws.ds, P.ws.ds1,
-                  &P.ws.cnt[1], &P.res->t_ns[12], true);
+                  &P.ws.cnt[1], P.sc.profile ? &P.res->t_ns[12] : nullptr, true);
     g.sync();
     KB_STAMP(2);
     const int n_ds = __ldcg(&P.ws.cnt[1]);
@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(BLOCK, 1) k_register_frame(const FrameParams P
         }
     }
     op_downsample(g, P.sc, sh, P.ws.ds1, n_ds, P.voxel_size * 1.5, P.ws.ds2, P.ws.src,
-                  &P.ws.cnt[2], &P.res->t_ns[16], true);
+                  &P.ws.cnt[2], P.sc.profile ? &P.res->t_ns[16] : nullptr, true);
     g.sync();
     KB_STAMP(3);
     const int n_src = __ldcg(&P.ws.cnt[2]);
@@ -158,17 +158,19 @@ __global__ void __launch_bounds__(BLOCK, 1) k_register_frame(const FrameParams P
         r->model_sse = sse;
         r->num_samples = ns;
         r->iterations = iters;
-        r->icp_candidates = icp_cand;
         r->icp_queries = icp_q;
-        r->cache_stats[0] = cs0;
-        r->cache_stats[1] = cs1;
-        r->cache_stats[2] = cs2;
         r->n_pre = n_pre;
         r->n_ds = n_ds;
         r->n_src = n_src;
     }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {  // work counters live in the coordinator's shared memory
+        P.res->icp_candidates = icp_cand;
+        P.res->cache_stats[0] = cs0;
+        P.res->cache_stats[1] = cs1;
+        P.res->cache_stats[2] = cs2;
+    }
     // local_map_.Update(frame_downsample, new_pose) (KissICP.cpp:61)
-    op_map_add(g, sh, P.m, P.ws.ds1, n_ds, true, new_pose, P.ws.tp, P.ws.next, P.ws.touched, &P.res->t_ns[8]);
+    op_map_add(g, sh, P.m, P.ws.ds1, n_ds, true, new_pose, P.ws.tp, P.ws.next, P.ws.touched, P.sc.profile ? &P.res->t_ns[8] : nullptr);
     op_map_remove_far(P.m, new_pose.t);
     g.sync();
     KB_STAMP(5);
@@ -178,7 +180,7 @@ __global__ void __launch_bounds__(BLOCK, 1) k_register_frame(const FrameParams P
         r->map_tomb = P.m.counters[C_TOMB];
         r->map_points = P.m.counters[C_POINTS];
         r->map_status = P.m.counters[C_STATUS];
-        r->t_ns[6] = globaltimer_ns();
+        if (P.sc.profile) r->t_ns[6] = globaltimer_ns();
     }
 }
 

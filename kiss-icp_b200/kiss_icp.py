@@ -128,6 +128,10 @@ class KissICP:
         N.check(N.lib().kb_pipeline_last_profile(self._h, N.ptr(us), 6))
         return us
 
+    def set_profiling(self, enabled: bool):
+        """in-kernel phase timestamps (last_profile_us, history phase_us): off by default, ~10 us/scan when on"""
+        N.check(N.lib().kb_pipeline_set_profiling(self._h, int(bool(enabled))))
+
     def start_history(self, capacity: int):
         """log per-frame statistics of the next ``capacity`` fused RegisterFrame calls (host side)"""
         N.check(N.lib().kb_pipeline_set_history(self._h, int(capacity)))

@@ -87,6 +87,7 @@ for stamps in ("none", "column"):
 hdr("timing: KITTI-shape fused pipeline")
 L = synthetic.kitti_shape(seed=0, device="cuda")
 g = K.KissICP(K.load_config()); o = O.KissICP()
+g.set_profiling(not os.environ.get('KB_NO_PROFILE'))
 tg = to = 0; worst = 0
 for k in range(30):
     p, t = L.scan(k)
