@@ -422,3 +422,26 @@ def test_pipeline_float32_ingestion_equals_float64(K):
             pb, sb = b.register_frame(p, t)
             assert np.array_equal(a.last_pose, b.last_pose)
             assert np.array_equal(pa, pb) and np.array_equal(sa, sb)
+
+
+def test_pipeline_work_counters_and_profiling(K):
+    """bookkeeping the bench relies on: per-frame ICP work counters, launch count, optional phase timestamps"""
+    from kiss_icp_b200 import synthetic
+    L = synthetic.small_shape(seed=17, beams=32, cols=512)
+    icp = K.KissICP(K.load_config())
+    icp.start_history(6)
+    for k in range(6):
+        if k == 3:
+            icp.set_profiling(True)
+        p, t = L.scan(k)
+        icp.register_frame(p, t, return_clouds=False)
+    h = icp.history()
+    assert len(h) == 6 and h[0].iterations == 0 and h[0].icp_queries == 0
+    for st in h[1:]:
+        assert st.iterations >= 1 and st.icp_queries == st.iterations * st.n_source
+        assert st.icp_candidates > st.icp_queries  # several candidate points per query on a populated map
+        assert 0 < st.n_source <= st.n_downsampled <= st.n_preprocessed <= st.n_points_in
+        assert st.map_points > 0 and st.map_voxels > 0
+    assert all(sum(st.phase_us) == 0 for st in h[:3])          # timestamps are off by default
+    assert all(10 < sum(st.phase_us) < 1e5 for st in h[3:])    # and plausible when switched on
+    assert np.allclose(np.array(h[-1].pose).reshape(4, 4), icp.last_pose)
