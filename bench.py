@@ -47,54 +47,101 @@ def parse():
     ap.add_argument("--streams", type=int, default=0, help="extra leg: S independent sequences per GPU on S streams")
     ap.add_argument("--no-nn", action="store_true", help="skip the NN-kernel roofline leg")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-clocks", action="store_true", help="diagnostic: do not sample clocks (an invalid run by the bench contract)")
     return ap.parse_args()
 
 
 # ----------------------------------------------------------------------------- clocks sampler
 class ClockSampler:
+    """SM clock + throttle reasons sampled DURING the timed regions. In-process NVML (the counters behind
+    `nvidia-smi --query-gpu=clocks.sm,clocks.max.sm,clocks_event_reasons.*`): a looping nvidia-smi process needs
+    ~0.4 s per sample on an 8-GPU box and was seen stalling 40 ms timed regions; the NVML calls take < 1 ms.
+    Falls back to the nvidia-smi loop of B200_PROFILING.md if NVML cannot be used from Python."""
     QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
+    BITS = {"sw_power_cap": 0x4, "hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
 
-    def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+    def __init__(self, index, uuid=None, period=0.05):
+        self.index, self.uuid, self.period = index, uuid, period
+        self.rows, self.proc, self.nvml, self.first = [], None, None, 0
+        self.max_mhz, self.stop_flag, self.source, self.query_ms = None, False, None, []
 
     def start(self):
         try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = None
+            if self.uuid:
+                try:
+                    h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + str(self.uuid)).encode())
+                except Exception:
+                    h = None
+            if h is None:
+                vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+                ids = [v for v in vis.split(",") if v.strip()]
+                phys = int(ids[self.index]) if ids and all(v.strip().isdigit() for v in ids) else self.index
+                h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            reasons_fn = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+            self.nvml = (pynvml, h, reasons_fn)
+            self.source = "NVML in-process, %d ms period" % int(self.period * 1e3)
+            threading.Thread(target=self._poll, daemon=True).start()
+            return
+        except Exception:
+            self.nvml = None
+        try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
                                           "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            self.source = "nvidia-smi -lms 100"
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        pynvml, h, reasons_fn = self.nvml
+        while not self.stop_flag:
+            try:
+                t0 = time.perf_counter()
+                sm = float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                bits = int(reasons_fn(h))
+                self.rows.append((sm, bits))
+                self.query_ms.append((time.perf_counter() - t0) * 1e3)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            r = [c.strip() for c in line.split(",")]
+            if len(r) > 8 and r[1].replace(".", "").isdigit():
+                bits = 0
+                for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[5:9]):
+                    if v.lower().startswith("active"):
+                        bits |= self.BITS[name]
+                if r[2].replace(".", "").isdigit():
+                    self.max_mhz = max(self.max_mhz or 0.0, float(r[2]))
+                self.rows.append((float(r[1]), bits))
 
     def wait_ready(self, timeout=20.0):
-        """nvidia-smi's NVML start-up stalls the GPU for hundreds of ms: never let it land in a timed region"""
+        """NVML / nvidia-smi start-up stalls the GPU for hundreds of ms: never let it land in a timed region"""
         t0 = time.perf_counter()
-        while self.proc and not self.rows and time.perf_counter() - t0 < timeout:
+        while (self.proc or self.nvml) and not self.rows and time.perf_counter() - t0 < timeout:
             time.sleep(0.05)
 
     def mark(self):
         self.first = len(self.rows)
 
     def stop(self):
+        self.stop_flag = True
         if self.proc:
             self.proc.terminate()
-        self.rows = self.rows[getattr(self, "first", 0):]
-        sm = [float(r[1]) for r in self.rows if len(r) > 8 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) > 8 and r[2].replace(".", "").isdigit()]
-        reasons = set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            if len(r) > 8:
-                for name, v in zip(names, r[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        rows = self.rows[self.first:]
+        sm = [r[0] for r in rows]
+        reasons = sorted(name for name, bit in self.BITS.items() if any(r[1] & bit for r in rows))
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.max_mhz,
+                "reasons": reasons, "samples": len(sm), "source": self.source,
+                "query_ms_max": float(max(self.query_ms)) if self.query_ms else None}
 
 
 # ----------------------------------------------------------------------------- reference arm
@@ -194,8 +241,8 @@ def main():
     torch.cuda.set_stream(stream)
     N.check(N.lib().kb_set_stream(C.c_void_p(stream.cuda_stream)))
 
-    sampler = ClockSampler(local)
-    if rank == 0:
+    sampler = ClockSampler(local, getattr(torch.cuda.get_device_properties(dev), "uuid", None))
+    if rank == 0 and not args.no_clocks:
         sampler.start()  # started long before the timed regions; samples before mark() are dropped
 
     seq = sharding.sequences_of_rank(rank, world, world)[0]
@@ -221,57 +268,81 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---------------- value: inputs resident in HBM
-    icp = make_pipeline()
-    for t in scans_dev[:args.prime + args.warmup]:
-        reg_dev(icp, t)
-    if rank == 0:
-        sampler.wait_ready()
-        sampler.mark()
+    def primed(n_blocking):
+        icp = make_pipeline()
+        for t in scans_dev[:n_blocking]:
+            reg_dev(icp, t)
+        return icp
+
+    def queued(icp, tensors, layout):
+        """KissICP.register_frames on raw addresses: the whole list is queued on the device, copy of frame k+1
+        overlaps the registration of frame k, every frame's result (pose + counters) is read back behind the queue"""
+        k = len(tensors)
+        return icp._register_frames_raw([t.data_ptr() for t in tensors], [t.shape[0] for t in tensors], [None] * k, [0] * k, layout)
+
+    def timed_region(fn):
+        barrier()
+        e0.record(stream)
+        fn()
+        e1.record(stream)
+        barrier()
+        return sharding.max_over_ranks(e0.elapsed_time(e1), dev)
+
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    warm = scans_dev[args.prime:args.prime + args.warmup]
     timed = scans_dev[args.prime + args.warmup:]
-    l0 = launches(icp)
     prof = np.zeros((len(timed), 6))
     iters = np.zeros(len(timed))
     work = np.zeros((len(timed), 2))
     npts = np.zeros(len(timed))
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    wall_dev = np.zeros(len(timed))
-    barrier()
-    e0.record(stream)
-    for i, t in enumerate(timed):
-        t0 = time.perf_counter()
-        reg_dev(icp, t)
-        wall_dev[i] = time.perf_counter() - t0
-    e1.record(stream)
-    barrier()
-    ms_dev = e0.elapsed_time(e1)
-    gpu_launches = launches(icp) - l0
     poses_local = []
-    # per-scan kernel statistics (untimed replay of bookkeeping only: values were stored per frame)
-    # -> collected in a second, untimed pass over the same scans on a fresh primed pipeline below
-    ms_max = sharding.max_over_ranks(ms_dev, dev)
+
+    # ---------------- value: inputs resident in HBM, frames queued (kb_pipeline_register_frames, device layout)
+    icp = primed(args.prime)
+    if rank == 0:
+        sampler.wait_ready()  # NVML start-up perturbs the GPU for tens of ms: let it land in the warm-up
+    queued(icp, warm, 2)
+    if rank == 0:
+        sampler.mark()
+    l0 = launches(icp)
+    ms_max = timed_region(lambda: queued(icp, timed, 2))
+    gpu_launches = launches(icp) - l0
+    ms_dev = ms_max
     value = world * args.steps / (ms_max * 1e-3)
 
-    # ---------------- e2e: host-facing call, pinned host buffers, H2D + D2H inside the timed region
-    icp2 = make_pipeline()
-    for t in scans_dev[:args.prime + args.warmup]:
-        reg_dev(icp2, t)
+    # ---------------- the same with one blocking RegisterFrame call per scan (the reference's call shape)
+    icp_b = primed(args.prime + args.warmup)
+    wall_dev = np.zeros(len(timed))
+
+    def blocking_dev():
+        for i, t in enumerate(timed):
+            t0 = time.perf_counter()
+            reg_dev(icp_b, t)
+            wall_dev[i] = time.perf_counter() - t0
+    ms_dev_blocking = timed_region(blocking_dev)
+
+    # ---------------- e2e: host-facing call, pinned host buffers, H2D + D2H of every step inside the timed region
+    pinned_warm = [t.cpu().pin_memory() for t in warm]
     pinned = [t.cpu().pin_memory() for t in timed]
     h2d = float(np.mean([p.numel() * 8 for p in pinned]))
-    barrier()
+    icp2 = primed(args.prime)
+    queued(icp2, pinned_warm, 0)
+    e2e_poses = []
+    ms_e2e = timed_region(lambda: e2e_poses.append(queued(icp2, pinned, 0)))
+    e2e_value = world * args.steps / (ms_e2e * 1e-3)
+    # blocking form: kb_pipeline_register_frame per scan
+    icp2b = primed(args.prime + args.warmup)
     wall_e2e = np.zeros(len(pinned))
-    e0.record(stream)
-    for i, p in enumerate(pinned):
-        t0 = time.perf_counter()
-        N.check(L.kb_pipeline_register_frame(icp2._h, C.c_void_p(p.data_ptr()), p.shape[0], None, 0))
-        wall_e2e[i] = time.perf_counter() - t0
-    e1.record(stream)
-    barrier()
+
+    def blocking_e2e():
+        for i, p in enumerate(pinned):
+            t0 = time.perf_counter()
+            N.check(L.kb_pipeline_register_frame(icp2b._h, C.c_void_p(p.data_ptr()), p.shape[0], None, 0))
+            wall_e2e[i] = time.perf_counter() - t0
+    ms_e2e_blocking = timed_region(blocking_e2e)
     # ---------------- profiling pass (untimed): the same scans once more with the in-kernel phase timestamps ON
     # (they cost ~1 us each on the kernel's critical path, so the timed passes above run without them)
-    icp4 = make_pipeline()
-    for t in scans_dev[:args.prime + args.warmup]:
-        reg_dev(icp4, t)
+    icp4 = primed(args.prime + args.warmup)
     icp4.set_profiling(True)
     icp4.start_history(len(timed))
     for t in timed:
@@ -282,26 +353,18 @@ def main():
         work[i] = (st.icp_queries, st.icp_candidates)
         npts[i] = st.n_points_in
         poses_local.append(np.array(st.pose).reshape(4, 4))
-    ms_e2e = sharding.max_over_ranks(e0.elapsed_time(e1), dev)
-    e2e_value = world * args.steps / (ms_e2e * 1e-3)
     # ---------------- e2e, float32 ingestion (KITTI .bin / PointCloud2 are float32; the scans are fp32-representable)
-    icp3 = make_pipeline()
-    for t in scans_dev[:args.prime + args.warmup]:
-        reg_dev(icp3, t)
+    icp3 = primed(args.prime)
+    queued(icp3, [p.to(torch.float32).pin_memory() for p in pinned_warm], 1)
     pinned32 = [p.to(torch.float32).pin_memory() for p in pinned]
-    barrier()
-    e0.record(stream)
-    for p in pinned32:
-        N.check(L.kb_pipeline_register_frame_f32(icp3._h, C.c_void_p(p.data_ptr()), p.shape[0], None, 0))
-    e1.record(stream)
-    barrier()
-    ms_e2e32 = sharding.max_over_ranks(e0.elapsed_time(e1), dev)
+    ms_e2e32 = timed_region(lambda: queued(icp3, pinned32, 1))
     same32 = bool(np.array_equal(icp3.last_pose, icp2.last_pose))
     clocks = sampler.stop() if rank == 0 else None
     d2h = 392.0  # sizeof(FrameResult): pose, delta, sigma, counters, stamps
 
     # the two pipelines saw identical inputs -> identical trajectories (determinism check)
-    same = bool(np.allclose(icp.last_pose, icp2.last_pose, atol=1e-12))
+    same = bool(np.array_equal(icp.last_pose, icp2.last_pose) and np.array_equal(icp_b.last_pose, icp2b.last_pose)
+                and np.array_equal(icp.last_pose, icp_b.last_pose) and np.array_equal(e2e_poses[0][-1], icp2.last_pose))
     all_poses = sharding.gather_poses(np.array(poses_local), dev)  # NCCL all_gather of the trajectories
 
     if rank != 0:
@@ -319,7 +382,7 @@ def main():
     # (24 + 27*16 + 32 per query + 24 per candidate) + one-off streams (raw scan in, result out)
     bytes_per_launch = work[:, 0] * (24 + 27 * 16 + 32) + 24.0 * work[:, 1] + 24.0 * npts + d2h
     # average launch duration of the dominant kernel: CUDA events over the timed (uninstrumented) region of the
-    # resident-input pass, one launch per step (this includes ~5 us of launch/sync overhead per step)
+    # resident-input pass, one launch per step, launches queued back to back
     kern_us = np.full(len(timed), ms_dev * 1e3 / len(timed))
     achieved = float(bytes_per_launch.mean() / (kern_us.mean() * 1e-6) / 1e9)
     roofline = {"kernel": "k_register_frame (persistent cooperative, 1 launch/scan)", "bound": "hbm",
@@ -349,14 +412,21 @@ def main():
                        "phase_us": dict(zip(["preprocess", "downsample_0.5v", "downsample_1.5v", "icp", "map_update", "epilogue"],
                                             [float(x) for x in prof.mean(0)])),
                        "call_latency_ms": {"resident": {"p50": float(np.percentile(wall_dev, 50) * 1e3), "p99": float(np.percentile(wall_dev, 99) * 1e3), "max": float(wall_dev.max() * 1e3)},
-                                           "e2e": {"p50": float(np.percentile(wall_e2e, 50) * 1e3), "p99": float(np.percentile(wall_e2e, 99) * 1e3), "max": float(wall_e2e.max() * 1e3)}},
+                                           "e2e": {"p50": float(np.percentile(wall_e2e, 50) * 1e3), "p99": float(np.percentile(wall_e2e, 99) * 1e3), "max": float(wall_e2e.max() * 1e3)},
+                                           "over_2ms": {"resident": [[int(i), float(wall_dev[i] * 1e3)] for i in np.nonzero(wall_dev > 2e-3)[0][:8]],
+                                                        "e2e": [[int(i), float(wall_e2e[i] * 1e3)] for i in np.nonzero(wall_e2e > 2e-3)[0][:8]]}},
                        "deterministic_replay": same, "gathered_trajectories": list(all_poses.shape)},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "scans/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": ms_e2e / args.steps},
+                    "ms_per_step": ms_e2e / args.steps,
+                    "api": "KissICP.register_frames / kb_pipeline_register_frames: pinned host float64 frames in, poses out; "
+                           "frames queued 3 deep (H2D of scan k+1 overlaps registration of scan k)"},
+            "blocking_calls": {"note": "one kb_pipeline_register_frame[_dev] call per scan, host waits for every result (the reference's call shape)",
+                               "value_resident": world * args.steps / (ms_dev_blocking * 1e-3),
+                               "e2e": world * args.steps / (ms_e2e_blocking * 1e-3), "unit": "scans/s"},
             "e2e_f32": {"value": world * args.steps / (ms_e2e32 * 1e-3), "unit": "scans/s", "h2d_bytes_per_step": h2d / 2,
                         "d2h_bytes_per_step": d2h, "same_trajectory_as_f64": same32,
-                        "note": "kb_pipeline_register_frame_f32: float32 host frames (native KITTI/ROS payload), widened on the device"},
+                        "note": "register_frames, float32 host frames (native KITTI/ROS payload), widened on the device"},
             "gpu_launches": int(gpu_launches),
             "roofline": roofline, "nn_kernel": nn, "multi_stream": ms_leg, "cpu_baseline": cpu}
     print(json.dumps(line), flush=True)

@@ -181,6 +181,20 @@ int kb_pipeline_register_frame_f32(kb_pipeline *p, const float *xyz, size_t n, c
 /* same, frame (and stamps) already resident in HBM on the pipeline's device */
 int kb_pipeline_register_frame_dev(kb_pipeline *p, const double *d_xyz, size_t n, const double *d_timestamps,
                                    size_t n_timestamps);
+/* A whole sequence: the loop `for frame in dataset: RegisterFrame(frame, stamps)` of
+ * python/kiss_icp/pipeline.py:106-112 as one call. Poses, motion model, threshold and map never leave the device
+ * between frames, so the frames are QUEUED: frame k+1 is copied to the device while frame k is registered and
+ * results are read back behind the queue (depth 3). Results are identical to `count` blocking calls.
+ * xyz[k] is frame k in the given layout, timestamps / n_timestamps may be NULL (no stamps at all);
+ * poses_out, if not NULL, receives the `count` row-major poses. An invalid frame (e.g. too few stamps) stops the
+ * sequence with the error the blocking call would give, after the frames before it were registered. Host buffers
+ * may be pageable (staged through pinned memory) or pinned (copied directly). */
+enum kb_frame_layout { KB_FRAMES_HOST_F64 = 0, KB_FRAMES_HOST_F32 = 1, KB_FRAMES_DEVICE_F64 = 2 };
+int kb_pipeline_register_frames(kb_pipeline *p, const void *const *xyz, const size_t *n,
+                                const double *const *timestamps, const size_t *n_timestamps, size_t count,
+                                int layout, double *poses_out);
+/* how many frames were vetoed by the kernel (voxel table sized too optimistically), grown for and replayed */
+int kb_pipeline_grow_retries(const kb_pipeline *p, unsigned long long *out);
 /* sizes / contents of the (preprocessed_frame, source) tuple of the last RegisterFrame */
 int kb_pipeline_last_cloud_sizes(const kb_pipeline *p, size_t *n_preprocessed, size_t *n_source);
 int kb_pipeline_last_clouds(const kb_pipeline *p, double *preprocessed_xyz, size_t cap_preprocessed,

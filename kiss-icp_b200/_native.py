@@ -125,6 +125,8 @@ SIGNATURES = {
     "kb_pipeline_register_frame": (i32, [vp, vp, sz, vp, sz]),
     "kb_pipeline_register_frame_f32": (i32, [vp, vp, sz, vp, sz]),
     "kb_pipeline_register_frame_dev": (i32, [vp, vp, sz, vp, sz]),
+    "kb_pipeline_register_frames": (i32, [vp, vp, vp, vp, vp, sz, i32, vp]),
+    "kb_pipeline_grow_retries": (i32, [vp, C.POINTER(C.c_ulonglong)]),
     "kb_pipeline_last_cloud_sizes": (i32, [vp, C.POINTER(sz), C.POINTER(sz)]),
     "kb_pipeline_last_clouds": (i32, [vp, vp, sz, vp, sz]),
     "kb_pipeline_voxelize": (i32, [vp, vp, sz, vp, sz, C.POINTER(sz), vp, sz, C.POINTER(sz)]),

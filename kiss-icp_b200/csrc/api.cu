@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -77,6 +78,28 @@ struct DBuf {
     }
 };
 
+// KB_TRACE_STALLS=<ms>: report host-side API calls of the frame paths that block longer than <ms> (diagnostic)
+struct StallTrace {
+    const char *what;
+    std::chrono::steady_clock::time_point t0;
+    static double limit_ms() {
+        static const double v = [] {
+            const char *e = std::getenv("KB_TRACE_STALLS");
+            return e ? std::atof(e) : 0.0;
+        }();
+        return v;
+    }
+    explicit StallTrace(const char *w) : what(w) {
+        if (limit_ms() > 0.0) t0 = std::chrono::steady_clock::now();
+    }
+    ~StallTrace() {
+        if (limit_ms() > 0.0) {
+            const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+            if (ms > limit_ms()) std::fprintf(stderr, "[kb stall] %s took %.1f ms\n", what, ms);
+        }
+    }
+};
+
 size_t pow2_at_least(size_t v) {
     size_t p = 1;
     while (p < v) p <<= 1;
@@ -92,6 +115,7 @@ struct Exec {
     Scratch sc{};  // all pointers null, profiling off
     unsigned tag_seq = 0;  // launch sequence number of the tagged ICP protocol
     unsigned long long launches = 0;
+    bool bar_dirty = true;  // the barrier words may be non-zero (a kernel without Grid::finish() ran last)
     unsigned next_tag_base() { return (++tag_seq) << 13; }  // 8192 epochs per launch
 
     int init() {
@@ -111,6 +135,7 @@ struct Exec {
         grid = tl_grid_blocks > 0 ? std::min(tl_grid_blocks, sms) : sms;
         grid = std::min(grid, 256);  // the two-level gather tree of the ICP loop handles up to 16 x 16 CTAs
         CK(cudaMalloc(&sc.bar, BAR_WORDS * sizeof(unsigned)));
+        CK(cudaMemsetAsync(sc.bar, 0, BAR_WORDS * sizeof(unsigned), stream));
         CK(cudaMalloc(&sc.blk_d, sizeof(double) * 2 * grid * NPART));
         CK(cudaMalloc(&sc.blk_i, sizeof(int) * 2 * grid));
         CK(cudaMalloc(&sc.icp_rec, sizeof(double) * 2 * ICP_REC));
@@ -136,7 +161,7 @@ struct Exec {
         if (own_stream && stream) cudaStreamDestroy(stream);
     }
     template <class P>
-    int coop(void (*kern)(P), const P &p, size_t smem = 0) {
+    int coop(void (*kern)(P), const P &p, size_t smem = 0, bool self_reset = false) {
         CK(cudaSetDevice(device));
         if (smem > 48 * 1024) {  // opt in to large dynamic shared memory once per kernel
             static thread_local std::vector<const void *> done;
@@ -146,7 +171,9 @@ struct Exec {
                 done.push_back(k);
             }
         }
-        CK(cudaMemsetAsync(sc.bar, 0, BAR_WORDS * sizeof(unsigned), stream));
+        if (!self_reset || bar_dirty)  // kernels that end with Grid::finish() leave the barrier words zeroed themselves
+            CK(cudaMemsetAsync(sc.bar, 0, BAR_WORDS * sizeof(unsigned), stream));
+        bar_dirty = !self_reset;
         void *args[] = {const_cast<P *>(&p)};
         CK(cudaLaunchCooperativeKernel(reinterpret_cast<const void *>(kern), dim3(grid), dim3(BLOCK), args, smem, stream));
         ++launches;
@@ -156,6 +183,7 @@ struct Exec {
     int coop(void (*kern)(A, B), const A &a, const B &b) {
         CK(cudaSetDevice(device));
         CK(cudaMemsetAsync(sc.bar, 0, BAR_WORDS * sizeof(unsigned), stream));
+        bar_dirty = true;
         void *args[] = {const_cast<A *>(&a), const_cast<B *>(&b)};
         CK(cudaLaunchCooperativeKernel(reinterpret_cast<const void *>(kern), dim3(grid), dim3(BLOCK), args, 0, stream));
         ++launches;
@@ -249,41 +277,76 @@ struct kb_map {
         m.vdiv = make_voxel_div(voxel_size);
         return m;
     }
-    void free_table() {
-        if (slots) cudaFree(slots);
-        if (points) cudaFree(points);
-        if (head) cudaFree(head);
-        if (pcount) cudaFree(pcount);
-        if (pending) cudaFree(pending);
-        slots = nullptr;
-        points = nullptr;
-        head = nullptr;
-        pcount = nullptr;
-        pending = nullptr;
+    // the table a rebuild moves the map into. Rebuilds are periodic in steady state (tombstones of voxels that left
+    // max_distance accumulate until load 0.5) and mostly keep the size, so the previous table is kept as a spare
+    // and the two ping-pong: cudaMalloc/cudaFree of a few hundred MB took 10-300 ms on the hot path.
+    struct Table {
+        size_t capacity = 0;
+        int4 *slots = nullptr;
+        double *points = nullptr;
+        int *head = nullptr, *pcount = nullptr, *pending = nullptr, *counters = nullptr;
+    };
+    Table spare;
+    static void free_table(Table &t) {
+        if (t.slots) cudaFree(t.slots);
+        if (t.points) cudaFree(t.points);
+        if (t.head) cudaFree(t.head);
+        if (t.pcount) cudaFree(t.pcount);
+        if (t.pending) cudaFree(t.pending);
+        if (t.counters) cudaFree(t.counters);
+        t = Table{};
+    }
+    Table current() const { return Table{capacity, slots, points, head, pcount, pending, counters}; }
+    void adopt(const Table &t) {
+        capacity = t.capacity;
+        slots = t.slots;
+        points = t.points;
+        head = t.head;
+        pcount = t.pcount;
+        pending = t.pending;
+        counters = t.counters;
     }
     ~kb_map() {
         if (ex) cudaSetDevice(ex->device);
-        free_table();
-        if (counters) cudaFree(counters);
+        Table t = current();
+        free_table(t);
+        free_table(spare);
     }
-    int alloc_table(size_t cap_slots, int4 **s, double **p, int **h, int **pc, int **pe) {
-        CK(cudaMalloc(s, cap_slots * sizeof(int4)));
-        CK(cudaMalloc(p, cap_slots * cap * 3 * sizeof(double)));
-        CK(cudaMalloc(h, cap_slots * sizeof(int)));
-        CK(cudaMalloc(pc, cap_slots * sizeof(int)));
-        CK(cudaMalloc(pe, cap_slots * PEND * sizeof(int)));
-        k_map_fill<<<std::min<size_t>(4096, (cap_slots + 255) / 256), 256, 0, ex->stream>>>(*s, *h, *pc, cap_slots);
+    // an empty table of cap_slots slots: the spare if it has that size, else a fresh allocation
+    int take_table(size_t cap_slots, Table *out) {
+        Table t;
+        if (spare.capacity == cap_slots) {
+            t = spare;
+            spare = Table{};
+        } else {
+            free_table(spare);
+            t.capacity = cap_slots;
+            auto bail = [&](cudaError_t e) {
+                free_table(t);
+                return fail(KB_ERR_CUDA, "voxel table allocation (%zu slots): %s", cap_slots, cudaGetErrorString(e));
+            };
+            cudaError_t e;
+            if ((e = cudaMalloc(&t.slots, cap_slots * sizeof(int4))) != cudaSuccess) return bail(e);
+            if ((e = cudaMalloc(&t.points, cap_slots * cap * 3 * sizeof(double))) != cudaSuccess) return bail(e);
+            if ((e = cudaMalloc(&t.head, cap_slots * sizeof(int))) != cudaSuccess) return bail(e);
+            if ((e = cudaMalloc(&t.pcount, cap_slots * sizeof(int))) != cudaSuccess) return bail(e);
+            if ((e = cudaMalloc(&t.pending, cap_slots * PEND * sizeof(int))) != cudaSuccess) return bail(e);
+            if ((e = cudaMalloc(&t.counters, sizeof(int) * C_NCOUNTERS)) != cudaSuccess) return bail(e);
+        }
+        k_map_fill<<<std::min<size_t>(4096, (cap_slots + 255) / 256), 256, 0, ex->stream>>>(t.slots, t.head, t.pcount, cap_slots);
         ++ex->launches;
         CK(cudaGetLastError());
+        CK(cudaMemsetAsync(t.counters, 0, sizeof(int) * C_NCOUNTERS, ex->stream));
+        *out = t;
         return KB_OK;
     }
     // make room for `extra` more voxels at load factor <= 0.5 (tombstones count as load)
+    bool would_grow(size_t extra) const {  // ensure_capacity(extra) would rebuild the table (needs an idle stream)
+        const size_t live = static_cast<size_t>(h_counters[C_LIVE]), tomb = static_cast<size_t>(h_counters[C_TOMB]);
+        return !capacity || (live + tomb + extra) * 2 > capacity;
+    }
     int ensure_capacity(size_t extra, size_t force_want = 0) {
         CK(cudaSetDevice(ex->device));
-        if (!counters) {
-            CK(cudaMalloc(&counters, sizeof(int) * C_NCOUNTERS));
-            CK(cudaMemsetAsync(counters, 0, sizeof(int) * C_NCOUNTERS, ex->stream));
-        }
         const size_t live = static_cast<size_t>(h_counters[C_LIVE]), tomb = static_cast<size_t>(h_counters[C_TOMB]);
         if (!force_want && capacity && (live + tomb + extra) * 2 <= capacity) return KB_OK;
         // grow/rebuild target: load factor <= 1/3 right after the rebuild (tombstones then accumulate up to 1/2)
@@ -291,44 +354,47 @@ struct kb_map {
             const char *e = std::getenv("KB_MAP_CAP_FACTOR");  // tuning aid: slots per expected voxel after a rebuild
             return (e && std::atoi(e) >= 2) ? static_cast<size_t>(std::atoi(e)) : size_t(3);
         }();
-        const size_t want = force_want ? force_want : std::max<size_t>(pow2_at_least(cap_factor * (live + extra)), size_t(1) << 14);
+        // never shrink on the hot path: the spare table has the current size, a smaller one would mean cudaMalloc
+        const size_t want = force_want ? force_want
+                                       : std::max<size_t>({pow2_at_least(cap_factor * (live + extra)), size_t(1) << 14, capacity});
         if (want > (size_t(1) << 31)) return fail(KB_ERR_INVALID_ARG, "voxel table would exceed 2^31 slots");
-        int4 *ns;
-        double *np;
-        int *nh, *npc, *npe;
-        RET(alloc_table(want, &ns, &np, &nh, &npc, &npe));
+        StallTrace trace("voxel table rebuild");
+        Table nt;
+        RET(take_table(want, &nt));
         if (capacity && live) {
             MapView from = view();
             MapView to = from;
-            to.slots = ns;
-            to.points = np;
-            to.head = nh;
-            to.pcount = npc;
-            to.pending = npe;
+            to.slots = nt.slots;
+            to.points = nt.points;
+            to.head = nt.head;
+            to.pcount = nt.pcount;
+            to.pending = nt.pending;
+            to.counters = nt.counters;
             to.mask = static_cast<unsigned>(want - 1);
-            int *nc;
-            CK(cudaMalloc(&nc, sizeof(int) * C_NCOUNTERS));
-            CK(cudaMemsetAsync(nc, 0, sizeof(int) * C_NCOUNTERS, ex->stream));
-            to.counters = nc;
             k_map_rehash<<<std::min<size_t>(2048, (capacity * 32 + 255) / 256), 256, 0, ex->stream>>>(from, to);
             ++ex->launches;
             CK(cudaGetLastError());
-            CK(cudaMemcpyAsync(h_counters, nc, sizeof(int) * C_NCOUNTERS, cudaMemcpyDeviceToHost, ex->stream));
+            CK(cudaMemcpyAsync(h_counters, nt.counters, sizeof(int) * C_NCOUNTERS, cudaMemcpyDeviceToHost, ex->stream));
             RET(ex->sync());
-            cudaFree(counters);
-            counters = nc;
-        } else if (capacity) {
-            CK(cudaMemsetAsync(counters, 0, sizeof(int) * C_NCOUNTERS, ex->stream));
+        } else {
             std::memset(h_counters, 0, sizeof(h_counters));
-            RET(ex->sync());
         }
-        free_table();
-        slots = ns;
-        points = np;
-        head = nh;
-        pcount = npc;
-        pending = npe;
-        capacity = want;
+        Table old = current();
+        adopt(nt);
+        free_table(spare);  // (empty unless take_table allocated)
+        spare = old;        // stays allocated: the next same-size rebuild moves back into it
+        return KB_OK;
+    }
+    // allocate the table AND its spare for `slots` slots now (pipeline creation), so that neither growth nor the
+    // periodic tombstone rebuild has to call cudaMalloc while frames are being registered
+    int reserve(size_t slots) {
+        slots = pow2_at_least(slots);
+        if (slots > capacity) RET(ensure_capacity(0, slots));
+        if (spare.capacity != capacity) {
+            Table t;
+            RET(take_table(capacity, &t));  // frees a spare of another size
+            spare = t;
+        }
         return KB_OK;
     }
     int pull_counters() {
@@ -416,8 +482,31 @@ struct kb_pipeline {
     unsigned long long grow_retries = 0;
     std::vector<kb_frame_stats> history;
     size_t history_cap = 0;
+    // frame queue of kb_pipeline_register_frames: frame k+1 is copied in while frame k is registered
+    static constexpr int Q_DEPTH = 3;
+    struct Slot {
+        DBuf<double> in, ts;  // device copy of one queued frame
+        void *pin_xyz = nullptr, *pin_ts = nullptr;  // pinned staging, used only when the caller's memory is pageable
+        size_t pin_xyz_bytes = 0, pin_ts_bytes = 0;
+        cudaEvent_t copied = nullptr, done = nullptr, read = nullptr;
+    };
+    Slot q[Q_DEPTH];
+    cudaStream_t copy_stream = nullptr, res_stream = nullptr;
+    FrameResult *q_res = nullptr;      // [Q_DEPTH] pinned host copies of the frame results
+    FrameResult *q_res_dev = nullptr;  // [Q_DEPTH] device side: where the kernels write them
     ~kb_pipeline() {
         if (ex) cudaSetDevice(ex->device);
+        for (Slot &s : q) {
+            if (s.pin_xyz) cudaFreeHost(s.pin_xyz);
+            if (s.pin_ts) cudaFreeHost(s.pin_ts);
+            if (s.copied) cudaEventDestroy(s.copied);
+            if (s.done) cudaEventDestroy(s.done);
+            if (s.read) cudaEventDestroy(s.read);
+        }
+        if (copy_stream) cudaStreamDestroy(copy_stream);
+        if (res_stream) cudaStreamDestroy(res_stream);
+        if (q_res_dev) cudaFree(q_res_dev);
+        if (q_res) cudaFreeHost(q_res);
         delete map;
         if (d_state) cudaFree(d_state);
         if (d_res) cudaFree(d_res);
@@ -927,7 +1016,7 @@ static int pipeline_push_state(kb_pipeline *p, const SE3 &pose, const SE3 &delta
     s.last_delta = delta;
     s.model_sse = sse;
     s.num_samples = ns;
-    s.pad0 = 0;
+    s.vetoed = 0;
     CK(cudaMemcpyAsync(p->d_state, &s, sizeof(s), cudaMemcpyHostToDevice, p->ex->stream));
     return p->ex->sync();
 }
@@ -940,6 +1029,16 @@ int kb_pipeline_create(const kb_config *cfg, kb_pipeline **out) {
     p->cfg = *cfg;
     RET(map_create_impl(cfg->voxel_size, cfg->max_range, static_cast<unsigned>(cfg->max_points_per_voxel), p->ex, &p->map));
     p->map->borrowed = true;
+    {
+        // size the local map for the sensor: occupied voxels within max_range are surface-like, ~10 pi r^2 for
+        // r = max_range / voxel_size (KITTI: ~300k at 100 m / 1 m), at load factor 1/3; capped at 2^20 slots
+        // (0.66 GB per table at 20 points per voxel) - beyond that the table grows on demand
+        const double r = cfg->max_range / cfg->voxel_size;
+        const double est = std::min(3.0 * 10.0 * 3.14159265358979 * r * r, double(size_t(1) << 20));
+        size_t slots = std::max<size_t>(static_cast<size_t>(est), size_t(1) << 14);
+        if (const char *e = std::getenv("KB_MAP_RESERVE_SLOTS")) slots = static_cast<size_t>(std::atoll(e));  // 0: none
+        if (slots) RET(p->map->reserve(std::min<size_t>(slots, size_t(1) << 31)));
+    }
     CK(cudaMalloc(&p->d_state, sizeof(PipeState)));
     CK(cudaMalloc(&p->d_res, sizeof(FrameResult)));
     CK(cudaHostAlloc(&p->h_res, sizeof(FrameResult), cudaHostAllocDefault));
@@ -964,34 +1063,23 @@ int kb_pipeline_destroy(kb_pipeline *p) {
     return KB_OK;
 }
 
-static int pipeline_run_once(kb_pipeline *p, const double *d_xyz, size_t n, const double *d_ts, size_t n_ts, size_t extra,
-                             bool in_f32);
-
-static int pipeline_run(kb_pipeline *p, const double *d_xyz, size_t n, const double *d_ts, size_t n_ts, bool in_f32 = false) {
-    // expected new voxels: at most one per downsampled point; the 0.5-voxel downsample keeps ~1/9 of a scan, so
-    // size for max(n/4, 2x the last frame's count) and let the kernel veto the frame if that was too optimistic
-    size_t extra = std::max<size_t>(n / 4, 2 * static_cast<size_t>(p->has_last ? p->last.n_ds : 0) + 1024);
-    extra = std::min(extra, n);
-    for (int attempt = 0; attempt < 3; ++attempt) {
-        RET(pipeline_run_once(p, d_xyz, n, d_ts, n_ts, extra, in_f32));
-        if (!(p->last.map_status & ST_NEED_GROW)) return KB_OK;
-        ++p->grow_retries;
-        extra = std::max<size_t>(static_cast<size_t>(p->last.n_ds), extra) + 1;  // exact bound now known
-        p->map->h_counters[C_STATUS] = 0;
-    }
-    return fail(KB_ERR_CUDA, "voxel table could not be grown (internal capacity bug)");
+// expected new voxels: at most one per downsampled point; the 0.5-voxel downsample keeps ~1/9 of a scan, so
+// size for max(n/4, 2x the last frame's count) and let the kernel veto the frame if that was too optimistic
+static size_t pipeline_extra(const kb_pipeline *p, size_t n) {
+    const size_t extra = std::max<size_t>(n / 4, 2 * static_cast<size_t>(p->has_last ? p->last.n_ds : 0) + 1024);
+    return std::min(extra, n);
 }
 
-static int pipeline_run_once(kb_pipeline *p, const double *d_xyz, size_t n, const double *d_ts, size_t n_ts, size_t extra,
-                             bool in_f32) {
+// enqueue one RegisterFrame on the pipeline's stream; the result goes to `res` (device-visible memory)
+static int pipeline_launch(kb_pipeline *p, const double *d_xyz, size_t n, const double *d_ts, size_t n_ts, bool in_f32,
+                           FrameResult *res) {
     Exec &ex = *p->ex;
-    RET(p->map->ensure_capacity(extra));
     FrameParams P;
     P.m = p->map->view();
     P.sc = ex.sc;
     P.ws = p->ws.view();
     P.st = p->d_state;
-    P.res = p->d_res;
+    P.res = res;
     P.in = d_xyz;
     P.ts = d_ts;
     P.n = static_cast<int>(n);
@@ -1006,15 +1094,12 @@ static int pipeline_run_once(kb_pipeline *p, const double *d_xyz, size_t n, cons
     P.use_qcache = 1;
     P.tag_base = ex.next_tag_base();
     P.in_f32 = in_f32 ? 1 : 0;
-    RET(ex.coop(k_register_frame, P, QC_BYTES));
-    CK(cudaMemcpyAsync(p->h_res, p->d_res, sizeof(FrameResult), cudaMemcpyDeviceToHost, ex.stream));
-    RET(ex.sync());
-    if (p->h_res->map_status & ST_NEED_GROW) {  // vetoed: no state was modified; only remember why
-        p->last.map_status = p->h_res->map_status;
-        p->last.n_ds = p->h_res->n_ds;
-        return KB_OK;
-    }
-    p->last = *p->h_res;
+    return ex.coop(k_register_frame, P, QC_BYTES, true);
+}
+
+// take over the result of a frame that ran (not vetoed): host mirror of the counters, history
+static int pipeline_absorb(kb_pipeline *p, const FrameResult &r, size_t n) {
+    p->last = r;
     p->has_last = true;
     p->map->h_counters[C_LIVE] = p->last.map_live;
     p->map->h_counters[C_TOMB] = p->last.map_tomb;
@@ -1041,6 +1126,37 @@ static int pipeline_run_once(kb_pipeline *p, const double *d_xyz, size_t n, cons
     return KB_OK;
 }
 
+// a vetoed frame modified nothing: grow the table for its now known voxel count and let frames run again
+static int pipeline_after_veto(kb_pipeline *p, const FrameResult &r, size_t n) {
+    ++p->grow_retries;
+    p->map->h_counters[C_STATUS] = 0;
+    CK(cudaMemsetAsync(&p->d_state->vetoed, 0, sizeof(int), p->ex->stream));
+    return p->map->ensure_capacity(std::max<size_t>(static_cast<size_t>(r.n_ds), pipeline_extra(p, n)) + 1);
+}
+
+// blocking RegisterFrame on device-resident input
+static int pipeline_run(kb_pipeline *p, const double *d_xyz, size_t n, const double *d_ts, size_t n_ts, bool in_f32 = false) {
+    Exec &ex = *p->ex;
+    RET(p->map->ensure_capacity(pipeline_extra(p, n)));
+    for (int attempt = 0; attempt < 3; ++attempt) {
+        {
+            StallTrace t("blocking: launch");
+            RET(pipeline_launch(p, d_xyz, n, d_ts, n_ts, in_f32, p->d_res));
+        }
+        {
+            StallTrace t("blocking: result D2H enqueue");
+            CK(cudaMemcpyAsync(p->h_res, p->d_res, sizeof(FrameResult), cudaMemcpyDeviceToHost, ex.stream));
+        }
+        {
+            StallTrace t("blocking: stream sync");
+            RET(ex.sync());
+        }
+        if (!(p->h_res->map_status & ST_NEED_GROW)) return pipeline_absorb(p, *p->h_res, n);
+        RET(pipeline_after_veto(p, *p->h_res, n));
+    }
+    return fail(KB_ERR_CUDA, "voxel table could not be grown (internal capacity bug)");
+}
+
 static int pipeline_check(kb_pipeline *p, const void *xyz, size_t n, const void *ts, size_t n_ts, bool *use_ts) {
     if (!p || (!xyz && n) || (!ts && n_ts)) return fail(KB_ERR_INVALID_ARG, "NULL argument");
     if (n >= (size_t(1) << 30)) return fail(KB_ERR_INVALID_ARG, "frame too large");
@@ -1057,8 +1173,11 @@ int kb_pipeline_register_frame(kb_pipeline *p, const double *xyz, size_t n, cons
     Exec &ex = *p->ex;
     CK(cudaSetDevice(ex.device));
     RET(p->ws.ensure(std::max(n, use_ts ? n_timestamps : 0)));
-    if (n) CK(cudaMemcpyAsync(p->ws.in.p, xyz, n * 24, cudaMemcpyHostToDevice, ex.stream));
-    if (use_ts) CK(cudaMemcpyAsync(p->ws.ts.p, timestamps, n_timestamps * 8, cudaMemcpyHostToDevice, ex.stream));
+    {
+        StallTrace t("blocking: H2D enqueue");
+        if (n) CK(cudaMemcpyAsync(p->ws.in.p, xyz, n * 24, cudaMemcpyHostToDevice, ex.stream));
+        if (use_ts) CK(cudaMemcpyAsync(p->ws.ts.p, timestamps, n_timestamps * 8, cudaMemcpyHostToDevice, ex.stream));
+    }
     return pipeline_run(p, p->ws.in.p, n, p->ws.ts.p, use_ts ? n_timestamps : 0);
 }
 int kb_pipeline_register_frame_f32(kb_pipeline *p, const float *xyz, size_t n, const double *timestamps, size_t n_timestamps) {
@@ -1078,6 +1197,158 @@ int kb_pipeline_register_frame_dev(kb_pipeline *p, const double *d_xyz, size_t n
     CK(cudaSetDevice(p->ex->device));
     RET(p->ws.ensure(std::max(n, use_ts ? n_timestamps : 0)));
     return pipeline_run(p, d_xyz, n, d_timestamps, use_ts ? n_timestamps : 0);
+}
+// ---- queued registration of a whole sequence ------------------------------------------------------------------
+static int queue_init(kb_pipeline *p, size_t max_n, bool any_ts, bool device_input) {
+    if (!p->copy_stream) {
+        CK(cudaStreamCreateWithFlags(&p->copy_stream, cudaStreamNonBlocking));
+        for (auto &s : p->q) {
+            CK(cudaEventCreateWithFlags(&s.copied, cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&s.read, cudaEventDisableTiming));
+        }
+        CK(cudaStreamCreateWithFlags(&p->res_stream, cudaStreamNonBlocking));
+        CK(cudaHostAlloc(&p->q_res, sizeof(FrameResult) * kb_pipeline::Q_DEPTH, cudaHostAllocDefault));
+        CK(cudaMalloc(&p->q_res_dev, sizeof(FrameResult) * kb_pipeline::Q_DEPTH));
+    }
+    if (!device_input)
+        for (auto &s : p->q) {
+            RET(s.in.ensure(3 * std::max<size_t>(max_n, 1)));
+            if (any_ts) RET(s.ts.ensure(std::max<size_t>(max_n, 1)));
+        }
+    return KB_OK;
+}
+
+static bool is_pinned(const void *ptr) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, ptr) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost;
+}
+
+// host -> device on the copy stream; pageable sources go through this slot's pinned staging buffer so that the copy
+// is truly asynchronous (the memcpy into it overlaps the frame being registered)
+static int queue_upload(kb_pipeline *p, void *dst, const void *src, size_t bytes, void **pin, size_t *pin_bytes) {
+    if (!bytes) return KB_OK;
+    if (!is_pinned(src)) {
+        if (*pin_bytes < bytes) {
+            if (*pin) cudaFreeHost(*pin);
+            *pin = nullptr;
+            *pin_bytes = 0;
+            CK(cudaHostAlloc(pin, bytes + bytes / 4, cudaHostAllocDefault));
+            *pin_bytes = bytes + bytes / 4;
+        }
+        std::memcpy(*pin, src, bytes);
+        src = *pin;
+    }
+    CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, p->copy_stream));
+    return KB_OK;
+}
+
+int kb_pipeline_register_frames(kb_pipeline *p, const void *const *xyz, const size_t *n, const double *const *timestamps,
+                                const size_t *n_timestamps, size_t count, int layout, double *poses_out) {
+    if (!p || (count && (!xyz || !n))) return fail(KB_ERR_INVALID_ARG, "NULL argument");
+    if (layout != KB_FRAMES_HOST_F64 && layout != KB_FRAMES_HOST_F32 && layout != KB_FRAMES_DEVICE_F64)
+        return fail(KB_ERR_INVALID_ARG, "unknown frame layout %d", layout);
+    constexpr size_t D = kb_pipeline::Q_DEPTH;
+    Exec &ex = *p->ex;
+    CK(cudaSetDevice(ex.device));
+    const bool dev_in = layout == KB_FRAMES_DEVICE_F64, f32 = layout == KB_FRAMES_HOST_F32;
+    // like a loop over RegisterFrame, an invalid frame stops the sequence AFTER the frames before it were registered
+    size_t valid = 0, max_n = 0;
+    bool any_ts = false;
+    int bad_status = KB_OK;
+    std::string bad_msg;
+    std::vector<char> use_ts(count, 0);
+    for (; valid < count; ++valid) {
+        bool u = false;
+        const size_t nt = (timestamps && n_timestamps) ? n_timestamps[valid] : 0;
+        bad_status = pipeline_check(p, xyz[valid], n[valid], (timestamps && nt) ? timestamps[valid] : nullptr, nt, &u);
+        if (bad_status != KB_OK) {
+            bad_msg = tl_err;
+            break;
+        }
+        use_ts[valid] = u;
+        any_ts |= u;
+        max_n = std::max(max_n, std::max(n[valid], u ? nt : size_t(0)));
+    }
+    RET(ex.sync());
+    RET(p->ws.ensure(max_n));
+    RET(queue_init(p, max_n, any_ts, dev_in));
+
+    size_t next_submit = 0, next_absorb = 0;
+    int attempts = 0;
+    while (next_absorb < valid) {
+        const size_t inflight = next_submit - next_absorb;
+        bool submit = next_submit < valid && inflight < D;
+        if (submit && inflight > 0 && p->map->would_grow(pipeline_extra(p, n[next_submit]))) submit = false;  // drain first
+        if (submit) {
+            const size_t k = next_submit, nk = n[k], ntk = use_ts[k] ? n_timestamps[k] : 0;
+            auto &s = p->q[k % D];
+            RET(p->map->ensure_capacity(pipeline_extra(p, nk)));  // rebuilds only with nothing in flight
+            const double *d_xyz, *d_ts = nullptr;
+            if (dev_in) {
+                d_xyz = static_cast<const double *>(xyz[k]);
+                if (ntk) d_ts = timestamps[k];
+            } else {
+                StallTrace t("queue: H2D enqueue");
+                RET(queue_upload(p, s.in.p, xyz[k], nk * (f32 ? 12 : 24), &s.pin_xyz, &s.pin_xyz_bytes));
+                if (ntk) RET(queue_upload(p, s.ts.p, timestamps[k], ntk * 8, &s.pin_ts, &s.pin_ts_bytes));
+                CK(cudaEventRecord(s.copied, p->copy_stream));
+                CK(cudaStreamWaitEvent(ex.stream, s.copied, 0));
+                d_xyz = s.in.p;
+                d_ts = s.ts.p;
+            }
+            {
+                StallTrace t("queue: launch");
+                RET(pipeline_launch(p, d_xyz, nk, d_ts, ntk, f32, p->q_res_dev + k % D));
+                CK(cudaEventRecord(s.done, ex.stream));
+                // result read-back on its own stream: neither the next kernel nor the next H2D waits for it (letting
+                // the kernel write to mapped host memory instead was measured ~1% slower)
+                CK(cudaStreamWaitEvent(p->res_stream, s.done, 0));
+                CK(cudaMemcpyAsync(p->q_res + k % D, p->q_res_dev + k % D, sizeof(FrameResult), cudaMemcpyDeviceToHost,
+                                   p->res_stream));
+                CK(cudaEventRecord(s.read, p->res_stream));
+            }
+            ++next_submit;
+            continue;
+        }
+        const size_t k = next_absorb;
+        {
+            StallTrace t("queue: wait for oldest frame");
+            CK(cudaEventSynchronize(p->q[k % D].read));  // also frees this slot's buffers for frame k + D
+        }
+        const FrameResult r = p->q_res[k % D];
+        if (r.map_status & ST_NEED_GROW) {  // frames queued behind it were skipped on the device: replay from k
+            if (++attempts >= 3) return fail(KB_ERR_CUDA, "voxel table could not be grown (internal capacity bug)");
+            RET(ex.sync());
+            CK(cudaStreamSynchronize(p->res_stream));
+            RET(pipeline_after_veto(p, r, n[k]));
+            next_submit = k;
+            continue;
+        }
+        attempts = 0;
+        const int st = pipeline_absorb(p, r, n[k]);
+        if (st != KB_OK) {
+            ex.sync();
+            return st;
+        }
+        if (poses_out) std::memcpy(poses_out + 16 * k, r.pose, sizeof(double) * 16);
+        ++next_absorb;
+    }
+    if (bad_status != KB_OK) {
+        tl_err = bad_msg;
+        return bad_status;
+    }
+    return KB_OK;
+}
+
+int kb_pipeline_grow_retries(const kb_pipeline *p, unsigned long long *out) {
+    if (!p || !out) return fail(KB_ERR_INVALID_ARG, "NULL argument");
+    *out = p->grow_retries;
+    return KB_OK;
 }
 int kb_pipeline_last_cloud_sizes(const kb_pipeline *p, size_t *n_preprocessed, size_t *n_source) {
     if (!p) return fail(KB_ERR_INVALID_ARG, "p == NULL");

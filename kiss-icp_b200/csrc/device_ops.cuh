@@ -39,7 +39,7 @@ constexpr int ICP_REC = 32;
 constexpr int LL_RES = 16;        // est(7) + done flag, final pose(7), spare      // est(7) t_icp(7) final(7) conv cand_total query_total ...
 
 enum Counter { C_LIVE = 0, C_TOMB = 1, C_POINTS = 2, C_STATUS = 3, C_TOUCHED = 4, C_NCOUNTERS = 8 };
-enum StatusBit { ST_TABLE_FULL = 1, ST_NEED_GROW = 2 };
+enum StatusBit { ST_TABLE_FULL = 1, ST_NEED_GROW = 2, ST_SKIPPED = 4 };
 
 // core/VoxelUtils.hpp:33-37 — FP64 DIVISION then floor then int cast (bit-exact with the CPU).
 // A DDIV costs ~131 cycles on B200; when voxel_size is an exact power of two (1.0, 0.5, 2.0 ...:
@@ -77,7 +77,7 @@ struct MapView {
 
 // cross-CTA scratch, sized by the grid
 struct Scratch {
-    unsigned *bar;  // [0] grid barrier counter, [BAR_ARRIVE] ICP arrivals, [BAR_EPOCH] ICP publish epoch: one 128-B
+    unsigned *bar;  // [0] grid barrier counter, [BAR_ARRIVE] CTAs that left the kernel (Grid::finish), [BAR_EPOCH] spare: one 128-B
                     // line each (arrival atomics must not fight the epoch pollers); zeroed before each launch
     double *blk_d;  // [2][NPART][grid] doubles (ping-pong by ICP iteration parity; value-major so the reduce is coalesced)
     double *icp_rec;  // (unused by the tagged protocol; kept for the debug tools)
@@ -157,6 +157,14 @@ struct Grid {
             __threadfence();  // acquire side; a gpu-scope fence also drops this SM's L1 lines (plain loads follow)
         }
         __syncthreads();
+    }
+    // every CTA, once, after its last sync(): the last one to leave re-arms the barrier for the next launch, which
+    // saves the host a memset node in front of every launch (kernels launched with Exec::coop(..., self_reset))
+    __device__ __forceinline__ void finish() {
+        if (threadIdx.x == 0 && atomicAdd(bar + BAR_ARRIVE, 1u) == gridDim.x - 1) {
+            atomicExch(bar + BAR_ARRIVE, 0u);
+            atomicExch(bar, 0u);
+        }
     }
 };
 

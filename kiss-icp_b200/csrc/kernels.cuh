@@ -12,7 +12,8 @@ struct PipeState {
     SE3 last_delta;
     double model_sse;  // AdaptiveThreshold::model_sse_   Threshold.hpp:45
     int num_samples;   // AdaptiveThreshold::num_samples_ Threshold.hpp:46
-    int pad0;
+    int vetoed;        // set by a frame that found the voxel table too small: frames already queued behind it
+                       // must not run on the stale state, they return ST_SKIPPED until the host has grown the table
 };
 
 // what the host reads back after every RegisterFrame (one small D2H)
@@ -93,6 +94,11 @@ __global__ void __launch_bounds__(BLOCK, 1) k_register_frame(const FrameParams P
     const SE3 last_delta = P.st->last_delta;
     const double model_sse = P.st->model_sse;
     const int num_samples = P.st->num_samples;
+    if (P.st->vetoed) {  // written only by an EARLIER launch: uniform across the grid
+        if (blockIdx.x == 0 && threadIdx.x == 0) P.res->map_status = ST_SKIPPED;
+        g.finish();
+        return;
+    }
 
     // the downsample scratch tables of both passes are cleared here, under the preprocess barriers
     ds_clear(P.ws.ds, P.n);
@@ -118,7 +124,9 @@ __global__ void __launch_bounds__(BLOCK, 1) k_register_frame(const FrameParams P
             if (blockIdx.x == 0 && threadIdx.x == 0) {
                 P.res->map_status = ST_NEED_GROW;
                 P.res->n_ds = n_ds;
+                P.st->vetoed = 1;  // every CTA read it before the first grid barrier
             }
+            g.finish();
             return;  // uniform across the grid
         }
     }
@@ -182,6 +190,7 @@ __global__ void __launch_bounds__(BLOCK, 1) k_register_frame(const FrameParams P
         r->map_status = P.m.counters[C_STATUS];
         if (P.sc.profile) r->t_ns[6] = globaltimer_ns();
     }
+    g.finish();
 }
 
 // ---- stand-alone wrappers (module-level API) -------------------------------------------------

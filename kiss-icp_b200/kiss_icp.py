@@ -132,6 +132,12 @@ class KissICP:
         """in-kernel phase timestamps (last_profile_us, history phase_us): off by default, ~10 us/scan when on"""
         N.check(N.lib().kb_pipeline_set_profiling(self._h, int(bool(enabled))))
 
+    def grow_retries(self) -> int:
+        """frames the kernel vetoed because the voxel table was sized too optimistically (grown + replayed)"""
+        v = C.c_ulonglong(0)
+        N.check(N.lib().kb_pipeline_grow_retries(self._h, C.byref(v)))
+        return int(v.value)
+
     def start_history(self, capacity: int):
         """log per-frame statistics of the next ``capacity`` fused RegisterFrame calls (host side)"""
         N.check(N.lib().kb_pipeline_set_history(self._h, int(capacity)))
@@ -168,6 +174,42 @@ class KissICP:
         src = np.empty((b.value, 3))
         N.check(N.lib().kb_pipeline_last_clouds(self._h, N.ptr(pre), a.value, N.ptr(src), b.value))
         return pre, src
+
+    def register_frames(self, frames, timestamps=None):
+        """Register a whole sequence (the dataset loop of python/kiss_icp/pipeline.py:106-112) -> poses (K,4,4).
+
+        Same results as K ``register_frame`` calls; the frames are queued on the device (copy of frame k+1
+        overlaps the registration of frame k, results are read behind the queue). ``frames`` is a sequence of
+        (N_k,3) arrays, all float64 or all float32; ``timestamps`` a matching sequence (or None)."""
+        K = len(frames)
+        if timestamps is None:
+            timestamps = [np.empty(0)] * K
+        if len(timestamps) != K:
+            raise ValueError("frames and timestamps differ in length")
+        if not self.fused:
+            poses = np.empty((K, 4, 4))
+            for k in range(K):
+                self._register_frame_modular(frames[k], timestamps[k])
+                poses[k] = self._last_pose
+            return poses
+        arrs = [np.asarray(f) for f in frames]
+        f32 = K > 0 and all(a.dtype == np.float32 and a.ndim == 2 and a.shape[1] == 3 for a in arrs)
+        pts = [np.ascontiguousarray(a) for a in arrs] if f32 else [N.points_arg(a) for a in arrs]
+        ts = [np.ascontiguousarray(np.asarray(t).ravel(), dtype=np.float64) for t in timestamps]
+        return self._register_frames_raw([N.ptr(a) for a in pts], [len(a) for a in pts], [N.ptr(t) for t in ts],
+                                         [len(t) for t in ts], 1 if f32 else 0)
+
+    def _register_frames_raw(self, xyz_ptrs, sizes, ts_ptrs, ts_sizes, layout):
+        """raw-pointer form (host or device addresses): layout 0 host f64, 1 host f32, 2 device f64"""
+        K = len(xyz_ptrs)
+        as_vp = lambda v: v if isinstance(v, C.c_void_p) else C.c_void_p(int(v) if v else None)
+        X = (C.c_void_p * K)(*[as_vp(v) for v in xyz_ptrs])
+        T = (C.c_void_p * K)(*[as_vp(v) for v in ts_ptrs])
+        n = (N.sz * K)(*sizes)
+        nt = (N.sz * K)(*ts_sizes)
+        poses = np.empty((K, 4, 4))
+        N.check(N.lib().kb_pipeline_register_frames(self._h, X, n, T, nt, K, int(layout), N.ptr(poses)))
+        return poses
 
     def _register_frame_modular(self, frame, timestamps):
         # python/kiss_icp/kiss_icp.py:43-75, line for line, on the per-module device API

@@ -374,9 +374,11 @@ def test_map_compact_keeps_content(K, O):
     assert np.array_equal(ap, bp) and np.array_equal(ad, bd)
 
 
-def test_pipeline_long_stream_with_table_rebuilds(K, O):
-    """300 free-running scans: eviction tombstones accumulate and the voxel table is rebuilt several times"""
+def test_pipeline_long_stream_with_table_rebuilds(K, O, monkeypatch):
+    """300 free-running scans: eviction tombstones accumulate and the voxel table is rebuilt several times
+    (growth into fresh allocations first, then same-size rebuilds that ping-pong with the spare table)"""
     from kiss_icp_b200 import synthetic
+    monkeypatch.setenv("KB_MAP_RESERVE_SLOTS", "0")  # start from the minimal table instead of the sensor-sized one
     L = synthetic.small_shape(seed=21, beams=32, cols=512)
     g, o = K.KissICP(K.load_config(max_range=40.0)), O.KissICP(max_range=40.0, voxel_size=0.4)
     worst = 0.0
@@ -394,9 +396,10 @@ def test_pipeline_long_stream_with_table_rebuilds(K, O):
     assert np.array_equal(gv, ov) and np.array_equal(gc, oc) and np.allclose(gp, op, atol=1e-9)
 
 
-def test_pipeline_capacity_veto_and_retry(K, O):
+def test_pipeline_capacity_veto_and_retry(K, O, monkeypatch):
     """frames whose downsampled size exceeds the optimistic table sizing (every point its own voxel): the kernel
     vetoes the frame before touching any state, the host grows the table and replays it"""
+    monkeypatch.setenv("KB_MAP_RESERVE_SLOTS", "0")  # start from the minimal table instead of the sensor-sized one
     g, o = K.KissICP(K.load_config(max_range=300.0, voxel_size=1.0)), O.KissICP(max_range=300.0, voxel_size=1.0)
     for k in range(4):
         pts = rng.uniform(-150, 150, size=(30000, 3)) * [1.0, 1.0, 0.2]
@@ -405,6 +408,7 @@ def test_pipeline_capacity_veto_and_retry(K, O):
         dt, dr = pose_error(g.last_pose, o.pose)
         assert dt < 1e-6 and dr < 1e-6
         assert g.local_map.num_points() == o.local_map.num_points()
+    assert g.grow_retries() >= 1
 
 
 def test_pipeline_float32_ingestion_equals_float64(K):
@@ -445,3 +449,72 @@ def test_pipeline_work_counters_and_profiling(K):
     assert all(sum(st.phase_us) == 0 for st in h[:3])          # timestamps are off by default
     assert all(10 < sum(st.phase_us) < 1e5 for st in h[3:])    # and plausible when switched on
     assert np.allclose(np.array(h[-1].pose).reshape(4, 4), icp.last_pose)
+
+
+def test_register_frames_queue_equals_blocking_calls(K):
+    """kb_pipeline_register_frames (queued, copy/compute overlapped) == the same frames through blocking
+    RegisterFrame calls: poses bit-identical, same map, same history; f64 and f32 layouts, with and without stamps"""
+    from kiss_icp_b200 import synthetic
+    for stamps, f32 in (("column", False), ("none", False), ("column", True)):
+        L = synthetic.small_shape(seed=5, beams=32, cols=512, stamps=stamps)
+        scans = [L.scan(k) for k in range(25)]
+        frames = [p.astype(np.float32) if f32 else p for p, _ in scans]
+        ts = [t for _, t in scans]
+        a, b = K.KissICP(K.load_config()), K.KissICP(K.load_config())
+        a.start_history(25)
+        b.start_history(25)
+        want = np.empty((25, 4, 4))
+        for k in range(25):
+            a.register_frame(frames[k], ts[k], return_clouds=False)
+            want[k] = a.last_pose
+        got = np.concatenate([b.register_frames(frames[:7], ts[:7]), b.register_frames(frames[7:8], ts[7:8]),
+                              b.register_frames(frames[8:], ts[8:])])
+        assert np.array_equal(got, want)
+        assert np.array_equal(b.last_pose, a.last_pose) and np.array_equal(b.last_delta, a.last_delta)
+        for x, y in zip(a.local_map.dump(), b.local_map.dump()):
+            assert np.array_equal(x, y)
+        ha, hb = a.history(), b.history()
+        assert [(h.iterations, h.n_source, h.map_points, h.icp_candidates) for h in ha] == \
+               [(h.iterations, h.n_source, h.map_points, h.icp_candidates) for h in hb]
+        # blocking calls continue seamlessly after a queued batch
+        p, t = L.scan(25)
+        a.register_frame(p.astype(np.float32) if f32 else p, t, return_clouds=False)
+        b.register_frame(p.astype(np.float32) if f32 else p, t, return_clouds=False)
+        assert np.array_equal(b.last_pose, a.last_pose)
+    assert len(b.register_frames([], [])) == 0
+
+
+def test_register_frames_veto_inside_the_queue(K, O, monkeypatch):
+    """a frame in the middle of a queued sequence needs a bigger voxel table than planned: it vetoes itself, the
+    frames queued behind it are skipped on the device, the host grows the table and replays from that frame"""
+    monkeypatch.setenv("KB_MAP_RESERVE_SLOTS", "0")  # start from the minimal table instead of the sensor-sized one
+    g, o = K.KissICP(K.load_config(max_range=300.0, voxel_size=1.0)), O.KissICP(max_range=300.0, voxel_size=1.0)
+    frames = []
+    for k in range(9):
+        n = 30000 if k in (0, 4, 5) else 3000   # sparse clouds: every point its own voxel
+        frames.append(rng.uniform(-150, 150, size=(n, 3)) * [1.0, 1.0, 0.2])
+    poses = g.register_frames(frames)
+    assert g.grow_retries() >= 2   # frame 0 (empty table) and the mid-queue one
+    for k, f in enumerate(frames):
+        o.register_frame(f, np.empty(0), want_clouds=False)
+        dt, dr = pose_error(poses[k], o.pose)
+        assert dt < 1e-6 and dr < 1e-6, (k, dt, dr)
+    assert g.local_map.num_points() == o.local_map.num_points() and g.local_map.num_voxels() == o.local_map.num_voxels()
+
+
+def test_register_frames_error_stops_the_sequence_where_the_loop_would(K):
+    """frame 3 has too few timestamps (std::out_of_range in the reference): frames 0-2 are registered, then the
+    error is raised, exactly like the dataset loop"""
+    from kiss_icp_b200 import synthetic
+    L = synthetic.small_shape(seed=6, beams=32, cols=512, stamps="column")
+    scans = [L.scan(k) for k in range(5)]
+    a, b = K.KissICP(K.load_config()), K.KissICP(K.load_config())
+    for p, t in scans[:3]:
+        a.register_frame(p, t, return_clouds=False)
+    frames = [p for p, _ in scans]
+    ts = [t for _, t in scans]
+    ts[3] = ts[3][:10]
+    with pytest.raises(IndexError):
+        b.register_frames(frames, ts)
+    assert np.array_equal(a.last_pose, b.last_pose)
+    assert a.local_map.num_points() == b.local_map.num_points()
