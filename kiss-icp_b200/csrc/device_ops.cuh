@@ -1449,16 +1449,52 @@ __device__ __noinline__ void op_map_remove_far(const MapView &m_in, const V3 &or
     const V3 origin = origin_in;
     const double max_d2 = m.max_distance * m.max_distance;
     const size_t cap3 = static_cast<size_t>(m.cap) * 3;
-    for (unsigned s = blockIdx.x * BLOCK + threadIdx.x; s <= m.mask; s += gridDim.x * BLOCK) {
-        const int w = m.slots[s].w;
-        if (w < 0) continue;
-        const double *vp = m.points + s * cap3;
-        const V3 pt{vp[0], vp[1], vp[2]};
-        if (sqnorm(pt - origin) >= max_d2) {  // tests only voxel_points.front()  (:125-126)
-            m.slots[s].w = KB_TOMB;
-            atomicSub(&m.counters[C_LIVE], 1);
-            atomicAdd(&m.counters[C_TOMB], 1);
-            atomicSub(&m.counters[C_POINTS], w);
+    // The test is on voxel_points.front() (:125-126), which lives in the sparse point blocks (one 32-B sector per
+    // voxel). That point lies inside its voxel, so the slot's key alone decides all voxels except the one-voxel
+    // shell around the sphere: box corners farthest from / nearest to the origin bound the distance. The box is
+    // widened by 1e-6 voxels so that rounding in PointToVoxel's division can never put the point outside it.
+    const double v = m.voxel_size, slack = 1e-6 * v;
+    const unsigned stride = gridDim.x * BLOCK;
+    for (unsigned s0 = blockIdx.x * BLOCK + threadIdx.x; s0 <= m.mask; s0 += 2 * stride) {
+        int4 key[2];
+        bool in[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {  // two independent slot loads in flight per thread
+            const unsigned s = s0 + u * stride;
+            in[u] = s <= m.mask;
+            key[u] = in[u] ? m.slots[s] : make_int4(0, 0, 0, -1);
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int w = key[u].w;
+            if (!in[u] || w < 0) continue;
+            const unsigned s = s0 + u * stride;
+            const double lo[3] = {key[u].x * v - slack - origin.x, key[u].y * v - slack - origin.y, key[u].z * v - slack - origin.z};
+            double far2 = 0.0, near2 = 0.0;
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                const double hi = lo[a] + v + 2.0 * slack;
+                const double f = fmax(fabs(lo[a]), fabs(hi));
+                const double n = (lo[a] > 0.0) ? lo[a] : ((hi < 0.0) ? -hi : 0.0);
+                far2 += f * f;
+                near2 += n * n;
+            }
+            bool remove;
+            if (far2 < max_d2) {
+                continue;  // the whole voxel is inside the sphere
+            } else if (near2 >= max_d2) {
+                remove = true;  // the whole voxel is outside
+            } else {
+                const double *vp = m.points + s * cap3;
+                const V3 pt{vp[0], vp[1], vp[2]};
+                remove = sqnorm(pt - origin) >= max_d2;
+            }
+            if (remove) {
+                m.slots[s].w = KB_TOMB;
+                atomicSub(&m.counters[C_LIVE], 1);
+                atomicAdd(&m.counters[C_TOMB], 1);
+                atomicSub(&m.counters[C_POINTS], w);
+            }
         }
     }
 }
