@@ -149,6 +149,13 @@ int kb_threshold_update_model_deviation(kb_threshold *th, const double model_dev
 int kb_voxel_down_sample(const double *xyz, size_t n, double voxel_size, double *out_xyz, size_t capacity,
                          size_t *n_out);
 
+/* ---- `_correct_kitti_scan(frame)` (python/kiss_icp/pybind/kiss_icp_pybind.cpp:127-138) ---- */
+/* The KITTI loader's per-point intrinsic correction (datasets/kitti.py:44-48,68): every point is rotated by
+ * 0.205 deg about normalized(pt x e_z). out_xyz may alias xyz. The _dev form works on device buffers and is
+ * asynchronous on the calling thread's stream (kb_set_stream), so it chains into kb_pipeline_register_frame_dev. */
+int kb_correct_kitti_scan(const double *xyz, size_t n, double *out_xyz);
+int kb_correct_kitti_scan_dev(const double *d_xyz, size_t n, double *d_out_xyz);
+
 /* ---- kiss_icp::pipeline::KissICP (cpp/kiss_icp/pipeline/KissICP.hpp:36-96) -------------- */
 /* KISSConfig KissICP.hpp:36-54, field for field */
 typedef struct kb_config {

@@ -119,6 +119,8 @@ SIGNATURES = {
     "kb_threshold_compute": (i32, [vp, C.POINTER(dbl)]),
     "kb_threshold_update_model_deviation": (i32, [vp, vp]),
     "kb_voxel_down_sample": (i32, [vp, sz, dbl, vp, sz, C.POINTER(sz)]),
+    "kb_correct_kitti_scan": (i32, [vp, sz, vp]),
+    "kb_correct_kitti_scan_dev": (i32, [vp, sz, vp]),
     "kb_config_default": (None, [C.POINTER(Config)]),
     "kb_pipeline_create": (i32, [C.POINTER(Config), C.POINTER(vp)]),
     "kb_pipeline_destroy": (i32, [vp]),

@@ -6,6 +6,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -993,6 +994,39 @@ int kb_voxel_down_sample(const double *xyz, size_t n, double voxel_size, double 
     if (capacity < static_cast<size_t>(m)) return fail(KB_ERR_CAPACITY, "output buffer too small");
     if (m) CK(cudaMemcpyAsync(out_xyz, c->ws.ds1.p, static_cast<size_t>(m) * 24, cudaMemcpyDeviceToHost, ex.stream));
     return ex.sync();
+}
+
+static int correct_kitti_launch(Exec &ex, const double *d_in, double *d_out, size_t n) {
+    if (!n) return KB_OK;
+    const double angle = (0.205 * M_PI) / 180.0;  // VERTICAL_ANGLE_OFFSET, kiss_icp_pybind.cpp:130
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ex.device);
+    const unsigned blocks = static_cast<unsigned>(std::min<size_t>((n + 255) / 256, static_cast<size_t>(sms) * 8));
+    k_correct_kitti<<<blocks, 256, 0, ex.stream>>>(d_in, d_out, n, std::sin(angle), std::cos(angle));
+    ++ex.launches;
+    CK(cudaGetLastError());
+    return KB_OK;
+}
+int kb_correct_kitti_scan(const double *xyz, size_t n, double *out_xyz) {
+    if (n && (!xyz || !out_xyz)) return fail(KB_ERR_INVALID_ARG, "NULL argument");
+    if (n >= (size_t(1) << 30)) return fail(KB_ERR_INVALID_ARG, "frame too large");
+    DefaultCtx *c;
+    RET(default_ctx(&c));
+    Exec &ex = *c->ex;
+    CK(cudaSetDevice(ex.device));
+    RET(c->ws.in.ensure(3 * std::max<size_t>(n, 1)));
+    RET(c->ws.tmp.ensure(3 * std::max<size_t>(n, 1)));
+    if (n) CK(cudaMemcpyAsync(c->ws.in.p, xyz, n * 24, cudaMemcpyHostToDevice, ex.stream));
+    RET(correct_kitti_launch(ex, c->ws.in.p, c->ws.tmp.p, n));
+    if (n) CK(cudaMemcpyAsync(out_xyz, c->ws.tmp.p, n * 24, cudaMemcpyDeviceToHost, ex.stream));
+    return ex.sync();
+}
+int kb_correct_kitti_scan_dev(const double *d_xyz, size_t n, double *d_out_xyz) {
+    if (n && (!d_xyz || !d_out_xyz)) return fail(KB_ERR_INVALID_ARG, "NULL argument");
+    DefaultCtx *c;
+    RET(default_ctx(&c));
+    CK(cudaSetDevice(c->ex->device));
+    return correct_kitti_launch(*c->ex, d_xyz, d_out_xyz, n);  // asynchronous on the calling thread's stream
 }
 
 // ------------------------------------------------------------------------------- KissICP pipeline

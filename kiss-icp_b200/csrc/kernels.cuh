@@ -193,6 +193,17 @@ __global__ void __launch_bounds__(BLOCK, 1) k_register_frame(const FrameParams P
     g.finish();
 }
 
+// ---- _correct_kitti_scan (kiss_icp_pybind.cpp:127-138): one point per thread, 24 B in + 24 B out, HBM-bound ----
+__global__ void __launch_bounds__(256) k_correct_kitti(const double *in, double *out, size_t n, double sn, double cs) {
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const V3 p = correct_kitti_point(V3{in[3 * i], in[3 * i + 1], in[3 * i + 2]}, sn, cs);
+        out[3 * i] = p.x;
+        out[3 * i + 1] = p.y;
+        out[3 * i + 2] = p.z;
+    }
+}
+
 // ---- stand-alone wrappers (module-level API) -------------------------------------------------
 struct PreParams {
     Scratch sc;

@@ -30,6 +30,29 @@ KB_HD V3 cross(const V3 &a, const V3 &b) {
 KB_HD double sqnorm(const V3 &a) { return (a.x * a.x + a.y * a.y) + a.z * a.z; }
 KB_HD double norm(const V3 &a) { return sqrt(sqnorm(a)); }
 
+// _correct_kitti_scan for one point (kiss_icp_pybind.cpp:127-138): rotate by the fixed angle about
+// normalized(pt x e_z), evaluated like Eigen's AngleAxisd::toRotationMatrix() * pt; sn, cs = sin / cos of the angle
+KB_HD V3 correct_kitti_point(const V3 &pt, double sn, double cs) {
+    V3 ax = cross(pt, V3{0.0, 0.0, 1.0});
+    const double z = sqnorm(ax);
+    if (z > 0.0) {
+        const double n = sqrt(z);
+        ax = V3{ax.x / n, ax.y / n, ax.z / n};
+    }
+    const V3 sa{sn * ax.x, sn * ax.y, sn * ax.z};
+    const double c1 = 1.0 - cs;
+    const V3 ca{c1 * ax.x, c1 * ax.y, c1 * ax.z};
+    double t = ca.x * ax.y;
+    const double r01 = t - sa.z, r10 = t + sa.z;
+    t = ca.x * ax.z;
+    const double r02 = t + sa.y, r20 = t - sa.y;
+    t = ca.y * ax.z;
+    const double r12 = t - sa.x, r21 = t + sa.x;
+    const double r00 = ca.x * ax.x + cs, r11 = ca.y * ax.y + cs, r22 = ca.z * ax.z + cs;
+    return V3{(r00 * pt.x + r01 * pt.y) + r02 * pt.z, (r10 * pt.x + r11 * pt.y) + r12 * pt.z,
+              (r20 * pt.x + r21 * pt.y) + r22 * pt.z};
+}
+
 struct Q4 {
     double x, y, z, w;
 };

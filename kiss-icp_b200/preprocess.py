@@ -39,3 +39,12 @@ class Preprocessor:
         N.check(N.lib().kb_preprocessor_preprocess(self._h, N.ptr(pts), len(pts), N.ptr(ts), len(ts), N.ptr(T),
                                                    N.ptr(out), len(pts), C.byref(n)))
         return out[: n.value]
+
+
+def correct_kitti_scan(frame: np.ndarray) -> np.ndarray:
+    """`kiss_icp_pybind._correct_kitti_scan` (kiss_icp_pybind.cpp:127-138; used by datasets/kitti.py:44-48,68):
+    the KITTI-only intrinsic correction, every point rotated by 0.205 deg about normalized(pt x e_z)."""
+    pts = N.points_arg(frame)
+    out = np.empty_like(pts)
+    N.check(N.lib().kb_correct_kitti_scan(N.ptr(pts), len(pts), N.ptr(out)))
+    return out

@@ -233,6 +233,13 @@ def preprocess(pts, timestamps, motion, max_range, min_range, deskew):
     return out[:n].copy()
 
 
+def correct_kitti_scan(pts):
+    pts = _pts(pts)
+    out = np.empty_like(pts)
+    lib().oracle_correct_kitti_scan(_p(pts), C.c_long(len(pts)), _p(out))
+    return out
+
+
 def threshold_update(model_sse, num_samples, deviation, min_motion_th, max_range):
     sse = C.c_double(model_sse)
     ns = C.c_int(num_samples)

@@ -190,6 +190,8 @@ long oracle_preprocess(const double *xyz, long n, const double *timestamps, long
     return static_cast<long>(r.size());
 }
 
+void oracle_correct_kitti_scan(const double *xyz, long n, double *out) { from_points(CorrectKITTIScan(to_points(xyz, n)), out); }
+
 // ---------------------------------------------------------------- AdaptiveThreshold
 int oracle_threshold_update(double *model_sse, int *num_samples, const double deviation[16], double min_motion_th,
                             double max_range) {

@@ -314,6 +314,46 @@ struct Preprocessor {
     int max_num_threads_;
 };
 
+// _correct_kitti_scan, python/kiss_icp/pybind/kiss_icp_pybind.cpp:127-138 (the lambda the KITTI loader applies before
+// RegisterFrame, datasets/kitti.py:44-48,68). Eigen 3.4 semantics restated: Vector3d::normalized() divides by
+// sqrt(squaredNorm) when squaredNorm > 0 and returns the vector unchanged otherwise; AngleAxisd * v =
+// toRotationMatrix() * v with Eigen's Rodrigues form (Geometry/AngleAxis.h, toRotationMatrix).
+inline Mat3 AngleAxisToRotationMatrix(double angle, const Vec3 &axis) {
+    Mat3 res;
+    const Vec3 sin_axis = std::sin(angle) * axis;
+    const double c = std::cos(angle);
+    const Vec3 cos1_axis = (1.0 - c) * axis;
+    double tmp;
+    tmp = cos1_axis.x * axis.y;
+    res.m[0][1] = tmp - sin_axis.z;
+    res.m[1][0] = tmp + sin_axis.z;
+    tmp = cos1_axis.x * axis.z;
+    res.m[0][2] = tmp + sin_axis.y;
+    res.m[2][0] = tmp - sin_axis.y;
+    tmp = cos1_axis.y * axis.z;
+    res.m[1][2] = tmp - sin_axis.x;
+    res.m[2][1] = tmp + sin_axis.x;
+    res.m[0][0] = cos1_axis.x * axis.x + c;
+    res.m[1][1] = cos1_axis.y * axis.y + c;
+    res.m[2][2] = cos1_axis.z * axis.z + c;
+    return res;
+}
+inline Points CorrectKITTIScan(const Points &frame) {
+    const double VERTICAL_ANGLE_OFFSET = (0.205 * M_PI) / 180.0;
+    Points out(frame.size());
+    for (size_t i = 0; i < frame.size(); ++i) {
+        const Vec3 &pt = frame[i];
+        Vec3 rotationVector = cross(pt, Vec3{0., 0., 1.});
+        const double z = squaredNorm(rotationVector);
+        if (z > 0.0) {
+            const double nrm = std::sqrt(z);
+            rotationVector = Vec3{rotationVector.x / nrm, rotationVector.y / nrm, rotationVector.z / nrm};
+        }
+        out[i] = matvec(AngleAxisToRotationMatrix(VERTICAL_ANGLE_OFFSET, rotationVector), pt);
+    }
+    return out;
+}
+
 // core/Threshold.hpp:29-47, core/Threshold.cpp:30-49
 struct AdaptiveThreshold {
     AdaptiveThreshold(double initial_threshold, double min_motion_threshold, double max_range)

@@ -518,3 +518,33 @@ def test_register_frames_error_stops_the_sequence_where_the_loop_would(K):
         b.register_frames(frames, ts)
     assert np.array_equal(a.last_pose, b.last_pose)
     assert a.local_map.num_points() == b.local_map.num_points()
+
+
+def test_correct_kitti_scan_matches_oracle(K, O):
+    """kb_correct_kitti_scan[_dev] vs the oracle and the frozen vectors (float work: a few ulps allowed, the
+    operation order is Eigen's so the expected difference is zero), then chained on the device into RegisterFrame"""
+    import ctypes as C
+    import os
+    import torch
+    from kiss_icp_b200 import _native as N, synthetic
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_kitti_v1.npz"))
+    got = K.correct_kitti_scan(g["pts"])
+    assert np.abs(got - g["corrected"]).max() <= 4e-14 * np.abs(g["pts"]).max()
+    for n in (0, 1, 100_003):
+        pts = rng.normal(size=(n, 3)) * [40.0, 40.0, 3.0]
+        a, b = K.correct_kitti_scan(pts), O.correct_kitti_scan(pts)
+        assert a.shape == b.shape and (n == 0 or np.abs(a - b).max() <= 4e-14 * 200.0)
+    # device form: correct two scans on the device and register them without a host round trip
+    L = synthetic.small_shape(seed=9, beams=32, cols=512)
+    a, b = K.KissICP(K.load_config()), K.KissICP(K.load_config())
+    for k in range(3):
+        p, t = L.scan(k)
+        a.register_frame(K.correct_kitti_scan(p), np.empty(0), return_clouds=False)
+        d_in = torch.from_numpy(p).cuda()
+        d_out = torch.empty_like(d_in)
+        torch.cuda.synchronize()
+        N.check(N.lib().kb_correct_kitti_scan_dev(C.c_void_p(d_in.data_ptr()), len(p), C.c_void_p(d_out.data_ptr())))
+        torch.cuda.synchronize()  # the correction ran on the library's default stream of this thread
+        assert np.array_equal(d_out.cpu().numpy(), K.correct_kitti_scan(p))
+        N.check(N.lib().kb_pipeline_register_frame_dev(b._h, C.c_void_p(d_out.data_ptr()), len(p), None, 0))
+        assert np.array_equal(a.last_pose, b.last_pose)

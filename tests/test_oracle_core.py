@@ -258,3 +258,26 @@ def test_config1_known_answer(O, golden):
     # and the multi-threaded CPU path (summation order differs) stays within the parity budget
     pose8, _ = O.align_points_to_map(m, golden["c1_src"], golden["c1_guess"], 3.0, 1.0, nthreads=8)
     assert np.allclose(pose8, pose, atol=1e-9)
+
+
+def test_correct_kitti_scan_is_a_rotation_about_pt_cross_z(O):
+    """_correct_kitti_scan (kiss_icp_pybind.cpp:127-138) against scipy's rotation-vector form; the elevation of
+    every point changes by exactly the 0.205 deg offset, ranges are preserved"""
+    import os
+    from scipy.spatial.transform import Rotation as R
+    pts = rng.normal(size=(2000, 3)) * [30.0, 30.0, 2.0]
+    got = O.correct_kitti_scan(pts)
+    ax = np.cross(pts, [0.0, 0.0, 1.0])
+    ax /= np.linalg.norm(ax, axis=1, keepdims=True)
+    ang = 0.205 * np.pi / 180.0
+    assert np.abs(got - R.from_rotvec(ax * ang).apply(pts)).max() < 1e-12
+    assert np.abs(np.linalg.norm(got, axis=1) - np.linalg.norm(pts, axis=1)).max() < 1e-12
+    elev = lambda p: np.arctan2(p[:, 2], np.hypot(p[:, 0], p[:, 1]))
+    assert np.abs((elev(got) - elev(pts)) - ang).max() < 1e-12
+    # degenerate axis (pt on the z axis or at the origin): Eigen's normalized() leaves the zero vector alone and
+    # the Rodrigues matrix collapses to cos(angle) * I
+    deg = O.correct_kitti_scan(np.array([[0.0, 0.0, 7.5], [0.0, 0.0, 0.0]]))
+    assert np.allclose(deg, [[0.0, 0.0, 7.5 * np.cos(ang)], [0.0, 0.0, 0.0]], rtol=0, atol=1e-15)
+    assert len(O.correct_kitti_scan(np.empty((0, 3)))) == 0
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_kitti_v1.npz"))
+    assert np.array_equal(O.correct_kitti_scan(g["pts"]), g["corrected"])
