@@ -360,6 +360,14 @@ def main():
     ms_e2e32 = timed_region(lambda: queued(icp3, pinned32, 1))
     same32 = bool(np.array_equal(icp3.last_pose, icp2.last_pose))
     clocks = sampler.stop() if rank == 0 else None
+    # ---------------- untimed: the whole trajectory from scan 0 (for the drift metrics below)
+    traj = None
+    if rank == 0:
+        try:
+            traj = queued(make_pipeline(), scans_dev, 2)
+        except Exception as e:  # never lose the bench line over a side leg
+            traj = None
+            print("trajectory pass failed:", e, file=sys.stderr)
     d2h = 392.0  # sizeof(FrameResult): pose, delta, sigma, counters, stamps
 
     # the two pipelines saw identical inputs -> identical trajectories (determinism check)
@@ -398,6 +406,7 @@ def main():
     ms_leg = multi_stream_leg(args, K, N, L, torch, dev, args.streams) if args.streams > 1 else None
     nn = None if args.no_nn else nn_leg(K, N, L, torch, dev, peak)
     cpu = None if args.no_cpu else cpu_leg(args, lidar)
+    quality = trajectory_quality(lidar, traj, cpu.pop("poses", None) if cpu else None)
 
     line = {"metric": METRIC, "value": value, "unit": "scans/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -415,7 +424,8 @@ def main():
                                            "e2e": {"p50": float(np.percentile(wall_e2e, 50) * 1e3), "p99": float(np.percentile(wall_e2e, 99) * 1e3), "max": float(wall_e2e.max() * 1e3)},
                                            "over_2ms": {"resident": [[int(i), float(wall_dev[i] * 1e3)] for i in np.nonzero(wall_dev > 2e-3)[0][:8]],
                                                         "e2e": [[int(i), float(wall_e2e[i] * 1e3)] for i in np.nonzero(wall_e2e > 2e-3)[0][:8]]}},
-                       "deterministic_replay": same, "gathered_trajectories": list(all_poses.shape)},
+                       "deterministic_replay": same, "gathered_trajectories": list(all_poses.shape),
+                       "trajectory_quality": quality},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "scans/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps,
@@ -530,6 +540,33 @@ def nn_leg(K, N, L, torch, dev, peak):
             "l2": "flushed (256 MiB write) before every timed launch", "reps": len(times)}
 
 
+def trajectory_quality(lidar, traj, cpu_poses):
+    """KITTI-style drift of the registered trajectory against the synthetic ground truth (kiss-icp_b200/metrics.py =
+    Metrics.cpp restated), for the GPU path and - over the scans the cpu_baseline leg registered - for the CPU port,
+    plus the largest pose difference between the two (parity drift is immaterial)."""
+    if traj is None:
+        return None
+    try:
+        from kiss_icp_b200 import metrics as M
+        n = len(traj)
+        gt = np.array([lidar.pose(k) for k in range(n)])
+        gt = np.array([np.linalg.inv(gt[0]) @ g for g in gt])  # KISS-ICP poses are relative to the first scan
+        dist = float(np.linalg.norm(np.diff(gt[:, :3, 3], axis=0), axis=1).sum())
+        out = {"scans": n, "path_m": dist,
+               "gpu": dict(zip(["seq_trans_pct", "seq_rot_deg_per_m", "ate_rot_rad", "ate_trans_m"],
+                               list(M.sequence_error(gt, traj)) + list(M.absolute_trajectory_error(gt, traj))))}
+        if cpu_poses is not None and len(cpu_poses) <= n:
+            m = len(cpu_poses)
+            out["cpu_port"] = dict(zip(["scans", "seq_trans_pct", "seq_rot_deg_per_m", "ate_rot_rad", "ate_trans_m"],
+                                       [m] + list(M.sequence_error(gt[:m], cpu_poses)) + list(M.absolute_trajectory_error(gt[:m], cpu_poses))))
+            out["gpu_same_scans"] = dict(zip(["seq_trans_pct", "seq_rot_deg_per_m", "ate_rot_rad", "ate_trans_m"],
+                                             list(M.sequence_error(gt[:m], traj[:m])) + list(M.absolute_trajectory_error(gt[:m], traj[:m]))))
+            out["max_abs_pose_diff_gpu_vs_cpu_port"] = float(np.abs(traj[:m] - cpu_poses).max())
+        return out
+    except Exception as e:
+        return {"error": repr(e)}
+
+
 def cpu_leg(args, lidar):
     """oracle (port of the reference CPU path) on the host cores, bounded sample of the same stream."""
     from oracle import oracle as O
@@ -537,13 +574,16 @@ def cpu_leg(args, lidar):
     scans = [lidar.scan(k) for k in range(args.prime + n)]
     nt = best_thread_count(O, scans, thread_candidates())
     icp = O.KissICP(max_num_threads=nt)
+    poses = []
     for p, t in scans[:args.prime]:
         icp.register_frame(p, t, want_clouds=False)
+        poses.append(np.array(icp.pose))
     t0 = time.perf_counter()
     for p, t in scans[args.prime:]:
         icp.register_frame(p, t, want_clouds=False)
+        poses.append(np.array(icp.pose))
     dt = time.perf_counter() - t0
-    return {"value": n / dt, "unit": "scans/s", "cores": nt, "kind": "port", "ms_per_scan": dt / n * 1e3,
+    return {"poses": np.array(poses), "value": n / dt, "unit": "scans/s", "cores": nt, "kind": "port", "ms_per_scan": dt / n * 1e3,
             "sample": f"{n} scans after {args.prime} untimed priming scans of the same stream (seed 0); OpenMP threads "
                       f"picked as fastest of {thread_candidates()} on {os.cpu_count()} cpus"}
 

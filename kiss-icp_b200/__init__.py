@@ -10,5 +10,6 @@ from .registration import Registration, get_registration  # noqa: F401
 from .threshold import AdaptiveThreshold, FixedThreshold, get_threshold_estimator  # noqa: F401
 from .voxelization import voxel_down_sample  # noqa: F401
 from .preprocess import correct_kitti_scan  # noqa: F401
+from .metrics import absolute_trajectory_error, sequence_error  # noqa: F401
 
 __version__ = "0.1.0"
