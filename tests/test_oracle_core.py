@@ -281,3 +281,111 @@ def test_correct_kitti_scan_is_a_rotation_about_pt_cross_z(O):
     assert len(O.correct_kitti_scan(np.empty((0, 3)))) == 0
     g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_kitti_v1.npz"))
     assert np.array_equal(O.correct_kitti_scan(g["pts"]), g["corrected"])
+
+
+def _sophus_se3_exp(a):
+    """Sophus SE3::exp restated with scipy/numpy only: tangent = (upsilon, omega), t = V(omega) upsilon"""
+    from scipy.spatial.transform import Rotation as R
+    ups, om = np.asarray(a[:3], float), np.asarray(a[3:], float)
+    th = np.linalg.norm(om)
+    W = np.array([[0, -om[2], om[1]], [om[2], 0, -om[0]], [-om[1], om[0], 0]])
+    if th < 1e-10:
+        V = np.eye(3) + 0.5 * W
+    else:
+        V = np.eye(3) + (1 - np.cos(th)) / th**2 * W + (th - np.sin(th)) / th**3 * (W @ W)
+    T = np.eye(4)
+    T[:3, :3] = R.from_rotvec(om).as_matrix()
+    T[:3, 3] = V @ ups
+    return T
+
+
+def test_align_loop_matches_an_independent_gauss_newton(O):
+    """Registration::AlignPointsToMap (Registration.cpp:138-167) re-derived with numpy only: brute-force search of
+    the 27-voxel neighbourhood, explicit 3x6 Jacobians, numpy.linalg.solve, Sophus exp via scipy; composition order
+    est * T_icp, stop on |dx| < 1e-4, result T_icp * guess. Same iteration count, same pose."""
+    pts = rng.uniform(-12, 12, size=(2500, 3))
+    m = O.VoxelHashMap(1.0, 100.0, 20)
+    m.add_points(pts)
+    vox, cnt, stored = m.dump()
+    table, off = {}, 0
+    for v, c in zip(map(tuple, vox), cnt):
+        table[v] = stored[off:off + c]
+        off += c
+    T_true = O.se3_exp([0.12, -0.08, 0.05, 0.006, -0.004, 0.008])
+    src0 = O.se3_act(np.linalg.inv(T_true), stored[::5])
+    guess = O.se3_exp([0.02, 0.01, -0.01, 0.001, 0.0, -0.002])
+    max_dist, kernel = 0.9, 0.3
+
+    def nearest(p):
+        v = np.floor(p / 1.0).astype(int)
+        best, bd = None, np.inf
+        for dx in (-1, 0, 1):
+            for dy in (-1, 0, 1):
+                for dz in (-1, 0, 1):
+                    blk = table.get((v[0] + dx, v[1] + dy, v[2] + dz))
+                    if blk is None:
+                        continue
+                    d = np.linalg.norm(blk - p, axis=1)
+                    k = int(np.argmin(d))
+                    if d[k] < bd:
+                        best, bd = blk[k], d[k]
+        return best, bd
+
+    src = (guess[:3, :3] @ src0.T).T + guess[:3, 3]
+    T_icp, iters = np.eye(4), 0
+    for j in range(500):
+        JTJ, JTr = np.zeros((6, 6)), np.zeros(6)
+        for s in src:
+            t, d = nearest(s)
+            if t is None or not d < max_dist:
+                continue
+            r = s - t
+            J = np.hstack([np.eye(3), -np.array([[0, -s[2], s[1]], [s[2], 0, -s[0]], [-s[1], s[0], 0]])])
+            w = kernel**2 / (kernel + r @ r) ** 2
+            JTJ += J.T @ (w * J)
+            JTr += J.T @ (w * r)
+        dx = np.linalg.solve(JTJ, -JTr)
+        est = _sophus_se3_exp(dx)
+        src = (est[:3, :3] @ src.T).T + est[:3, 3]
+        T_icp = est @ T_icp
+        iters = j + 1
+        if np.linalg.norm(dx) < 1e-4:
+            break
+    want = T_icp @ guess
+    pose, it = O.align_points_to_map(m, src0, guess, max_dist, kernel, nthreads=1)
+    assert it == iters and 2 < it < 100
+    assert np.abs(pose - want).max() < 1e-9
+    assert np.abs(pose - T_true).max() < 5e-3  # and it actually registers
+
+
+def test_register_frame_matches_the_python_twin_orchestration(O):
+    """KissICP::RegisterFrame (pipeline/KissICP.cpp:35-68) against the reference's OTHER statement of the same
+    sequence, python/kiss_icp/kiss_icp.py:43-75, re-run here on the oracle's module-level functions (np.linalg.inv in
+    place of SE3::inverse, as the Python twin does)"""
+    from kiss_icp_b200 import synthetic
+    for stamps in ("none", "column"):
+        L = synthetic.small_shape(seed=11, beams=16, cols=256, stamps=stamps)
+        icp = O.KissICP(max_num_threads=1)
+        vmap = O.VoxelHashMap(1.0, 100.0, 20)
+        last_pose, last_delta = np.eye(4), np.eye(4)
+        sse, ns = 2.0 * 2.0, 1
+        for k in range(8):
+            frame, ts = L.scan(k)
+            pre_c, src_c = icp.register_frame(frame, ts)
+            # --- python/kiss_icp/kiss_icp.py:43-75
+            pre = O.preprocess(frame, ts, last_delta, 100.0, 0.0, True)
+            frame_downsample = O.voxel_down_sample(pre, 1.0 * 0.5)
+            source = O.voxel_down_sample(frame_downsample, 1.0 * 1.5)
+            sigma = np.sqrt(sse / ns)
+            initial_guess = last_pose @ last_delta
+            new_pose, _ = O.align_points_to_map(vmap, source, initial_guess, 3 * sigma, sigma, nthreads=1)
+            model_deviation = np.linalg.inv(initial_guess) @ new_pose
+            sse, ns = O.threshold_update(sse, ns, model_deviation, 0.1, 100.0)
+            vmap.update(frame_downsample, new_pose)
+            last_delta = np.linalg.inv(last_pose) @ new_pose
+            last_pose = new_pose
+            # ---
+            assert np.array_equal(pre, pre_c) if k == 0 else np.abs(pre - pre_c).max() < 1e-9
+            assert source.shape == src_c.shape
+            assert np.abs(np.array(icp.pose) - last_pose).max() < 1e-9, (stamps, k)
+        assert vmap.num_points() == icp.local_map.num_points()
