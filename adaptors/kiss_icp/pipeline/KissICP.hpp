@@ -18,21 +18,19 @@
 
 namespace kiss_icp::pipeline {
 
-struct KISSConfig {  // KissICP.hpp:36-54, field for field
-    // map params
-    double voxel_size = 1.0;
-    double max_range = 100.0;
+// Same field names, types and defaults as the reference's KISSConfig (KissICP.hpp:36-54) so that callers that fill
+// it field by field (ros/src/OdometryServer.cpp:60-80) compile unchanged; kb_config is its C mirror.
+struct KISSConfig {
+    double voxel_size = 1.0;            // local map / downsampling grid [m]
+    double max_range = 100.0;           // crop + map radius [m]
     double min_range = 0.0;
     int max_points_per_voxel = 20;
-    // th parms
-    double min_motion_th = 0.1;
-    double initial_threshold = 2.0;
-    // registration params
-    int max_num_iterations = 500;
+    double min_motion_th = 0.1;         // adaptive threshold: ignore model deviations below this [m]
+    double initial_threshold = 2.0;     // sigma before any motion was observed [m]
+    int max_num_iterations = 500;       // ICP
     double convergence_criterion = 0.0001;
-    int max_num_threads = 0;
-    // Motion compensation
-    bool deskew = true;
+    int max_num_threads = 0;            // accepted, ignored on the GPU
+    bool deskew = true;                 // needs per-point timestamps
 };
 
 class KissICP {
