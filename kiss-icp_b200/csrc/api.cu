@@ -114,9 +114,12 @@ struct Exec {
     bool own_stream = false;
     int grid = 0;
     Scratch sc{};  // all pointers null, profiling off
+    TeamScratch team{};  // ll / out (qrec belongs to the caller's workspace)
+    int icp_team_q = TQ_PER_PASS;  // source points per CTA of the ICP team (KB_ICP_TEAM_Q; 0 = whole-grid ICP loop)
     unsigned tag_seq = 0;  // launch sequence number of the tagged ICP protocol
     unsigned long long launches = 0;
     bool bar_dirty = true;  // the barrier words may be non-zero (a kernel without Grid::finish() ran last)
+    std::vector<const void *> smem_opted;  // kernels opted in to > 48 KB of dynamic shared memory on THIS context's device
     unsigned next_tag_base() { return (++tag_seq) << 13; }  // 8192 epochs per launch
 
     int init() {
@@ -146,6 +149,10 @@ struct Exec {
         CK(cudaMemsetAsync(sc.ll_group, 0, sizeof(uint4) * NPART * 16, stream));
         CK(cudaMemsetAsync(sc.ll_part, 0, sizeof(uint4) * NPART * grid, stream));
         CK(cudaMemsetAsync(sc.ll_res, 0, sizeof(uint4) * LL_RES, stream));
+        CK(cudaMalloc(&team.ll, sizeof(uint4) * 2 * NPART * TEAM_MAX));
+        CK(cudaMemsetAsync(team.ll, 0, sizeof(uint4) * 2 * NPART * TEAM_MAX, stream));
+        CK(cudaMalloc(&team.out, sizeof(double) * 16));
+        if (const char *e = std::getenv("KB_ICP_TEAM_Q")) icp_team_q = std::max(0, std::min(std::atoi(e), TQ_CAP));
         CK(cudaMalloc(&sc.dbg, sizeof(unsigned long long) * (64 + 4 * grid)));
         CK(cudaMemsetAsync(sc.dbg, 0, sizeof(unsigned long long) * (64 + 4 * grid), stream));
         return KB_OK;
@@ -159,17 +166,18 @@ struct Exec {
         if (sc.ll_res) cudaFree(sc.ll_res);
         if (sc.ll_group) cudaFree(sc.ll_group);
         if (sc.dbg) cudaFree(sc.dbg);
+        if (team.ll) cudaFree(team.ll);
+        if (team.out) cudaFree(team.out);
         if (own_stream && stream) cudaStreamDestroy(stream);
     }
     template <class P>
     int coop(void (*kern)(P), const P &p, size_t smem = 0, bool self_reset = false) {
         CK(cudaSetDevice(device));
-        if (smem > 48 * 1024) {  // opt in to large dynamic shared memory once per kernel
-            static thread_local std::vector<const void *> done;
+        if (smem > 48 * 1024) {  // opt in to large dynamic shared memory once per kernel AND device (the attribute is per device)
             const void *k = reinterpret_cast<const void *>(kern);
-            if (std::find(done.begin(), done.end(), k) == done.end()) {
+            if (std::find(smem_opted.begin(), smem_opted.end(), k) == smem_opted.end()) {
                 CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-                done.push_back(k);
+                smem_opted.push_back(k);
             }
         }
         if (!self_reset || bar_dirty)  // kernels that end with Grid::finish() leave the barrier words zeroed themselves
@@ -206,6 +214,8 @@ int make_exec(std::shared_ptr<Exec> *out) {
 // per-call workspace sized by the largest cloud seen
 struct Work {
     DBuf<double> in, ts, tmp, pre, ds1, src, work, tp;
+    DBuf<double> pre_b, ds1_b, src_b;  // second front-end set (Workspace::fr[1])
+    DBuf<QList> qrec;                  // per source point: candidate lists of the ICP team
     DBuf<int> next, touched, ds_chunk, ds_order, ds2_chunk, ds2_order, cnt;
     DBuf<int4> ds_slots, ds2_slots;
     DBuf<int2> ds_sim, ds2_sim;
@@ -233,10 +243,28 @@ struct Work {
         RET(cnt.ensure(8));
         return KB_OK;
     }
+    // the buffers only a pipeline needs: the second front-end set; the candidate lists of the ICP team
+    int ensure_pipeline(size_t n) {
+        n = std::max<size_t>(n, 1);
+        RET(pre_b.ensure(3 * n));
+        RET(ds1_b.ensure(3 * n));
+        RET(src_b.ensure(3 * n));
+        return qrec.ensure(n);
+    }
     DsScratch ds_view() { return DsScratch{ds_slots.p, ds_chunk.p, ds_order.p, ds_sim.p}; }
     DsScratch ds2_view() { return DsScratch{ds2_slots.p, ds2_chunk.p, ds2_order.p, ds2_sim.p}; }
     Workspace view() {
-        return Workspace{tmp.p, pre.p, ds1.p, src.p, work.p, tp.p, next.p, touched.p, ds_view(), ds2_view(), cnt.p};
+        Workspace w;
+        w.tmp = tmp.p;
+        w.fr[0] = Front{pre.p, ds1.p, src.p, cnt.p};
+        w.fr[1] = Front{pre_b.p, ds1_b.p, src_b.p, cnt.p + 4};
+        w.work = work.p;
+        w.tp = tp.p;
+        w.next = next.p;
+        w.touched = touched.p;
+        w.ds = ds_view();
+        w.ds2 = ds2_view();
+        return w;
     }
 };
 
@@ -480,11 +508,14 @@ struct kb_pipeline {
     FrameResult *h_res = nullptr;  // pinned
     FrameResult last{};
     bool has_last = false;
+    long long next_id = 0;  // id of the next frame to register (Workspace::fr[id & 1] holds its front end)
+    long long last_id = 0;  // id of the frame `last` describes
+    Work vox_ws;            // scratch of kb_pipeline_voxelize (must not clobber the clouds of the last frame)
     unsigned long long grow_retries = 0;
     std::vector<kb_frame_stats> history;
     size_t history_cap = 0;
     // frame queue of kb_pipeline_register_frames: frame k+1 is copied in while frame k is registered
-    static constexpr int Q_DEPTH = 3;
+    static constexpr int Q_DEPTH = 4;  // frame k registering, k+1 being prefetched by the same launch, k+2 / k+3 copying
     struct Slot {
         DBuf<double> in, ts;  // device copy of one queued frame
         void *pin_xyz = nullptr, *pin_ts = nullptr;  // pinned staging, used only when the caller's memory is pageable
@@ -809,6 +840,7 @@ static int registration_run(kb_registration *reg, const double *xyz, size_t n, k
     RET(reg->ws.work.ensure(3 * std::max<size_t>(n, 1)));
     RET(reg->out.ensure(16 + NACC));
     RET(reg->iout.ensure(2));
+    RET(reg->ws.qrec.ensure(std::max<size_t>(n, 1)));
     if (n) CK(cudaMemcpyAsync(reg->ws.src.p, xyz, n * 24, cudaMemcpyHostToDevice, ex.stream));
     IcpParams P;
     P.m = map->view();
@@ -828,6 +860,9 @@ static int registration_run(kb_registration *reg, const double *xyz, size_t n, k
     P.out_ncorr = reg->iout.p + 1;
     P.use_qcache = system_only ? 0 : 1;
     P.tag_base = ex.next_tag_base();
+    P.team = ex.team;
+    P.team.qrec = reg->ws.qrec.p;
+    P.icp_team_q = ex.icp_team_q;
     return ex.coop(k_icp, P, system_only ? 0 : QC_BYTES);
 }
 int kb_registration_align_points_to_map(kb_registration *reg, const double *xyz, size_t n, const kb_map *cmap,
@@ -1051,6 +1086,7 @@ static int pipeline_push_state(kb_pipeline *p, const SE3 &pose, const SE3 &delta
     s.model_sse = sse;
     s.num_samples = ns;
     s.vetoed = 0;
+    s.front_id = -1;
     CK(cudaMemcpyAsync(p->d_state, &s, sizeof(s), cudaMemcpyHostToDevice, p->ex->stream));
     return p->ex->sync();
 }
@@ -1105,12 +1141,20 @@ static size_t pipeline_extra(const kb_pipeline *p, size_t n) {
 }
 
 // enqueue one RegisterFrame on the pipeline's stream; the result goes to `res` (device-visible memory)
-static int pipeline_launch(kb_pipeline *p, const double *d_xyz, size_t n, const double *d_ts, size_t n_ts, bool in_f32,
-                           FrameResult *res) {
+// `next_xyz` (may be null): the frame after this one, already on the device, no timestamps -> its front end is prefetched
+static int pipeline_launch(kb_pipeline *p, long long id, const double *d_xyz, size_t n, const double *d_ts, size_t n_ts,
+                           bool in_f32, FrameResult *res, const double *next_xyz = nullptr, size_t next_n = 0) {
     Exec &ex = *p->ex;
     FrameParams P;
     P.m = p->map->view();
     P.sc = ex.sc;
+    P.team = ex.team;
+    P.team.qrec = p->ws.qrec.p;
+    P.icp_team_q = ex.icp_team_q;
+    P.id = id;
+    P.next_in = next_xyz;
+    P.next_n = static_cast<int>(next_n);
+    P.next_in_f32 = in_f32 ? 1 : 0;
     P.ws = p->ws.view();
     P.st = p->d_state;
     P.res = res;
@@ -1132,8 +1176,9 @@ static int pipeline_launch(kb_pipeline *p, const double *d_xyz, size_t n, const 
 }
 
 // take over the result of a frame that ran (not vetoed): host mirror of the counters, history
-static int pipeline_absorb(kb_pipeline *p, const FrameResult &r, size_t n) {
+static int pipeline_absorb(kb_pipeline *p, const FrameResult &r, size_t n, long long id) {
     p->last = r;
+    p->last_id = id;
     p->has_last = true;
     p->map->h_counters[C_LIVE] = p->last.map_live;
     p->map->h_counters[C_TOMB] = p->last.map_tomb;
@@ -1172,10 +1217,11 @@ static int pipeline_after_veto(kb_pipeline *p, const FrameResult &r, size_t n) {
 static int pipeline_run(kb_pipeline *p, const double *d_xyz, size_t n, const double *d_ts, size_t n_ts, bool in_f32 = false) {
     Exec &ex = *p->ex;
     RET(p->map->ensure_capacity(pipeline_extra(p, n)));
+    const long long id = p->next_id++;
     for (int attempt = 0; attempt < 3; ++attempt) {
         {
             StallTrace t("blocking: launch");
-            RET(pipeline_launch(p, d_xyz, n, d_ts, n_ts, in_f32, p->d_res));
+            RET(pipeline_launch(p, id, d_xyz, n, d_ts, n_ts, in_f32, p->d_res));
         }
         {
             StallTrace t("blocking: result D2H enqueue");
@@ -1185,7 +1231,7 @@ static int pipeline_run(kb_pipeline *p, const double *d_xyz, size_t n, const dou
             StallTrace t("blocking: stream sync");
             RET(ex.sync());
         }
-        if (!(p->h_res->map_status & ST_NEED_GROW)) return pipeline_absorb(p, *p->h_res, n);
+        if (!(p->h_res->map_status & ST_NEED_GROW)) return pipeline_absorb(p, *p->h_res, n, id);
         RET(pipeline_after_veto(p, *p->h_res, n));
     }
     return fail(KB_ERR_CUDA, "voxel table could not be grown (internal capacity bug)");
@@ -1207,6 +1253,7 @@ int kb_pipeline_register_frame(kb_pipeline *p, const double *xyz, size_t n, cons
     Exec &ex = *p->ex;
     CK(cudaSetDevice(ex.device));
     RET(p->ws.ensure(std::max(n, use_ts ? n_timestamps : 0)));
+    RET(p->ws.ensure_pipeline(std::max(n, use_ts ? n_timestamps : 0)));
     {
         StallTrace t("blocking: H2D enqueue");
         if (n) CK(cudaMemcpyAsync(p->ws.in.p, xyz, n * 24, cudaMemcpyHostToDevice, ex.stream));
@@ -1220,6 +1267,7 @@ int kb_pipeline_register_frame_f32(kb_pipeline *p, const float *xyz, size_t n, c
     Exec &ex = *p->ex;
     CK(cudaSetDevice(ex.device));
     RET(p->ws.ensure(std::max(n, use_ts ? n_timestamps : 0)));
+    RET(p->ws.ensure_pipeline(std::max(n, use_ts ? n_timestamps : 0)));
     if (n) CK(cudaMemcpyAsync(p->ws.in.p, xyz, n * 12, cudaMemcpyHostToDevice, ex.stream));  // half the bytes of the f64 path
     if (use_ts) CK(cudaMemcpyAsync(p->ws.ts.p, timestamps, n_timestamps * 8, cudaMemcpyHostToDevice, ex.stream));
     return pipeline_run(p, p->ws.in.p, n, p->ws.ts.p, use_ts ? n_timestamps : 0, true);
@@ -1230,6 +1278,7 @@ int kb_pipeline_register_frame_dev(kb_pipeline *p, const double *d_xyz, size_t n
     RET(pipeline_check(p, d_xyz, n, d_timestamps, n_timestamps, &use_ts));
     CK(cudaSetDevice(p->ex->device));
     RET(p->ws.ensure(std::max(n, use_ts ? n_timestamps : 0)));
+    RET(p->ws.ensure_pipeline(std::max(n, use_ts ? n_timestamps : 0)));
     return pipeline_run(p, d_xyz, n, d_timestamps, use_ts ? n_timestamps : 0);
 }
 // ---- queued registration of a whole sequence ------------------------------------------------------------------
@@ -1310,34 +1359,49 @@ int kb_pipeline_register_frames(kb_pipeline *p, const void *const *xyz, const si
     }
     RET(ex.sync());
     RET(p->ws.ensure(max_n));
+    RET(p->ws.ensure_pipeline(max_n));
     RET(queue_init(p, max_n, any_ts, dev_in));
 
-    size_t next_submit = 0, next_absorb = 0;
+    // Pipeline: frame k is registered by launch k, whose idle CTAs also compute the front end of frame k + 1 when that
+    // frame has no timestamps (nothing of it depends on frame k's pose then); so frame k + 1 must be on the device when
+    // launch k starts: uploads run one frame ahead of the launches, Q_DEPTH - 1 launches may be in flight.
+    size_t next_submit = 0, next_absorb = 0, next_upload = 0;
     int attempts = 0;
+    const long long id0 = p->next_id;
+    auto upload = [&](size_t u) -> int {  // host layouts: frame u -> slot u % D on the copy stream
+        auto &s = p->q[u % D];
+        StallTrace t("queue: H2D enqueue");
+        RET(queue_upload(p, s.in.p, xyz[u], n[u] * (f32 ? 12 : 24), &s.pin_xyz, &s.pin_xyz_bytes));
+        if (use_ts[u]) RET(queue_upload(p, s.ts.p, timestamps[u], n_timestamps[u] * 8, &s.pin_ts, &s.pin_ts_bytes));
+        CK(cudaEventRecord(s.copied, p->copy_stream));
+        return KB_OK;
+    };
     while (next_absorb < valid) {
         const size_t inflight = next_submit - next_absorb;
-        bool submit = next_submit < valid && inflight < D;
+        bool submit = next_submit < valid && inflight + 1 < D;
         if (submit && inflight > 0 && p->map->would_grow(pipeline_extra(p, n[next_submit]))) submit = false;  // drain first
         if (submit) {
             const size_t k = next_submit, nk = n[k], ntk = use_ts[k] ? n_timestamps[k] : 0;
             auto &s = p->q[k % D];
             RET(p->map->ensure_capacity(pipeline_extra(p, nk)));  // rebuilds only with nothing in flight
-            const double *d_xyz, *d_ts = nullptr;
+            const bool prefetch = k + 1 < valid && !use_ts[k + 1] && n[k + 1] > 0;
+            const double *d_xyz, *d_ts = nullptr, *d_next = nullptr;
             if (dev_in) {
                 d_xyz = static_cast<const double *>(xyz[k]);
                 if (ntk) d_ts = timestamps[k];
+                if (prefetch) d_next = static_cast<const double *>(xyz[k + 1]);
             } else {
-                StallTrace t("queue: H2D enqueue");
-                RET(queue_upload(p, s.in.p, xyz[k], nk * (f32 ? 12 : 24), &s.pin_xyz, &s.pin_xyz_bytes));
-                if (ntk) RET(queue_upload(p, s.ts.p, timestamps[k], ntk * 8, &s.pin_ts, &s.pin_ts_bytes));
-                CK(cudaEventRecord(s.copied, p->copy_stream));
+                for (; next_upload <= k + (prefetch ? 1 : 0); ++next_upload) RET(upload(next_upload));
                 CK(cudaStreamWaitEvent(ex.stream, s.copied, 0));
+                if (prefetch) CK(cudaStreamWaitEvent(ex.stream, p->q[(k + 1) % D].copied, 0));
                 d_xyz = s.in.p;
                 d_ts = s.ts.p;
+                if (prefetch) d_next = p->q[(k + 1) % D].in.p;
             }
             {
                 StallTrace t("queue: launch");
-                RET(pipeline_launch(p, d_xyz, nk, d_ts, ntk, f32, p->q_res_dev + k % D));
+                RET(pipeline_launch(p, id0 + static_cast<long long>(k), d_xyz, nk, d_ts, ntk, f32, p->q_res_dev + k % D, d_next,
+                                    prefetch ? n[k + 1] : 0));
                 CK(cudaEventRecord(s.done, ex.stream));
                 // result read-back on its own stream: neither the next kernel nor the next H2D waits for it (letting
                 // the kernel write to mapped host memory instead was measured ~1% slower)
@@ -1361,10 +1425,12 @@ int kb_pipeline_register_frames(kb_pipeline *p, const void *const *xyz, const si
             CK(cudaStreamSynchronize(p->res_stream));
             RET(pipeline_after_veto(p, r, n[k]));
             next_submit = k;
+            next_upload = k;
             continue;
         }
         attempts = 0;
-        const int st = pipeline_absorb(p, r, n[k]);
+        p->next_id = id0 + static_cast<long long>(k) + 1;
+        const int st = pipeline_absorb(p, r, n[k], id0 + static_cast<long long>(k));
         if (st != KB_OK) {
             ex.sync();
             return st;
@@ -1399,11 +1465,11 @@ int kb_pipeline_last_clouds(const kb_pipeline *cp, double *preprocessed_xyz, siz
     const size_t npre = static_cast<size_t>(p->last.n_pre), nsrc = static_cast<size_t>(p->last.n_src);
     if (preprocessed_xyz) {
         if (cap_preprocessed < npre) return fail(KB_ERR_CAPACITY, "preprocessed buffer too small");
-        if (npre) CK(cudaMemcpyAsync(preprocessed_xyz, p->ws.pre.p, npre * 24, cudaMemcpyDeviceToHost, p->ex->stream));
+        if (npre) CK(cudaMemcpyAsync(preprocessed_xyz, (p->last_id & 1) ? p->ws.pre_b.p : p->ws.pre.p, npre * 24, cudaMemcpyDeviceToHost, p->ex->stream));
     }
     if (source_xyz) {
         if (cap_source < nsrc) return fail(KB_ERR_CAPACITY, "source buffer too small");
-        if (nsrc) CK(cudaMemcpyAsync(source_xyz, p->ws.src.p, nsrc * 24, cudaMemcpyDeviceToHost, p->ex->stream));
+        if (nsrc) CK(cudaMemcpyAsync(source_xyz, (p->last_id & 1) ? p->ws.src_b.p : p->ws.src.p, nsrc * 24, cudaMemcpyDeviceToHost, p->ex->stream));
     }
     return p->ex->sync();
 }
@@ -1412,23 +1478,23 @@ int kb_pipeline_voxelize(kb_pipeline *p, const double *xyz, size_t n, double *so
     if (!p || (!xyz && n) || !n_source || !n_downsample) return fail(KB_ERR_INVALID_ARG, "NULL argument");
     Exec &ex = *p->ex;
     CK(cudaSetDevice(ex.device));
-    RET(p->ws.ensure(n));
-    if (n) CK(cudaMemcpyAsync(p->ws.in.p, xyz, n * 24, cudaMemcpyHostToDevice, ex.stream));
-    RET(run_downsample(ex, p->ws, p->ws.in.p, n, p->cfg.voxel_size * 0.5, p->ws.ds1.p, p->ws.cnt.p + 1,
-                       p->cfg.voxel_size * 1.5, p->ws.src.p, p->ws.cnt.p + 2));
+    RET(p->vox_ws.ensure(n));
+    if (n) CK(cudaMemcpyAsync(p->vox_ws.in.p, xyz, n * 24, cudaMemcpyHostToDevice, ex.stream));
+    RET(run_downsample(ex, p->vox_ws, p->vox_ws.in.p, n, p->cfg.voxel_size * 0.5, p->vox_ws.ds1.p, p->vox_ws.cnt.p + 1,
+                       p->cfg.voxel_size * 1.5, p->vox_ws.src.p, p->vox_ws.cnt.p + 2));
     int c[2] = {0, 0};
-    CK(cudaMemcpyAsync(c, p->ws.cnt.p + 1, sizeof(c), cudaMemcpyDeviceToHost, ex.stream));
+    CK(cudaMemcpyAsync(c, p->vox_ws.cnt.p + 1, sizeof(c), cudaMemcpyDeviceToHost, ex.stream));
     RET(ex.sync());
     *n_downsample = static_cast<size_t>(c[0]);
     *n_source = static_cast<size_t>(c[1]);
     if (source_xyz) {
         if (cap_source < *n_source) return fail(KB_ERR_CAPACITY, "source buffer too small");
-        if (*n_source) CK(cudaMemcpyAsync(source_xyz, p->ws.src.p, *n_source * 24, cudaMemcpyDeviceToHost, ex.stream));
+        if (*n_source) CK(cudaMemcpyAsync(source_xyz, p->vox_ws.src.p, *n_source * 24, cudaMemcpyDeviceToHost, ex.stream));
     }
     if (downsample_xyz) {
         if (cap_downsample < *n_downsample) return fail(KB_ERR_CAPACITY, "downsample buffer too small");
         if (*n_downsample)
-            CK(cudaMemcpyAsync(downsample_xyz, p->ws.ds1.p, *n_downsample * 24, cudaMemcpyDeviceToHost, ex.stream));
+            CK(cudaMemcpyAsync(downsample_xyz, p->vox_ws.ds1.p, *n_downsample * 24, cudaMemcpyDeviceToHost, ex.stream));
     }
     return ex.sync();
 }

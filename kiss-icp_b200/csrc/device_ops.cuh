@@ -34,7 +34,7 @@ constexpr int NWARPS = BLOCK / 32;
 constexpr int NACC = 16;  // unique accumulators of the 6x6 normal equations (see icp_accumulate)
 constexpr int NPART = NACC + 5;  // per-CTA partial: accumulators, #correspondences, #candidate points, cache hits/fills/overflows
 constexpr int DS_MAX_CHUNKS = 4096;  // downsample: 32-bucket chunks up to 131072 buckets (a 65k-point scan), coarser beyond
-constexpr int BAR_ARRIVE = 32, BAR_EPOCH = 64, BAR_WORDS = 96;  // word offsets inside Scratch::bar
+constexpr int BAR_ARRIVE = 32, BAR_TEAM = 64, BAR_WORDS = 96;  // word offsets inside Scratch::bar (one 128-byte line each)
 constexpr int ICP_REC = 32;
 constexpr int LL_RES = 16;        // est(7) + done flag, final pose(7), spare      // est(7) t_icp(7) final(7) conv cand_total query_total ...
 
@@ -77,7 +77,7 @@ struct MapView {
 
 // cross-CTA scratch, sized by the grid
 struct Scratch {
-    unsigned *bar;  // [0] grid barrier counter, [BAR_ARRIVE] CTAs that left the kernel (Grid::finish), [BAR_EPOCH] spare: one 128-B
+    unsigned *bar;  // [0] grid barrier counter, [BAR_ARRIVE] CTAs that left the kernel (Grid::finish), [BAR_TEAM] barrier counter of the front-end team: one 128-B
                     // line each (arrival atomics must not fight the epoch pollers); zeroed before each launch
     double *blk_d;  // [2][NPART][grid] doubles (ping-pong by ICP iteration parity; value-major so the reduce is coalesced)
     double *icp_rec;  // (unused by the tagged protocol; kept for the debug tools)
@@ -139,17 +139,31 @@ __device__ __forceinline__ bool ll_load(const uint4 *p, unsigned tag, double *v)
 
 __device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 
+// A Grid is the set of CTAs that take part in a barrier: the whole launch (init) or a TEAM of consecutive
+// CTAs (init_team) with its own counter word — k_register_frame splits the launch into an ICP team and a
+// front-end team that work on different scans at the same time. rank/size replace blockIdx.x/gridDim.x in
+// every op that may run on a team.
 struct Grid {
     unsigned *bar;
     unsigned target;
+    int rank, size;
     __device__ __forceinline__ void init(unsigned *b) {
         bar = b;
         target = 0;
+        rank = static_cast<int>(blockIdx.x);
+        size = static_cast<int>(gridDim.x);
+    }
+    // CTAs [first, first + count) of the launch; `word` = this team's counter (its own 128-byte line)
+    __device__ __forceinline__ void init_team(unsigned *word, int first, int count) {
+        bar = word;
+        target = 0;
+        rank = static_cast<int>(blockIdx.x) - first;
+        size = count;
     }
     __device__ __forceinline__ void sync() {
         __syncthreads();
         if (threadIdx.x == 0) {
-            target += gridDim.x;
+            target += static_cast<unsigned>(size);
             unsigned old;  // release our writes / acquire everybody else's
             asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(old) : "l"(bar) : "memory");
             while (ld_relaxed_u32(bar) < target) {
@@ -160,9 +174,11 @@ struct Grid {
     }
     // every CTA, once, after its last sync(): the last one to leave re-arms the barrier for the next launch, which
     // saves the host a memset node in front of every launch (kernels launched with Exec::coop(..., self_reset))
+    // (full-grid object only; also re-arms the team counter word)
     __device__ __forceinline__ void finish() {
         if (threadIdx.x == 0 && atomicAdd(bar + BAR_ARRIVE, 1u) == gridDim.x - 1) {
             atomicExch(bar + BAR_ARRIVE, 0u);
+            atomicExch(bar + BAR_TEAM, 0u);
             atomicExch(bar, 0u);
         }
     }
@@ -279,14 +295,14 @@ __device__ __forceinline__ int block_sum(int v, int *s_warp) {
 }
 
 // offset of this CTA (sum of blk_i[0..b-1]) and grand total, read after a grid barrier
-__device__ __forceinline__ void grid_offsets(const int *blk_i, int *offset, int *total, int *s_two) {
+__device__ __forceinline__ void grid_offsets(const Grid &g, const int *blk_i, int *offset, int *total, int *s_two) {
     __syncthreads();
     if (threadIdx.x < 32) {
         int before = 0, tot = 0;
-        for (int i = threadIdx.x; i < static_cast<int>(gridDim.x); i += 32) {
+        for (int i = threadIdx.x; i < g.size; i += 32) {
             const int c = __ldcg(&blk_i[i]);
             tot += c;
-            if (i < static_cast<int>(blockIdx.x)) before += c;
+            if (i < g.rank) before += c;
         }
         for (int o = 16; o > 0; o >>= 1) {
             before += __shfl_xor_sync(FULL, before, o);
@@ -302,9 +318,9 @@ __device__ __forceinline__ void grid_offsets(const int *blk_i, int *offset, int 
     *total = s_two[1];
 }
 
-__device__ __forceinline__ void chunk_of(long long n, long long *lo, long long *hi) {
-    *lo = n * blockIdx.x / gridDim.x;
-    *hi = n * (blockIdx.x + 1) / gridDim.x;
+__device__ __forceinline__ void chunk_of(const Grid &g, long long n, long long *lo, long long *hi) {
+    *lo = n * static_cast<unsigned>(g.rank) / static_cast<unsigned>(g.size);
+    *hi = n * (static_cast<unsigned>(g.rank) + 1) / static_cast<unsigned>(g.size);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -391,7 +407,7 @@ __device__ __noinline__ void op_preprocess(Grid &g, const Scratch &sc, Shared &s
     if (do_deskew) {
         // std::minmax_element over ALL stamps (Preprocessing.cpp:62-64)
         double mn = DBL_MAX, mx = -DBL_MAX;
-        for (int i = blockIdx.x * BLOCK + threadIdx.x; i < n_ts; i += gridDim.x * BLOCK) {
+        for (int i = static_cast<unsigned>(g.rank) * BLOCK + threadIdx.x; i < n_ts; i += static_cast<unsigned>(g.size) * BLOCK) {
             const double t = ts[i];
             mn = fmin(mn, t);
             mx = fmax(mx, t);
@@ -410,13 +426,13 @@ __device__ __noinline__ void op_preprocess(Grid &g, const Scratch &sc, Shared &s
                 mn = fmin(mn, sh.warp_d[w][0]);
                 mx = fmax(mx, sh.warp_d[w][1]);
             }
-            sc.blk_d[2 * blockIdx.x] = mn;
-            sc.blk_d[2 * blockIdx.x + 1] = mx;
+            sc.blk_d[2 * static_cast<unsigned>(g.rank)] = mn;
+            sc.blk_d[2 * static_cast<unsigned>(g.rank) + 1] = mx;
         }
         g.sync();
         if (threadIdx.x == 0) {
             double a = DBL_MAX, b = -DBL_MAX;
-            for (unsigned i = 0; i < gridDim.x; ++i) {
+            for (unsigned i = 0; i < static_cast<unsigned>(g.size); ++i) {
                 a = fmin(a, __ldcg(&sc.blk_d[2 * i]));
                 b = fmax(b, __ldcg(&sc.blk_d[2 * i + 1]));
             }
@@ -427,7 +443,7 @@ __device__ __noinline__ void op_preprocess(Grid &g, const Scratch &sc, Shared &s
         __syncthreads();
     }
     long long lo, hi;
-    chunk_of(n, &lo, &hi);
+    chunk_of(g, n, &lo, &hi);
     // pass 1: deskew into tmp, count survivors of the crop
     int kept = 0;
     for (long long base = lo; base < hi; base += BLOCK) {
@@ -449,11 +465,11 @@ __device__ __noinline__ void op_preprocess(Grid &g, const Scratch &sc, Shared &s
         }
     }
     const int blk_kept = block_sum(kept, sh.warp_i);
-    if (threadIdx.x == 0) sc.blk_i[blockIdx.x] = blk_kept;
+    if (threadIdx.x == 0) sc.blk_i[static_cast<unsigned>(g.rank)] = blk_kept;
     g.sync();
     int offset, total;
-    grid_offsets(sc.blk_i, &offset, &total, sh.two);
-    if (blockIdx.x == 0 && threadIdx.x == 0) *out_n = total;
+    grid_offsets(g, sc.blk_i, &offset, &total, sh.two);
+    if (static_cast<unsigned>(g.rank) == 0 && threadIdx.x == 0) *out_n = total;
     // pass 2: ordered compaction
     const double *src = do_deskew ? tmp : in;
     const bool src_f32 = in_f32 && !do_deskew;
@@ -521,11 +537,11 @@ __device__ __forceinline__ unsigned ds_chunk_shift(unsigned B) {
 }
 
 // clear the scratch for a table of n inputs (grid-stride; the caller provides the barrier)
-__device__ __forceinline__ void ds_clear(const DsScratch &ds, int n_upper) {
+__device__ __forceinline__ void ds_clear(const Grid &g, const DsScratch &ds, int n_upper) {
     const unsigned B = robin_bucket_count(n_upper);
     const int4 empty = make_int4(-1, -1, -1, KB_EMPTY);
-    for (unsigned i = blockIdx.x * BLOCK + threadIdx.x; i < B; i += gridDim.x * BLOCK) ds.slots[i] = empty;
-    for (unsigned i = blockIdx.x * BLOCK + threadIdx.x; i < static_cast<unsigned>(DS_MAX_CHUNKS); i += gridDim.x * BLOCK)
+    for (unsigned i = static_cast<unsigned>(g.rank) * BLOCK + threadIdx.x; i < B; i += static_cast<unsigned>(g.size) * BLOCK) ds.slots[i] = empty;
+    for (unsigned i = static_cast<unsigned>(g.rank) * BLOCK + threadIdx.x; i < static_cast<unsigned>(DS_MAX_CHUNKS); i += static_cast<unsigned>(g.size) * BLOCK)
         ds.chunk_cnt[i] = 0;
 }
 
@@ -570,7 +586,7 @@ __device__ __noinline__ void op_downsample(Grid &g, const Scratch &sc, Shared &s
     const DsScratch ds = ds_in;
     const unsigned B = robin_bucket_count(n);
     if (B == 0) {
-        if (blockIdx.x == 0 && threadIdx.x == 0) *out_n = 0;
+        if (static_cast<unsigned>(g.rank) == 0 && threadIdx.x == 0) *out_n = 0;
         return;  // uniform across the grid
     }
     const unsigned mask = B - 1;
@@ -580,13 +596,13 @@ __device__ __noinline__ void op_downsample(Grid &g, const Scratch &sc, Shared &s
     const unsigned CH = 1u << csh;
     const unsigned nchunks = (B + CH - 1) >> csh;
     if (!precleared) {
-        ds_clear(ds, n);
+        ds_clear(g, ds, n);
         g.sync();
     }
-    if (stamps && blockIdx.x == 0 && threadIdx.x == 0) stamps[0] = globaltimer_ns();
+    if (stamps && static_cast<unsigned>(g.rank) == 0 && threadIdx.x == 0) stamps[0] = globaltimer_ns();
     // (a) dedupe: first input index per voxel; claimed buckets are counted per chunk
     const VoxelDiv vd = make_voxel_div(voxel_size);
-    for (int i = blockIdx.x * BLOCK + threadIdx.x; i < n; i += gridDim.x * BLOCK) {
+    for (int i = static_cast<unsigned>(g.rank) * BLOCK + threadIdx.x; i < n; i += static_cast<unsigned>(g.size) * BLOCK) {
         const int3 v = point_to_voxel(in[3 * i], in[3 * i + 1], in[3 * i + 2], vd);
         unsigned h = ref_hash(v.x, v.y, v.z) & mask;
         while (true) {
@@ -604,7 +620,7 @@ __device__ __noinline__ void op_downsample(Grid &g, const Scratch &sc, Shared &s
         }
     }
     g.sync();
-    if (stamps && blockIdx.x == 0 && threadIdx.x == 0) stamps[1] = stamps[2] = stamps[3] = globaltimer_ns();
+    if (stamps && static_cast<unsigned>(g.rank) == 0 && threadIdx.x == 0) stamps[1] = stamps[2] = stamps[3] = globaltimer_ns();
     // (b) exclusive prefix of the chunk counts (every CTA, in shared memory): DS_MAX_CHUNKS / BLOCK chunks per thread
     {
         constexpr int PER = DS_MAX_CHUNKS / BLOCK;
@@ -639,13 +655,13 @@ __device__ __noinline__ void op_downsample(Grid &g, const Scratch &sc, Shared &s
             sh.chunk_pref[PER * t + k] = excl;
             excl += cv[k];
         }
-        if (blockIdx.x == 0 && t == 0) *out_n = total;
+        if (static_cast<unsigned>(g.rank) == 0 && t == 0) *out_n = total;
         __syncthreads();
     }
     // (c) one warp per chunk: singleton runs per lane, longer runs replayed in registers
     const int lane = threadIdx.x & 31;
     const unsigned lt = (1u << lane) - 1u;
-    for (unsigned c = blockIdx.x + gridDim.x * (threadIdx.x >> 5); c < nchunks; c += gridDim.x * NWARPS) {
+    for (unsigned c = static_cast<unsigned>(g.rank) + static_cast<unsigned>(g.size) * (threadIdx.x >> 5); c < nchunks; c += static_cast<unsigned>(g.size) * NWARPS) {
         const unsigned cbase = c << csh;
         const unsigned cend = min(cbase + CH, B);
         int before = sh.chunk_pref[c];  // occupied buckets before the current group

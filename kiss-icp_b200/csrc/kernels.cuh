@@ -3,6 +3,7 @@
 #pragma once
 
 #include "device_ops.cuh"
+#include "icp_team.cuh"
 
 namespace kb {
 
@@ -14,6 +15,8 @@ struct PipeState {
     int num_samples;   // AdaptiveThreshold::num_samples_ Threshold.hpp:46
     int vetoed;        // set by a frame that found the voxel table too small: frames already queued behind it
                        // must not run on the stale state, they return ST_SKIPPED until the host has grown the table
+    long long front_id;  // id of the frame whose preprocessed / downsampled clouds are in Workspace::fr[id & 1]
+                         // (written by the launch that prefetched them), -1: none
 };
 
 // what the host reads back after every RegisterFrame (one small D2H)
@@ -26,43 +29,57 @@ struct FrameResult {
     int iterations;
     int n_pre, n_ds, n_src;
     int map_live, map_tomb, map_points, map_status;
-    int pad;
+    int team;          // CTAs of the ICP team (0: the whole-grid loop ran)
     double icp_candidates;  // map points examined by all ICP iterations of this frame
     double icp_queries;     // GetClosestNeighbor calls (iterations x source points)
     double cache_stats[3];  // NN-cache hits / fills / overflows over all iterations
     unsigned long long t_ns[20];  // %globaltimer at phase boundaries (CTA 0): start, pre, ds1, ds2, icp, map, end
 };
 
+// output of the front end of one frame (Preprocess + Voxelize, KissICP.cpp:38,41): two sets, so that the next
+// frame's front end can be computed while this frame is still being registered
+struct Front {
+    double *pre;  // [n][3] preprocessed frame
+    double *ds1;  // [n][3] frame_downsample (0.5 v)
+    double *src;  // [n][3] source (1.5 v)
+    int *cnt;     // [4] n_pre, n_ds, n_src
+};
+
 struct Workspace {
     double *tmp;    // [n][3] deskewed points
-    double *pre;    // [n][3] preprocessed frame
-    double *ds1;    // [n][3] frame_downsample (0.5 v)
-    double *src;    // [n][3] source (1.5 v)
-    double *work;   // [n][3] source in the map frame (ICP iterate)
+    Front fr[2];    // by frame id parity
+    double *work;   // [n][3] source in the map frame (ICP iterate of the whole-grid loop)
     double *tp;     // [n][3] points being inserted, map frame
     int *next;      // [n] pending-list links
     int *touched;   // [n] voxels touched by the current AddPoints
     DsScratch ds;    // [pow2 >= 2n] downsample scratch tables (0.5 v pass)
     DsScratch ds2;   // second set for the 1.5 v pass (both are cleared during preprocessing)
-    int *cnt;        // [8] device-side counts (n_pre, n_ds, n_src, ...)
 };
 
 struct FrameParams {
     MapView m;
     Scratch sc;
+    TeamScratch team;
     Workspace ws;
     PipeState *st;
     FrameResult *res;
     const double *in;
     const double *ts;
     int n, n_ts;
+    int in_f32;  // the frame is float[n][3] instead of double[n][3]
+    long long id;  // frame id (monotonic per pipeline; a frame replayed after a capacity veto keeps its id)
+    // the frame after this one, when the caller already has it on the device (kb_pipeline_register_frames) and its
+    // front end does not depend on this frame's result (no timestamps to deskew with): its preprocessing and
+    // downsampling run on the CTAs the ICP team leaves idle. next_in == nullptr: none.
+    const double *next_in;
+    int next_n, next_in_f32;
     int deskew;
     double max_range, min_range, voxel_size;
     int max_iter;
     double conv, min_motion_th;
     int use_qcache;
+    int icp_team_q;  // source points per CTA of the ICP team; 0: whole-grid loop (op_icp)
     unsigned tag_base;
-    int in_f32;  // the frame is float[n][3] instead of double[n][3]
 };
 
 __device__ __forceinline__ void threshold_update(const SE3 &dev, double min_motion_th, double max_range,
@@ -78,15 +95,37 @@ __device__ __forceinline__ void threshold_update(const SE3 &dev, double min_moti
     }
 }
 
-// ---- KissICP::RegisterFrame (pipeline/KissICP.cpp:35-68) as ONE persistent kernel ----------
 #define KB_STAMP(i) \
     if (P.sc.profile && blockIdx.x == 0 && threadIdx.x == 0) P.res->t_ns[i] = globaltimer_ns()
 
-extern __shared__ __align__(16) unsigned char kb_dyn_smem[];  // QCache[NWARPS][QC_SLOTS] when launched with QC_BYTES
+extern __shared__ __align__(16) unsigned char kb_dyn_smem[];  // QCache[NWARPS][QC_SLOTS] (op_icp) or QList[TQ_CAP] (op_icp_team)
 
+// Preprocess + Voxelize of one frame on the CTAs of `g` (the whole launch, or the front-end team), KissICP.cpp:38,41,70-75.
+// Three barriers of `g` inside; the caller provides the one behind it. No timestamps => `motion` is not used.
+__device__ __noinline__ void op_front(Grid &g, const Scratch &sc, Shared &sh, const Workspace &ws, const Front &fr,
+                                      const double *in, int n, const double *ts, int n_ts, bool deskew, const SE3 &motion,
+                                      double max_range, double min_range, double voxel_size, bool in_f32,
+                                      unsigned long long *t_ns /* stamps of the profiled launch or nullptr */) {
+    // the downsample scratch tables of both passes are cleared here, under the preprocess barriers
+    ds_clear(g, ws.ds, n);
+    ds_clear(g, ws.ds2, n);
+    op_preprocess(g, sc, sh, in, n, ts, n_ts, deskew, motion, max_range, min_range, ws.tmp, fr.pre, &fr.cnt[0], in_f32);
+    g.sync();
+    if (t_ns && g.rank == 0 && threadIdx.x == 0) t_ns[1] = globaltimer_ns();
+    const int n_pre = __ldcg(&fr.cnt[0]);
+    op_downsample(g, sc, sh, fr.pre, n_pre, voxel_size * 0.5, ws.ds, fr.ds1, &fr.cnt[1], t_ns ? &t_ns[12] : nullptr, true);
+    g.sync();
+    if (t_ns && g.rank == 0 && threadIdx.x == 0) t_ns[2] = globaltimer_ns();
+    const int n_ds = __ldcg(&fr.cnt[1]);
+    op_downsample(g, sc, sh, fr.ds1, n_ds, voxel_size * 1.5, ws.ds2, fr.src, &fr.cnt[2], t_ns ? &t_ns[16] : nullptr, true);
+}
+
+// ---- KissICP::RegisterFrame (pipeline/KissICP.cpp:35-68) as ONE persistent kernel ----------
+//   [front end of this frame, unless a previous launch prefetched it]
+//   capacity check | fill pass (all CTAs) | ICP iterations on the team  ||  front end of the NEXT frame on the rest
+//   map update (all CTAs) | epilogue
 __global__ void __launch_bounds__(BLOCK, 1) k_register_frame(const FrameParams P) {
     __shared__ Shared sh;
-    QCache *qcache = P.use_qcache ? reinterpret_cast<QCache *>(kb_dyn_smem) : nullptr;
     Grid g;
     g.init(P.sc.bar);
     KB_STAMP(0);
@@ -94,52 +133,72 @@ __global__ void __launch_bounds__(BLOCK, 1) k_register_frame(const FrameParams P
     const SE3 last_delta = P.st->last_delta;
     const double model_sse = P.st->model_sse;
     const int num_samples = P.st->num_samples;
+    const long long front_id = P.st->front_id;
     if (P.st->vetoed) {  // written only by an EARLIER launch: uniform across the grid
         if (blockIdx.x == 0 && threadIdx.x == 0) P.res->map_status = ST_SKIPPED;
         g.finish();
         return;
     }
-
-    // the downsample scratch tables of both passes are cleared here, under the preprocess barriers
-    ds_clear(P.ws.ds, P.n);
-    ds_clear(P.ws.ds2, P.n);
-    // Preprocess (KissICP.cpp:38)
-    op_preprocess(g, P.sc, sh, P.in, P.n, P.ts, P.n_ts, P.deskew != 0, last_delta, P.max_range, P.min_range,
-                  P.ws.tmp, P.ws.pre, &P.ws.cnt[0], P.in_f32 != 0);
-    g.sync();
-    KB_STAMP(1);
-    const int n_pre = __ldcg(&P.ws.cnt[0]);
-    // Voxelize (KissICP.cpp:70-75)
-    op_downsample(g, P.sc, sh, P.ws.pre, n_pre, P.voxel_size * 0.5, P.ws.ds, P.ws.ds1,
-                  &P.ws.cnt[1], P.sc.profile ? &P.res->t_ns[12] : nullptr, true);
-    g.sync();
-    KB_STAMP(2);
-    const int n_ds = __ldcg(&P.ws.cnt[1]);
+    const Front fr = P.ws.fr[P.id & 1];
+    if (front_id != P.id) {  // uniform: written only by an earlier launch
+        op_front(g, P.sc, sh, P.ws, fr, P.in, P.n, P.ts, P.n_ts, P.deskew != 0, last_delta, P.max_range, P.min_range,
+                 P.voxel_size, P.in_f32 != 0, P.sc.profile ? P.res->t_ns : nullptr);
+        g.sync();
+    } else if (P.sc.profile && blockIdx.x == 0 && threadIdx.x == 0) {
+        P.res->t_ns[1] = P.res->t_ns[2] = globaltimer_ns();  // front end prefetched by the previous launch
+    }
+    KB_STAMP(3);
+    const int n_pre = __ldcg(&fr.cnt[0]), n_ds = __ldcg(&fr.cnt[1]), n_src = __ldcg(&fr.cnt[2]);
     // optimistic table capacity: the host sized the voxel table for the EXPECTED number of new voxels. If this
     // frame could push the load factor beyond 0.5, nothing has been modified yet: report and let the host grow
-    // the table and replay the frame (rare; first frames of a sequence).
+    // the table and replay the frame (rare; first frames of a sequence). The frame's front end stays valid.
     {
         const long long need = static_cast<long long>(__ldcg(&P.m.counters[C_LIVE])) + __ldcg(&P.m.counters[C_TOMB]) + n_ds;
         if (need * 2 > static_cast<long long>(P.m.mask) + 1) {
             if (blockIdx.x == 0 && threadIdx.x == 0) {
                 P.res->map_status = ST_NEED_GROW;
                 P.res->n_ds = n_ds;
-                P.st->vetoed = 1;  // every CTA read it before the first grid barrier
+                P.st->vetoed = 1;     // every CTA read it before the first grid barrier
+                P.st->front_id = P.id;  // fr[id & 1] holds this frame's front end: the replay skips it
             }
             g.finish();
             return;  // uniform across the grid
         }
     }
-    op_downsample(g, P.sc, sh, P.ws.ds1, n_ds, P.voxel_size * 1.5, P.ws.ds2, P.ws.src,
-                  &P.ws.cnt[2], P.sc.profile ? &P.res->t_ns[16] : nullptr, true);
-    g.sync();
-    KB_STAMP(3);
-    const int n_src = __ldcg(&P.ws.cnt[2]);
     // sigma, initial guess (KissICP.cpp:44,47)
     const double sigma = sqrt(model_sse / num_samples);
     const SE3 guess = se3_mul(last_pose, last_delta);
     // ICP (KissICP.cpp:50-54)
-    op_icp(g, P.sc, sh, P.m, P.ws.src, P.ws.work, n_src, guess, 3.0 * sigma, sigma, P.max_iter, P.conv, qcache, P.tag_base);
+    const int G = static_cast<int>(gridDim.x);
+    const bool icp_runs = __ldcg(&P.m.counters[C_LIVE]) != 0 && P.max_iter > 0;  // voxel_map.Empty() -> initial_guess
+    int T = 0;
+    if (icp_runs && P.icp_team_q > 0 && P.m.cap <= NN_FLAT_CAP && (static_cast<unsigned long long>(P.m.mask) + 1) * P.m.cap < (1ull << 31)) {
+        T = icp_team_size(n_src, min(P.icp_team_q, TQ_CAP), G);
+        if (!icp_team_fits(n_src, T)) T = 0;
+    }
+    if (T > 0) {
+        icp_fill_pass(g, sh, P.m, fr.src, n_src, guess, P.team.qrec);
+        g.sync();
+        if (static_cast<int>(blockIdx.x) < T) {
+            op_icp_team(P.team, P.sc, sh, P.m, n_src, guess, 3.0 * sigma, sigma, P.max_iter, P.conv,
+                        reinterpret_cast<QList *>(kb_dyn_smem), T, P.tag_base);
+            if (blockIdx.x == 0 && threadIdx.x == 0) team_publish(P.team, sh);
+        } else if (P.next_in != nullptr && 2 * (G - T) >= G) {
+            // the CTAs the team does not need register nothing now: they run the next frame's front end
+            Grid gf;
+            gf.init_team(P.sc.bar + BAR_TEAM, T, G - T);
+            const Front nf = P.ws.fr[(P.id + 1) & 1];
+            op_front(gf, P.sc, sh, P.ws, nf, P.next_in, P.next_n, nullptr, 0, false, last_delta, P.max_range, P.min_range,
+                     P.voxel_size, P.next_in_f32 != 0, nullptr);
+            if (gf.rank == 0 && threadIdx.x == 0) P.st->front_id = P.id + 1;  // visible to the next launch
+        }
+        g.sync();
+        if (threadIdx.x == 0) team_collect(P.team, sh);
+        __syncthreads();
+    } else {
+        op_icp(g, P.sc, sh, P.m, fr.src, P.ws.work, n_src, guess, 3.0 * sigma, sigma, P.max_iter, P.conv,
+               P.use_qcache ? reinterpret_cast<QCache *>(kb_dyn_smem) : nullptr, P.tag_base);
+    }
     const SE3 new_pose = sh.result;
     const int iters = sh.iters;
     const double icp_cand = sh.cand_total, icp_q = sh.query_total;
@@ -148,17 +207,16 @@ __global__ void __launch_bounds__(BLOCK, 1) k_register_frame(const FrameParams P
     // Bookkeeping (KissICP.cpp:57-63: model deviation, threshold, delta, pose) is ~6 us of single-thread FP64
     // math; it only needs new_pose, so one thread of the LAST CTA does it now, hidden behind the map update's
     // first phase (that thread owns no insert work), instead of serially after the map update.
+    // The pipeline state itself is stored after the last barrier: with a prefetched front end and no ICP (empty
+    // map) there may be no barrier between the slowest CTA's read of the state and this point.
     const bool book = (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0);
+    double sse = model_sse;
+    int ns = num_samples;
+    SE3 delta = last_delta;
     if (book) {
         const SE3 dev = se3_mul(se3_inverse(guess), new_pose);
-        double sse = model_sse;
-        int ns = num_samples;
         threshold_update(dev, P.min_motion_th, P.max_range, &sse, &ns);
-        const SE3 delta = se3_mul(se3_inverse(last_pose), new_pose);
-        P.st->model_sse = sse;
-        P.st->num_samples = ns;
-        P.st->last_delta = delta;
-        P.st->last_pose = new_pose;
+        delta = se3_mul(se3_inverse(last_pose), new_pose);
         FrameResult *r = P.res;
         se3_to_matrix(new_pose, r->pose);
         se3_to_matrix(delta, r->delta);
@@ -170,19 +228,22 @@ __global__ void __launch_bounds__(BLOCK, 1) k_register_frame(const FrameParams P
         r->n_pre = n_pre;
         r->n_ds = n_ds;
         r->n_src = n_src;
-    }
-    if (blockIdx.x == 0 && threadIdx.x == 0) {  // work counters live in the coordinator's shared memory
-        P.res->icp_candidates = icp_cand;
-        P.res->cache_stats[0] = cs0;
-        P.res->cache_stats[1] = cs1;
-        P.res->cache_stats[2] = cs2;
+        r->team = T;
+        r->icp_candidates = icp_cand;
+        r->cache_stats[0] = cs0;
+        r->cache_stats[1] = cs1;
+        r->cache_stats[2] = cs2;
     }
     // local_map_.Update(frame_downsample, new_pose) (KissICP.cpp:61)
-    op_map_add(g, sh, P.m, P.ws.ds1, n_ds, true, new_pose, P.ws.tp, P.ws.next, P.ws.touched, P.sc.profile ? &P.res->t_ns[8] : nullptr);
+    op_map_add(g, sh, P.m, fr.ds1, n_ds, true, new_pose, P.ws.tp, P.ws.next, P.ws.touched, P.sc.profile ? &P.res->t_ns[8] : nullptr);
     op_map_remove_far(P.m, new_pose.t);
     g.sync();
     KB_STAMP(5);
     if (book) {
+        P.st->model_sse = sse;
+        P.st->num_samples = ns;
+        P.st->last_delta = delta;
+        P.st->last_pose = new_pose;
         FrameResult *r = P.res;
         r->map_live = P.m.counters[C_LIVE];
         r->map_tomb = P.m.counters[C_TOMB];
@@ -266,6 +327,8 @@ struct IcpParams {
     int *out_ncorr;
     int use_qcache;
     unsigned tag_base;
+    TeamScratch team;
+    int icp_team_q;  // source points per CTA of the ICP team; 0: whole-grid loop
 };
 __global__ void __launch_bounds__(BLOCK, 1) k_icp(const IcpParams P) {
     __shared__ Shared sh;
@@ -282,8 +345,22 @@ __global__ void __launch_bounds__(BLOCK, 1) k_icp(const IcpParams P) {
         }
         return;
     }
-    op_icp(g, P.sc, sh, P.m, P.src, P.work, P.n, P.guess, P.max_dist, P.kscale, P.max_iter, P.conv,
-           P.use_qcache ? reinterpret_cast<QCache *>(kb_dyn_smem) : nullptr, P.tag_base);
+    int T = 0;
+    if (__ldcg(&P.m.counters[C_LIVE]) != 0 && P.max_iter > 0 && P.icp_team_q > 0 && P.use_qcache && P.m.cap <= NN_FLAT_CAP &&
+        (static_cast<unsigned long long>(P.m.mask) + 1) * P.m.cap < (1ull << 31)) {
+        T = icp_team_size(P.n, min(P.icp_team_q, TQ_CAP), static_cast<int>(gridDim.x));
+        if (!icp_team_fits(P.n, T)) T = 0;
+    }
+    if (T > 0) {
+        icp_fill_pass(g, sh, P.m, P.src, P.n, P.guess, P.team.qrec);
+        g.sync();
+        if (static_cast<int>(blockIdx.x) >= T) return;
+        op_icp_team(P.team, P.sc, sh, P.m, P.n, P.guess, P.max_dist, P.kscale, P.max_iter, P.conv,
+                    reinterpret_cast<QList *>(kb_dyn_smem), T, P.tag_base);
+    } else {
+        op_icp(g, P.sc, sh, P.m, P.src, P.work, P.n, P.guess, P.max_dist, P.kscale, P.max_iter, P.conv,
+               P.use_qcache ? reinterpret_cast<QCache *>(kb_dyn_smem) : nullptr, P.tag_base);
+    }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         se3_to_matrix(sh.result, P.out_pose);
         *P.out_iters = sh.iters;
@@ -459,7 +536,7 @@ __global__ void __launch_bounds__(BLOCK, 1) k_map_export(const ExportParams P) {
     Grid g;
     g.init(P.sc.bar);
     long long lo, hi;
-    chunk_of(static_cast<long long>(P.m.mask) + 1, &lo, &hi);
+    chunk_of(g, static_cast<long long>(P.m.mask) + 1, &lo, &hi);
     int nv = 0, np = 0;
     for (long long i = lo + threadIdx.x; i < hi; i += BLOCK) {
         const int w = P.m.slots[i].w;
@@ -476,8 +553,8 @@ __global__ void __launch_bounds__(BLOCK, 1) k_map_export(const ExportParams P) {
     }
     g.sync();
     int voff, vtot, poff, ptot;
-    grid_offsets(P.sc.blk_i, &voff, &vtot, sh.two);
-    grid_offsets(P.sc.blk_i + gridDim.x, &poff, &ptot, sh.two);
+    grid_offsets(g, P.sc.blk_i, &voff, &vtot, sh.two);
+    grid_offsets(g, P.sc.blk_i + gridDim.x, &poff, &ptot, sh.two);
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         P.totals[0] = vtot;
         P.totals[1] = ptot;

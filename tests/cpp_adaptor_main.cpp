@@ -10,6 +10,12 @@ int main() {
     config.deskew = false;
     try {
         kiss_icp::pipeline::KissICP icp(config);
+        kb_config kc;
+        kb_config_default(&kc);
+        kc.max_range = config.max_range;
+        kc.deskew = 0;
+        kb_pipeline *twin = nullptr;
+        if (kb_pipeline_create(&kc, &twin) != KB_OK) throw std::runtime_error(kb_last_error());
         std::vector<Eigen::Vector3d> points;
         for (int i = 0; i < 4000; ++i) {  // a coarse ring of walls
             const double a = 0.0015707963267948967 * i;
@@ -21,8 +27,19 @@ int main() {
             std::printf("frame %d: %zu preprocessed, %zu keypoints, t = (%.3g %.3g %.3g)\n", k, frame.size(), keypoints.size(),
                         pose.matrix()(0, 3), pose.matrix()(1, 3), pose.matrix()(2, 3));
             if (frame.size() != points.size() || keypoints.empty()) return 2;
-            if (__builtin_fabs(pose.matrix()(0, 3)) > 1e-6) return 3;  // the sensor did not move
+            // the same frame through the plain C-ABI on a second pipeline: the adaptor adds nothing of its own
+            if (kb_pipeline_register_frame(twin, points.front().data(), points.size(), nullptr, 0) != KB_OK) return 5;
+            double M[16];
+            if (kb_pipeline_pose(twin, M) != KB_OK) return 5;
+            for (int i = 0; i < 4; ++i)
+                for (int j = 0; j < 4; ++j)
+                    if (pose.matrix()(i, j) != M[4 * i + j]) {
+                        std::printf("pose(%d,%d) = %.17g, C-ABI %.17g\n", i, j, pose.matrix()(i, j), M[4 * i + j]);
+                        return 3;
+                    }
+            if (__builtin_fabs(pose.matrix()(0, 3)) > 0.05) return 6;  // the sensor did not move (ICP stops at |dx| < 1e-4 per step)
         }
+        kb_pipeline_destroy(twin);
         const auto [source, downsample] = icp.Voxelize(points);
         if (icp.LocalMap().empty() || source.empty() || downsample.size() < source.size()) return 4;
         std::puts("adaptor ok");

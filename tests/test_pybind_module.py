@@ -120,7 +120,6 @@ def test_reference_python_layer_imports_on_top_of_it(mod):
 
 
 @pytest.mark.gpu
-@pytest.mark.xfail(strict=False, reason="binding layer written after this round's GPU budget was spent: not yet run on a GPU")
 def test_every_bound_call_equals_the_ctypes_mirror(mod):
     import kiss_icp_b200 as K
     from kiss_icp_b200 import synthetic

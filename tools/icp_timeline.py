@@ -1,0 +1,32 @@
+"""Developer aid (GPU box): per-phase and per-ICP-iteration times of k_register_frame on a KITTI-shape stream,
+from the in-kernel %globaltimer stamps (they cost ~1 us each, so these are upper bounds).
+usage: python tools/icp_timeline.py [prime=100] [frames=8]"""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import kiss_icp_b200 as K
+from kiss_icp_b200 import _native as N, synthetic
+
+prime = int(sys.argv[1]) if len(sys.argv) > 1 else 100
+frames = int(sys.argv[2]) if len(sys.argv) > 2 else 8
+L = synthetic.kitti_shape(seed=0, device="cuda")
+scans = [L.scan(k) for k in range(prime + frames)]
+g = K.KissICP(K.load_config())
+for p, t in scans[:prime]:
+    g.register_frame(p, t, return_clouds=False)
+g.set_profiling(True)
+names = ["pre", "ds1", "ds2", "icp", "map", "epi"]
+for p, t in scans[prime:]:
+    g.register_frame(p, t, return_clouds=False)
+    ns = np.zeros(64)
+    N.check(N.lib().kb_pipeline_debug_stamps(g._h, N.ptr(ns), 64))
+    it = g.last_iterations
+    st = ns[41:41 + min(it, 20)]
+    d = np.diff(st) * 1e-3
+    print("iters", it, "phases_us", dict(zip(names, np.round(g.last_profile_us, 1))),
+          "iter_us first", np.round(d[:3], 2), "median", round(float(np.median(d)), 2) if len(d) else None,
+          "env", os.environ.get("KB_ICP_TEAM_Q", "default"))
