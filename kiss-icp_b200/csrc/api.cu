@@ -758,13 +758,35 @@ static int nn_launch(kb_map *map, const double *d_q, size_t n, double *d_p, doub
     if (n == 0) return KB_OK;
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, map->ex->device);
+    // default: candidate blocks staged by bulk async copies (needs 16-byte aligned blocks: an even max_points_per_voxel
+    // <= 32); KB_NN_KERNEL=regs selects the register-staged kernel (A/B, odd capacities)
+    static const bool want_bulk = [] {
+        const char *e = std::getenv("KB_NN_KERNEL");
+        return !(e && std::strcmp(e, "regs") == 0);
+    }();
+    const bool bulk = want_bulk && map->cap <= static_cast<unsigned>(NN_FLAT_CAP) && (map->cap & 1u) == 0;
     const int threads = 256;
     const size_t want = (n * 32 + threads - 1) / threads;
-    const unsigned blocks = static_cast<unsigned>(std::min<size_t>(want, static_cast<size_t>(sms) * 4));  // 4 CTAs/SM, grid-stride
-    if (d_cand)
-        k_nn_query<true><<<blocks, threads, 0, map->ex->stream>>>(map->view(), d_q, n, d_p, d_d, d_cand);
-    else
-        k_nn_query<false><<<blocks, threads, 0, map->ex->stream>>>(map->view(), d_q, n, d_p, d_d, nullptr);
+    if (bulk) {
+        const size_t smem = static_cast<size_t>(NNB_WARPS) * NNB_BUF;
+        const void *k0 = reinterpret_cast<const void *>(&k_nn_query_bulk<false>), *k1 = reinterpret_cast<const void *>(&k_nn_query_bulk<true>);
+        for (const void *k : {k0, k1})
+            if (std::find(map->ex->smem_opted.begin(), map->ex->smem_opted.end(), k) == map->ex->smem_opted.end()) {
+                CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+                map->ex->smem_opted.push_back(k);
+            }
+        const unsigned blocks = static_cast<unsigned>(std::min<size_t>(want, static_cast<size_t>(sms) * 3));  // 3 CTAs/SM, grid-stride
+        if (d_cand)
+            k_nn_query_bulk<true><<<blocks, threads, smem, map->ex->stream>>>(map->view(), d_q, n, d_p, d_d, d_cand);
+        else
+            k_nn_query_bulk<false><<<blocks, threads, smem, map->ex->stream>>>(map->view(), d_q, n, d_p, d_d, nullptr);
+    } else {
+        const unsigned blocks = static_cast<unsigned>(std::min<size_t>(want, static_cast<size_t>(sms) * 4));  // 4 CTAs/SM, grid-stride
+        if (d_cand)
+            k_nn_query<true><<<blocks, threads, 0, map->ex->stream>>>(map->view(), d_q, n, d_p, d_d, d_cand);
+        else
+            k_nn_query<false><<<blocks, threads, 0, map->ex->stream>>>(map->view(), d_q, n, d_p, d_d, nullptr);
+    }
     ++map->ex->launches;
     CK(cudaGetLastError());
     return KB_OK;

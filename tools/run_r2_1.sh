@@ -8,6 +8,9 @@ echo "== timeline team"
 timeout -k 10 200 python tools/icp_timeline.py 100 6 > gpurun_out/r2_tl_team.log 2>&1; echo rc=$?; tail -7 gpurun_out/r2_tl_team.log
 echo "== timeline legacy"
 KB_ICP_TEAM_Q=0 timeout -k 10 200 python tools/icp_timeline.py 100 6 > gpurun_out/r2_tl_legacy.log 2>&1; echo rc=$?; tail -7 gpurun_out/r2_tl_legacy.log
+echo "== nn A/B (checksums must agree)"
+timeout -k 10 200 python tools/nn_ab.py 2>&1 | tail -1 | sed 's/^/bulk: /'
+KB_NN_KERNEL=regs timeout -k 10 200 python tools/nn_ab.py 2>&1 | tail -1 | sed 's/^/regs: /'
 echo "== bench team"
 timeout -k 10 400 python bench.py --steps 200 --warmup 10 --no-nn --no-cpu > gpurun_out/r2_b_team.json 2> gpurun_out/r2_b_team.err; echo rc=$?
 echo "== bench legacy"
