@@ -3,9 +3,10 @@
 // Sophus exist (they do on a ROS machine, not in this repo's build image: tests/test_cpp_adaptor.py compiles it
 // against two minimal stand-in headers) and link libkiss_icp_b200 instead of kiss_icp_pipeline / kiss_icp_core.
 //
-// Differences a caller can see: pose() / delta() are returned by const reference only (set them with SetPose /
-// SetDelta: the state lives on the device), VoxelMap() is replaced by LocalMap(), and where Sophus would abort on a
-// non-SE(3) matrix a std::invalid_argument is thrown.
+// Differences a caller can see: pose() / delta() also exist in their mutable form (OdometryServer.cpp:162,165 writes
+// through them): the state lives on the device, so a modified value is written back at the next RegisterFrame;
+// VoxelMap() returns the kiss_icp::VoxelHashMap adaptor of core/VoxelHashMap.hpp borrowing the pipeline's map; where
+// Sophus would abort on a non-SE(3) matrix a std::invalid_argument is thrown.
 #pragma once
 
 #include <Eigen/Core>
@@ -14,6 +15,8 @@
 #include <tuple>
 #include <vector>
 
+#include "kiss_icp/core/Registration.hpp"
+#include "kiss_icp/core/VoxelHashMap.hpp"
 #include "kiss_icp_b200.h"
 
 namespace kiss_icp::pipeline {
@@ -37,30 +40,18 @@ class KissICP {
 public:
     using Vector3dVector = std::vector<Eigen::Vector3d>;
     using Vector3dVectorTuple = std::tuple<Vector3dVector, Vector3dVector>;
-    static_assert(sizeof(Eigen::Vector3d) == 3 * sizeof(double), "std::vector<Eigen::Vector3d>::data() must be double[n][3]");
 
-    explicit KissICP(const KISSConfig &c) {
-        kb_config k;
-        kb_config_default(&k);
-        k.voxel_size = c.voxel_size;
-        k.max_range = c.max_range;
-        k.min_range = c.min_range;
-        k.max_points_per_voxel = c.max_points_per_voxel;
-        k.min_motion_th = c.min_motion_th;
-        k.initial_threshold = c.initial_threshold;
-        k.max_num_iterations = c.max_num_iterations;
-        k.convergence_criterion = c.convergence_criterion;
-        k.max_num_threads = c.max_num_threads;
-        k.deskew = c.deskew ? 1 : 0;
-        Check(kb_pipeline_create(&k, &p_));
-        Refresh();
+    explicit KissICP(const KISSConfig &c) : p_(Create(c)), local_map_(VoxelHashMap::Borrowed{}, kb_pipeline_voxel_map(p_)) { Refresh(); }
+    ~KissICP() {
+        local_map_.map_handle_ = nullptr;  // borrowed from the pipeline, which owns and frees it
+        kb_pipeline_destroy(p_);
     }
-    ~KissICP() { kb_pipeline_destroy(p_); }
     KissICP(const KissICP &) = delete;
     KissICP &operator=(const KissICP &) = delete;
 
     // RegisterFrame(frame, timestamps) -> (preprocessed frame, source), KissICP.cpp:35-68
     Vector3dVectorTuple RegisterFrame(const Vector3dVector &frame, const std::vector<double> &timestamps) {
+        WriteBack();
         Check(kb_pipeline_register_frame(p_, Data(frame), frame.size(), timestamps.data(), timestamps.size()));
         size_t np = 0, ns = 0;
         Check(kb_pipeline_last_cloud_sizes(p_, &np, &ns));
@@ -78,59 +69,70 @@ public:
         ds.resize(nd);
         return {std::move(src), std::move(ds)};
     }
-    Vector3dVector LocalMap() const {
-        kb_map *m = kb_pipeline_voxel_map(p_);
-        size_t n = 0;
-        Check(kb_map_pointcloud(m, nullptr, 0, &n));
-        Vector3dVector out(n);
-        if (n) Check(kb_map_pointcloud(m, MutableData(out), n, &n));
-        return out;
-    }
+    std::vector<Eigen::Vector3d> LocalMap() const { return local_map_.Pointcloud(); }
+
+    const VoxelHashMap &VoxelMap() const { return local_map_; }
+    VoxelHashMap &VoxelMap() { return local_map_; }
+
     const Sophus::SE3d &pose() const { return last_pose_; }
+    Sophus::SE3d &pose() { return last_pose_; }  // written back to the device at the next RegisterFrame
+
     const Sophus::SE3d &delta() const { return last_delta_; }
-    void SetPose(const Sophus::SE3d &T) {
-        double M[16];
-        ToRowMajor(T, M);
-        Check(kb_pipeline_set_pose(p_, M));
-        Refresh();
-    }
-    void SetDelta(const Sophus::SE3d &T) {
-        double M[16];
-        ToRowMajor(T, M);
-        Check(kb_pipeline_set_delta(p_, M));
-        Refresh();
-    }
+    Sophus::SE3d &delta() { return last_delta_; }
 
 private:
-    static const double *Data(const Vector3dVector &v) { return v.empty() ? nullptr : v.front().data(); }
-    static double *MutableData(Vector3dVector &v) { return v.empty() ? nullptr : v.front().data(); }
-    static void Check(int st) {
-        if (st == KB_OK) return;
-        if (st == KB_ERR_OUT_OF_RANGE) throw std::out_of_range(kb_last_error());  // timestamps.at(idx), Preprocessing.cpp:76-77
-        if (st == KB_ERR_NOT_SE3) throw std::invalid_argument(kb_last_error());
-        throw std::runtime_error(kb_last_error());
+    static const double *Data(const Vector3dVector &v) { return b200_detail::Data(v); }
+    static double *MutableData(Vector3dVector &v) { return b200_detail::MutableData(v); }
+    static void Check(int st) { b200_detail::Check(st); }
+    static kb_pipeline *Create(const KISSConfig &c) {
+        kb_config k;
+        kb_config_default(&k);
+        k.voxel_size = c.voxel_size;
+        k.max_range = c.max_range;
+        k.min_range = c.min_range;
+        k.max_points_per_voxel = c.max_points_per_voxel;
+        k.min_motion_th = c.min_motion_th;
+        k.initial_threshold = c.initial_threshold;
+        k.max_num_iterations = c.max_num_iterations;
+        k.convergence_criterion = c.convergence_criterion;
+        k.max_num_threads = c.max_num_threads;
+        k.deskew = c.deskew ? 1 : 0;
+        kb_pipeline *p = nullptr;
+        Check(kb_pipeline_create(&k, &p));
+        return p;
     }
-    static Sophus::SE3d FromRowMajor(const double M[16]) {  // the C-ABI is row-major, Eigen's default is column-major
-        Eigen::Matrix4d E;
+    static bool Same(const Sophus::SE3d &a, const Sophus::SE3d &b) {
+        const Eigen::Matrix4d A = a.matrix(), B = b.matrix();
         for (int i = 0; i < 4; ++i)
-            for (int j = 0; j < 4; ++j) E(i, j) = M[4 * i + j];
-        return Sophus::SE3d(E);
-    }
-    static void ToRowMajor(const Sophus::SE3d &T, double M[16]) {
-        const Eigen::Matrix4d E = T.matrix();
-        for (int i = 0; i < 4; ++i)
-            for (int j = 0; j < 4; ++j) M[4 * i + j] = E(i, j);
+            for (int j = 0; j < 4; ++j)
+                if (A(i, j) != B(i, j)) return false;
+        return true;
     }
     void Refresh() {
         double M[16];
         Check(kb_pipeline_pose(p_, M));
-        last_pose_ = FromRowMajor(M);
+        last_pose_ = synced_pose_ = b200_detail::FromRowMajor(M);
         Check(kb_pipeline_delta(p_, M));
-        last_delta_ = FromRowMajor(M);
+        last_delta_ = synced_delta_ = b200_detail::FromRowMajor(M);
+    }
+    void WriteBack() {  // the caller assigned through the mutable pose() / delta() since the last call
+        double M[16];
+        if (!Same(last_pose_, synced_pose_)) {
+            b200_detail::ToRowMajor(last_pose_, M);
+            Check(kb_pipeline_set_pose(p_, M));
+            synced_pose_ = last_pose_;
+        }
+        if (!Same(last_delta_, synced_delta_)) {
+            b200_detail::ToRowMajor(last_delta_, M);
+            Check(kb_pipeline_set_delta(p_, M));
+            synced_delta_ = last_delta_;
+        }
     }
 
     kb_pipeline *p_ = nullptr;
+    VoxelHashMap local_map_;  // borrows the pipeline's map
     Sophus::SE3d last_pose_, last_delta_;
+    Sophus::SE3d synced_pose_, synced_delta_;  // what the device holds
 };
 
 }  // namespace kiss_icp::pipeline

@@ -1,20 +1,24 @@
 #!/usr/bin/env python
-"""bench.py — scans/s of KissICP::RegisterFrame on KITTI-shape synthetic streams.
+"""bench.py — scans/s of KissICP::RegisterFrame on synthetic LiDAR streams (BASELINE.json configs[1], [2], [3]).
 
 Contract (driver):  python bench.py --gpus N --steps K --warmup W [--impl reference]
-  * a "step" = one scan (64 x 1024 rays, ~65k points) registered by one pipeline, i.e. one pass
-    of the hot path (pipeline/KissICP.cpp:35-68). Workload = BASELINE.json configs[1]
-    ("KITTI-00-shape synthetic stream on 1xB200"); at N GPUs every rank runs its own sequence
-    (seed = rank) — weak scaling, no collective on the data path, poses gathered at the end.
-  * before the W warm-up steps each pipeline is PRIMED with --prime scans (setup, untimed) so the
-    timed region sees a steady-state local map instead of an almost empty one.
-  * value  = scans/s with the K timed scans already resident in HBM (kb_pipeline_register_frame_dev)
-  * e2e    = scans/s through the host-facing C-ABI call (kb_pipeline_register_frame) with pinned
-    HOST buffers: H2D of the scan and D2H of the result inside the timed region.
-  * --impl reference times the reference's CPU algorithm (the oracle port, OpenMP over the host
-    cores; the real TBB/Eigen build is impossible offline — see DESIGN.md) on the same stream.
-Timing: CUDA events on the stream the kernels are launched on, barrier + synchronize on both
-sides, max over ranks. One JSON line on stdout (rank 0).
+  * a "step" = one scan registered by one pipeline, i.e. one pass of the hot path (pipeline/KissICP.cpp:35-68).
+    Default workload = BASELINE.json configs[1] ("KITTI-00-shape synthetic stream on 1xB200", 64 x 1024 rays);
+    --workload ouster128 = configs[2] (128 x 1024 rays, 0.3 m voxels, per-column stamps, deskew). At N GPUs every rank
+    runs its own sequence (seed = rank) — weak scaling, no collective on the data path, poses gathered at the end.
+  * before the W warm-up steps each pipeline is PRIMED with --prime scans (setup, untimed) so the timed region
+    sees a steady-state local map instead of an almost empty one.
+  * a timed WINDOW is exactly K consecutive scans of the stream, bracketed by barrier + synchronize and timed with
+    CUDA events on the launching stream. The stream simply continues for --repeats R windows (R*K scans in all);
+    every number in the line is the MEDIAN window (per rank), then the max over ranks; min/max and the per-rank
+    medians are in `windows`. (One 20-scan window is ~3 ms: a single host hiccup used to move the result by 2x.)
+  * value  = scans/s with the scans already resident in HBM, frames queued (kb_pipeline_register_frames, device layout)
+  * e2e    = scans/s through the host-facing C-ABI call with pinned HOST buffers: H2D of every scan and D2H of every
+             result inside the timed region (kb_pipeline_register_frames, host layout); `blocking_calls` is the same
+             with one blocking kb_pipeline_register_frame call per scan (the reference's call shape).
+  * --impl reference times the reference's CPU algorithm (the oracle port, OpenMP over the host cores; the real
+    TBB/Eigen build is impossible offline — see DESIGN.md) on the same stream, same windows.
+One JSON line on stdout (rank 0).
 """
 from __future__ import annotations
 
@@ -32,23 +36,53 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-WORKLOAD = "KITTI-00-shape synthetic stream (64x1024 rays, ~65k pts/scan, voxel 1.0 m, no stamps), 1 sequence per GPU"
-METRIC = "scans/sec (65k-pt KITTI-shape clouds)"
+WORKLOADS = {
+    "kitti": {"name": "KITTI-00-shape synthetic stream (64x1024 rays, ~65k pts/scan, voxel 1.0 m, no stamps), 1 sequence per GPU",
+              "metric": "scans/sec (65k-pt KITTI-shape clouds)"},
+    "ouster128": {"name": "Ouster-128-shape synthetic stream (128x1024 rays, ~131k pts/scan, voxel 0.3 m, per-column stamps, deskew), 1 sequence per GPU",
+                  "metric": "scans/sec (131k-pt Ouster-128-shape clouds, 0.3 m voxels)"},
+}
 
 
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20, help="scans per timed window")
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--repeats", type=int, default=9, help="timed windows of --steps scans each (the stream continues); medians are reported")
     ap.add_argument("--prime", type=int, default=100, help="scans registered before warm-up (steady-state map)")
+    ap.add_argument("--workload", default="kitti", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-sample", type=int, default=60, help="scans timed by the cpu_baseline leg")
-    ap.add_argument("--streams", type=int, default=0, help="extra leg: S independent sequences per GPU on S streams")
+    ap.add_argument("--streams", type=int, default=4, help="multi_stream leg: S independent sequences per GPU (0 = skip)")
     ap.add_argument("--no-nn", action="store_true", help="skip the NN-kernel roofline leg")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-extra", action="store_true", help="skip the f32 / profile / trajectory side legs")
     ap.add_argument("--no-clocks", action="store_true", help="diagnostic: do not sample clocks (an invalid run by the bench contract)")
     return ap.parse_args()
+
+
+def make_lidar(workload, seed, device):
+    from kiss_icp_b200 import synthetic
+    return synthetic.ouster128_shape(seed=seed, device=device) if workload == "ouster128" else synthetic.kitti_shape(seed=seed, device=device)
+
+
+def pipeline_config(workload):
+    """KISSConfig of the workload: the reference's defaults; Ouster-128: 0.3 m voxels"""
+    import kiss_icp_b200 as K
+    return K.load_config(voxel_size=0.3) if workload == "ouster128" else K.load_config()
+
+
+def oracle_kwargs(workload):
+    return {"voxel_size": 0.3} if workload == "ouster128" else {}
+
+
+def common_config(args, world):
+    """identical in both arms (the driver compares the two dicts)"""
+    return {"workload": WORKLOADS[args.workload]["name"], "prime_scans": args.prime, "sequences": world,
+            "windows": args.repeats, "steps_per_window": args.steps,
+            "statistic": "median over the windows of the per-window scans/s (each window = exactly --steps consecutive scans); max over ranks of the per-rank median time",
+            "l2": "every step consumes a new scan (1.5 MB KITTI / 3 MB Ouster); the local map (the state of the stream) is legitimately L2-resident across steps"}
 
 
 # ----------------------------------------------------------------------------- clocks sampler
@@ -62,7 +96,7 @@ class ClockSampler:
              "clocks_event_reasons.sw_power_cap")
     BITS = {"sw_power_cap": 0x4, "hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
 
-    def __init__(self, index, uuid=None, period=0.05):
+    def __init__(self, index, uuid=None, period=0.01):
         self.index, self.uuid, self.period = index, uuid, period
         self.rows, self.proc, self.nvml, self.first = [], None, None, 0
         self.max_mhz, self.stop_flag, self.source, self.query_ms = None, False, None, []
@@ -145,12 +179,12 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------- reference arm
-def best_thread_count(O, scans, candidates):
+def best_thread_count(O, scans, candidates, **kw):
     """the oracle's OpenMP regions are tiny (1-2k points per ICP iteration): pick the thread count
     that makes the REFERENCE fastest on this box, so the baseline is not handicapped"""
     best, best_t = None, None
     for nt in candidates:
-        icp = O.KissICP(max_num_threads=nt)
+        icp = O.KissICP(max_num_threads=nt, **kw)
         for p, t in scans[:4]:
             icp.register_frame(p, t, want_clouds=False)
         t0 = time.perf_counter()
@@ -164,51 +198,57 @@ def best_thread_count(O, scans, candidates):
 
 def thread_candidates():
     n = os.cpu_count() or 1
-    c = sorted({min(n, x) for x in (4, 8, 16, 32, 64, n)})
-    return c
+    return sorted({min(n, x) for x in (4, 8, 16, 32, 64, n)})
 
 
 def run_reference(args, rank, world):
     """the reference's CPU implementation of the path on the host cores (oracle port). At --gpus N the job is
     N independent sequences (one per GPU in our arm): here they run concurrently on the host, each with its
-    share of the cores, and value = N * steps / wall."""
+    share of the cores. Same windows as our arm: R windows of K scans, value = N * K / median window time."""
     if rank != 0:
         return
     from concurrent.futures import ThreadPoolExecutor
-    from kiss_icp_b200 import synthetic
     from oracle import oracle as O
     import torch
     dev = "cuda" if torch.cuda.is_available() else "cpu"
     nseq = max(1, args.gpus)
-    n_total = args.prime + args.warmup + args.steps
+    R = max(1, min(args.repeats, 5))  # bounded: the whole run must end within a few minutes on a slow host
+    head = args.prime + args.warmup
+    n_total = head + R * args.steps
+    kw = oracle_kwargs(args.workload)
     streams = []
     for sid in range(nseq):
-        lidar = synthetic.kitti_shape(seed=sid, device=dev)
+        lidar = make_lidar(args.workload, sid, dev)
         streams.append([lidar.scan(k) for k in range(n_total)])
     ncpu = os.cpu_count() or 1
-    best = best_thread_count(O, streams[0], thread_candidates())
+    best = best_thread_count(O, streams[0], thread_candidates(), **kw)
     nt = max(1, min(best, ncpu // nseq))
-    icps = [O.KissICP(max_num_threads=nt) for _ in range(nseq)]
+    icps = [O.KissICP(max_num_threads=nt, **kw) for _ in range(nseq)]
 
     def run(sid, lo, hi):
         for p, t in streams[sid][lo:hi]:
             icps[sid].register_frame(p, t, want_clouds=False)  # ctypes releases the GIL during the call
 
+    win = []
     with ThreadPoolExecutor(nseq) as ex:
-        list(ex.map(lambda sid: run(sid, 0, args.prime + args.warmup), range(nseq)))
-        t0 = time.perf_counter()
-        list(ex.map(lambda sid: run(sid, args.prime + args.warmup, n_total), range(nseq)))
-        dt = time.perf_counter() - t0
+        list(ex.map(lambda sid: run(sid, 0, head), range(nseq)))
+        for r in range(R):
+            t0 = time.perf_counter()
+            list(ex.map(lambda sid: run(sid, head + r * args.steps, head + (r + 1) * args.steps), range(nseq)))
+            win.append(time.perf_counter() - t0)
+    dt = float(np.median(win))
     val = nseq * args.steps / dt
-    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "scans/s", "n_gpus": args.gpus,
+    cfg = common_config(args, nseq)
+    cfg["windows"] = R
+    line = {"impl": "reference", "metric": WORKLOADS[args.workload]["metric"], "value": val, "unit": "scans/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "prime_scans": args.prime, "sequences": nseq,
-                       "note": "reference CPU path = dependency-free restatement of cpp/kiss_icp (oracle port, OpenMP "
-                               "for TBB); the real TBB/Eigen build needs network-fetched deps. N sequences run "
-                               "concurrently on the host cores."},
+            "config": cfg,
+            "windows": {"ms": [w * 1e3 for w in win]},
+            "note": "reference CPU path = dependency-free restatement of cpp/kiss_icp (oracle port, OpenMP for TBB); the real "
+                    "TBB/Eigen build needs network-fetched deps. N sequences run concurrently on the host cores.",
             "cpu_baseline": {"value": val, "unit": "scans/s", "cores": nt * nseq, "kind": "port",
-                             "sample": f"{nseq} x {args.steps} scans after {args.prime + args.warmup} untimed; {nt} OpenMP "
+                             "sample": f"{nseq} x {R} windows of {args.steps} scans after {head} untimed; {nt} OpenMP "
                                        f"threads per sequence (fastest single-sequence count of {thread_candidates()} "
                                        f"capped at cpus/sequences) on {ncpu} cpus"},
             "e2e": {"value": val, "unit": "scans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -226,7 +266,7 @@ def main():
     import torch
     import torch.distributed as dist
     import kiss_icp_b200 as K
-    from kiss_icp_b200 import _native as N, sharding, synthetic
+    from kiss_icp_b200 import _native as N, sharding
 
     if not torch.cuda.is_available() or N.lib().kb_device_count() < 1:
         raise SystemExit("bench.py needs a CUDA device: kiss_icp_b200 has no CPU fallback")
@@ -246,17 +286,28 @@ def main():
         sampler.start()  # started long before the timed regions; samples before mark() are dropped
 
     seq = sharding.sequences_of_rank(rank, world, world)[0]
-    lidar = synthetic.kitti_shape(seed=seq, device=dev)
-    n_total = args.prime + args.warmup + args.steps
-    scans_dev = [lidar.scan_torch(k)[0].contiguous() for k in range(n_total)]
-    empty_ts = np.empty(0)
+    lidar = make_lidar(args.workload, seq, dev)
+    Kw, R = args.steps, max(1, args.repeats)
+    head = args.prime + args.warmup
+    n_total = head + R * Kw
+    scans_dev = []
+    for k in range(n_total):
+        p, t = lidar.scan_torch(k)
+        scans_dev.append((p.contiguous(), t.contiguous()))
     L = N.lib()
+    cfg = pipeline_config(args.workload)
 
     def make_pipeline():
-        return K.KissICP(K.load_config())
+        return K.KissICP(cfg)
 
-    def reg_dev(icp, t):
-        N.check(L.kb_pipeline_register_frame_dev(icp._h, C.c_void_p(t.data_ptr()), t.shape[0], None, 0))
+    def tsp(t):
+        return C.c_void_p(t.data_ptr()) if t.numel() else None
+
+    def reg_dev(icp, s):
+        N.check(L.kb_pipeline_register_frame_dev(icp._h, C.c_void_p(s[0].data_ptr()), s[0].shape[0], tsp(s[1]), s[1].numel()))
+
+    def reg_host(icp, s):
+        N.check(L.kb_pipeline_register_frame(icp._h, C.c_void_p(s[0].data_ptr()), s[0].shape[0], tsp(s[1]), s[1].numel()))
 
     def launches(icp):
         c = C.c_ulonglong(0)
@@ -270,32 +321,39 @@ def main():
 
     def primed(n_blocking):
         icp = make_pipeline()
-        for t in scans_dev[:n_blocking]:
-            reg_dev(icp, t)
+        for s in scans_dev[:n_blocking]:
+            reg_dev(icp, s)
         return icp
 
-    def queued(icp, tensors, layout):
+    def queued(icp, scans, layout):
         """KissICP.register_frames on raw addresses: the whole list is queued on the device, copy of frame k+1
         overlaps the registration of frame k, every frame's result (pose + counters) is read back behind the queue"""
-        k = len(tensors)
-        return icp._register_frames_raw([t.data_ptr() for t in tensors], [t.shape[0] for t in tensors], [None] * k, [0] * k, layout)
+        return icp._register_frames_raw([s[0].data_ptr() for s in scans], [s[0].shape[0] for s in scans],
+                                        [s[1].data_ptr() if s[1].numel() else None for s in scans], [s[1].numel() for s in scans], layout)
 
-    def timed_region(fn):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def window(fn):
         barrier()
         e0.record(stream)
         fn()
         e1.record(stream)
         barrier()
-        return sharding.max_over_ranks(e0.elapsed_time(e1), dev)
+        return e0.elapsed_time(e1)
 
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    warm = scans_dev[args.prime:args.prime + args.warmup]
-    timed = scans_dev[args.prime + args.warmup:]
-    prof = np.zeros((len(timed), 6))
-    iters = np.zeros(len(timed))
-    work = np.zeros((len(timed), 2))
-    npts = np.zeros(len(timed))
-    poses_local = []
+    def timed_windows(fn_of_window):
+        """R windows of K scans each -> (this rank's window times [ms], median over windows maxed over ranks)"""
+        ms = [window(lambda r=r: fn_of_window(r)) for r in range(R)]
+        return ms, sharding.max_over_ranks(float(np.median(ms)), dev)
+
+    def win_scans(pool, r):
+        return pool[head - head_of(pool) + r * Kw: head - head_of(pool) + (r + 1) * Kw]
+
+    def head_of(pool):  # pools hold either the whole stream or only the timed part
+        return head if len(pool) == n_total else 0
+
+    warm = scans_dev[args.prime:head]
+    legs = {}
 
     # ---------------- value: inputs resident in HBM, frames queued (kb_pipeline_register_frames, device layout)
     icp = primed(args.prime)
@@ -305,48 +363,63 @@ def main():
     if rank == 0:
         sampler.mark()
     l0 = launches(icp)
-    ms_max = timed_region(lambda: queued(icp, timed, 2))
-    gpu_launches = launches(icp) - l0
-    ms_dev = ms_max
-    value = world * args.steps / (ms_max * 1e-3)
+    legs["value"] = timed_windows(lambda r: queued(icp, win_scans(scans_dev, r), 2))
+    gpu_launches = (launches(icp) - l0) // R
+    ms_value = legs["value"][1]
+    value = world * Kw / (ms_value * 1e-3)
 
     # ---------------- the same with one blocking RegisterFrame call per scan (the reference's call shape)
-    icp_b = primed(args.prime + args.warmup)
-    wall_dev = np.zeros(len(timed))
+    icp_b = primed(head)
+    wall_dev = []
 
-    def blocking_dev():
-        for i, t in enumerate(timed):
+    def blocking_dev(r):
+        for s in win_scans(scans_dev, r):
             t0 = time.perf_counter()
-            reg_dev(icp_b, t)
-            wall_dev[i] = time.perf_counter() - t0
-    ms_dev_blocking = timed_region(blocking_dev)
+            reg_dev(icp_b, s)
+            wall_dev.append(time.perf_counter() - t0)
+    legs["blocking_resident"] = timed_windows(blocking_dev)
 
     # ---------------- e2e: host-facing call, pinned host buffers, H2D + D2H of every step inside the timed region
-    pinned_warm = [t.cpu().pin_memory() for t in warm]
-    pinned = [t.cpu().pin_memory() for t in timed]
-    h2d = float(np.mean([p.numel() * 8 for p in pinned]))
+    def to_pinned(s):
+        return (s[0].cpu().pin_memory(), s[1].cpu().pin_memory() if s[1].numel() else s[1].cpu())
+    pinned_warm = [to_pinned(s) for s in warm]
+    pinned = [to_pinned(s) for s in scans_dev[head:]]
+    h2d = float(np.mean([p.numel() * 8 + t.numel() * 8 for p, t in pinned]))
     icp2 = primed(args.prime)
     queued(icp2, pinned_warm, 0)
-    e2e_poses = []
-    ms_e2e = timed_region(lambda: e2e_poses.append(queued(icp2, pinned, 0)))
-    e2e_value = world * args.steps / (ms_e2e * 1e-3)
+    e2e_last = []
+    legs["e2e"] = timed_windows(lambda r: e2e_last.append(queued(icp2, win_scans(pinned, r), 0)[-1]))
+    ms_e2e = legs["e2e"][1]
+    e2e_value = world * Kw / (ms_e2e * 1e-3)
     # blocking form: kb_pipeline_register_frame per scan
-    icp2b = primed(args.prime + args.warmup)
-    wall_e2e = np.zeros(len(pinned))
+    icp2b = primed(head)
+    wall_e2e = []
 
-    def blocking_e2e():
-        for i, p in enumerate(pinned):
+    def blocking_e2e(r):
+        for s in win_scans(pinned, r):
             t0 = time.perf_counter()
-            N.check(L.kb_pipeline_register_frame(icp2b._h, C.c_void_p(p.data_ptr()), p.shape[0], None, 0))
-            wall_e2e[i] = time.perf_counter() - t0
-    ms_e2e_blocking = timed_region(blocking_e2e)
-    # ---------------- profiling pass (untimed): the same scans once more with the in-kernel phase timestamps ON
+            reg_host(icp2b, s)
+            wall_e2e.append(time.perf_counter() - t0)
+    legs["blocking_e2e"] = timed_windows(blocking_e2e)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # the four pipelines saw identical inputs -> identical trajectories (determinism check)
+    same = bool(np.array_equal(icp.last_pose, icp2.last_pose) and np.array_equal(icp_b.last_pose, icp2b.last_pose)
+                and np.array_equal(icp.last_pose, icp_b.last_pose) and np.array_equal(e2e_last[-1], icp2.last_pose))
+
+    # ---------------- profiling pass (untimed): one window once more with the in-kernel phase timestamps ON
     # (they cost ~1 us each on the kernel's critical path, so the timed passes above run without them)
-    icp4 = primed(args.prime + args.warmup)
+    prof_n = Kw * min(R, 3)
+    prof = np.zeros((prof_n, 6))
+    iters = np.zeros(prof_n)
+    work = np.zeros((prof_n, 2))
+    npts = np.zeros(prof_n)
+    poses_local = []
+    icp4 = primed(head)
     icp4.set_profiling(True)
-    icp4.start_history(len(timed))
-    for t in timed:
-        reg_dev(icp4, t)
+    icp4.start_history(prof_n)
+    for s in scans_dev[head:head + prof_n]:
+        reg_dev(icp4, s)
     for i, st in enumerate(icp4.history()):
         prof[i] = list(st.phase_us)
         iters[i] = st.iterations
@@ -354,31 +427,38 @@ def main():
         npts[i] = st.n_points_in
         poses_local.append(np.array(st.pose).reshape(4, 4))
     # ---------------- e2e, float32 ingestion (KITTI .bin / PointCloud2 are float32; the scans are fp32-representable)
-    icp3 = primed(args.prime)
-    queued(icp3, [p.to(torch.float32).pin_memory() for p in pinned_warm], 1)
-    pinned32 = [p.to(torch.float32).pin_memory() for p in pinned]
-    ms_e2e32 = timed_region(lambda: queued(icp3, pinned32, 1))
-    same32 = bool(np.array_equal(icp3.last_pose, icp2.last_pose))
-    clocks = sampler.stop() if rank == 0 else None
+    f32 = None
+    if not args.no_extra:
+        icp3 = primed(args.prime)
+        queued(icp3, [(p.to(torch.float32).pin_memory(), t) for p, t in pinned_warm], 1)
+        pinned32 = [(p.to(torch.float32).pin_memory(), t) for p, t in pinned]
+        legs["e2e_f32"] = timed_windows(lambda r: queued(icp3, win_scans(pinned32, r), 1))
+        f32 = {"value": world * Kw / (legs["e2e_f32"][1] * 1e-3), "unit": "scans/s", "h2d_bytes_per_step": h2d - 12.0 * float(np.mean([p.shape[0] for p, _ in pinned])),
+               "d2h_bytes_per_step": 512.0, "same_trajectory_as_f64": bool(np.array_equal(icp3.last_pose, icp2.last_pose)),
+               "note": "register_frames, float32 host frames (native KITTI/ROS payload), widened on the device"}
     # ---------------- untimed: the whole trajectory from scan 0 (for the drift metrics below)
     traj = None
-    if rank == 0:
+    if rank == 0 and not args.no_extra:
         try:
             traj = queued(make_pipeline(), scans_dev, 2)
         except Exception as e:  # never lose the bench line over a side leg
             traj = None
             print("trajectory pass failed:", e, file=sys.stderr)
-    d2h = 392.0  # sizeof(FrameResult): pose, delta, sigma, counters, stamps
+    d2h = 512.0  # sizeof(FrameResult): pose, delta, sigma, counters, stamps
 
-    # the two pipelines saw identical inputs -> identical trajectories (determinism check)
-    same = bool(np.array_equal(icp.last_pose, icp2.last_pose) and np.array_equal(icp_b.last_pose, icp2b.last_pose)
-                and np.array_equal(icp.last_pose, icp_b.last_pose) and np.array_equal(e2e_poses[0][-1], icp2.last_pose))
     all_poses = sharding.gather_poses(np.array(poses_local), dev)  # NCCL all_gather of the trajectories
+    per_rank = {name: sharding.gather_poses(np.array(ms).reshape(1, -1, 1, 1), dev).reshape(world, -1) for name, (ms, _) in legs.items()}
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
+
+    def win_summary(name):
+        a = per_rank[name]
+        med = np.median(a, axis=1)
+        return {"median_ms_per_rank": [float(x) for x in med], "min_ms": float(a.min()), "max_ms": float(a.max()),
+                "slowest_rank": int(np.argmax(med)), "scans_per_s": world * Kw / (float(med.max()) * 1e-3)}
 
     # ---------------- roofline of the dominant kernel (k_register_frame, one launch per scan)
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -389,89 +469,97 @@ def main():
     # algorithmic bytes per launch (DESIGN.md "algorithmic bytes"): ICP GetClosestNeighbor traffic
     # (24 + 27*16 + 32 per query + 24 per candidate) + one-off streams (raw scan in, result out)
     bytes_per_launch = work[:, 0] * (24 + 27 * 16 + 32) + 24.0 * work[:, 1] + 24.0 * npts + d2h
-    # average launch duration of the dominant kernel: CUDA events over the timed (uninstrumented) region of the
-    # resident-input pass, one launch per step, launches queued back to back
-    kern_us = np.full(len(timed), ms_dev * 1e3 / len(timed))
-    achieved = float(bytes_per_launch.mean() / (kern_us.mean() * 1e-6) / 1e9)
+    kern_us = ms_value * 1e3 / Kw  # CUDA-event time of the median window / launches in it (queued back to back)
+    achieved = float(bytes_per_launch.mean() / (kern_us * 1e-6) / 1e9)
+    traffic, traffic_src = profiled_traffic("r2_register_frame")
     roofline = {"kernel": "k_register_frame (persistent cooperative, 1 launch/scan)", "bound": "hbm",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "algorithmic_bytes_per_launch": float(bytes_per_launch.mean()), "kernel_us": float(kern_us.mean()),
-                "traffic": profiled_traffic("r1_register_frame"),
-                "traffic_source": "profiles/r1_register_frame_ncu_raw_selected.csv (ncu --set full, bytes per launch)",
+                "algorithmic_bytes_per_launch": float(bytes_per_launch.mean()), "kernel_us": float(kern_us),
+                "traffic": traffic, "traffic_source": traffic_src, "traffic_measured_in_this_run": False,
                 "peak_source": peak_src,
-                "note": "latency-bound: ~%.0f ICP iterations x %.0f queries per launch, working set L2-resident; "
-                        "kernel time = CUDA-event time of the timed region / launches; see nn_kernel for the bandwidth-bound NN query"
-                        % (iters.mean(), work[:, 0].mean() / max(iters.mean(), 1))}
+                "note": "latency-bound: ~%.0f ICP iterations x %.0f queries per launch, working set L2-resident; algorithmic bytes "
+                        "count the full 27-voxel neighbourhood of every query and iteration (most are served from the "
+                        "candidate lists); kernel time = CUDA-event time of the median window / launches; see nn_kernel "
+                        "for the bandwidth-bound NN query" % (iters.mean(), work[:, 0].mean() / max(iters.mean(), 1))}
 
-    ms_leg = multi_stream_leg(args, K, N, L, torch, dev, args.streams) if args.streams > 1 else None
+    ms_leg = multi_stream_leg(args, K, N, L, torch, dev, args.streams, cfg) if (args.streams > 1 and not args.no_extra) else None
     nn = None if args.no_nn else nn_leg(K, N, L, torch, dev, peak)
     cpu = None if args.no_cpu else cpu_leg(args, lidar)
     quality = trajectory_quality(lidar, traj, cpu.pop("poses", None) if cpu else None)
+    wall_dev_a, wall_e2e_a = np.array(wall_dev), np.array(wall_e2e)
 
-    line = {"metric": METRIC, "value": value, "unit": "scans/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
+    line = {"metric": WORKLOADS[args.workload]["metric"], "value": value, "unit": "scans/s", "n_gpus": world, "steps": Kw,
+            "warmup": args.warmup, "ms_per_step": ms_value / Kw, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "prime_scans": args.prime, "sequences": world,
-                       "points_per_scan": float(npts.mean()), "icp_iterations_per_scan": float(iters.mean()),
-                       "icp_source_points": float((work[:, 0] / np.maximum(iters, 1)).mean()),
-                       "icp_candidates_per_query": float(work[:, 1].sum() / max(work[:, 0].sum(), 1.0)),
-                       "l2": "every step consumes a new 1.5 MB scan; the local map (the state of the stream) is "
-                             "legitimately L2-resident across steps",
-                       "phase_us_note": "from a separate untimed pass with in-kernel %globaltimer stamps ON (they add ~1 us per phase/iteration)",
-                       "phase_us": dict(zip(["preprocess", "downsample_0.5v", "downsample_1.5v", "icp", "map_update", "epilogue"],
-                                            [float(x) for x in prof.mean(0)])),
-                       "call_latency_ms": {"resident": {"p50": float(np.percentile(wall_dev, 50) * 1e3), "p99": float(np.percentile(wall_dev, 99) * 1e3), "max": float(wall_dev.max() * 1e3)},
-                                           "e2e": {"p50": float(np.percentile(wall_e2e, 50) * 1e3), "p99": float(np.percentile(wall_e2e, 99) * 1e3), "max": float(wall_e2e.max() * 1e3)},
-                                           "over_2ms": {"resident": [[int(i), float(wall_dev[i] * 1e3)] for i in np.nonzero(wall_dev > 2e-3)[0][:8]],
-                                                        "e2e": [[int(i), float(wall_e2e[i] * 1e3)] for i in np.nonzero(wall_e2e > 2e-3)[0][:8]]}},
-                       "deterministic_replay": same, "gathered_trajectories": list(all_poses.shape),
-                       "trajectory_quality": quality},
+            "config": common_config(args, world),
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "scans/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": ms_e2e / args.steps,
+                    "ms_per_step": ms_e2e / Kw,
                     "api": "KissICP.register_frames / kb_pipeline_register_frames: pinned host float64 frames in, poses out; "
-                           "frames queued 3 deep (H2D of scan k+1 overlaps registration of scan k)"},
+                           "frames queued (H2D of scans k+1, k+2 overlaps the registration of scan k, whose launch also runs "
+                           "the front end of scan k+1 on the SMs its ICP team leaves idle)"},
             "blocking_calls": {"note": "one kb_pipeline_register_frame[_dev] call per scan, host waits for every result (the reference's call shape)",
-                               "value_resident": world * args.steps / (ms_dev_blocking * 1e-3),
-                               "e2e": world * args.steps / (ms_e2e_blocking * 1e-3), "unit": "scans/s"},
-            "e2e_f32": {"value": world * args.steps / (ms_e2e32 * 1e-3), "unit": "scans/s", "h2d_bytes_per_step": h2d / 2,
-                        "d2h_bytes_per_step": d2h, "same_trajectory_as_f64": same32,
-                        "note": "register_frames, float32 host frames (native KITTI/ROS payload), widened on the device"},
+                               "value_resident": world * Kw / (legs["blocking_resident"][1] * 1e-3),
+                               "e2e": world * Kw / (legs["blocking_e2e"][1] * 1e-3), "unit": "scans/s"},
+            "e2e_f32": f32,
             "gpu_launches": int(gpu_launches),
+            "windows": {name: win_summary(name) for name in legs},
+            "details": {"points_per_scan": float(npts.mean()), "icp_iterations_per_scan": float(iters.mean()),
+                        "icp_source_points": float((work[:, 0] / np.maximum(iters, 1)).mean()),
+                        "icp_candidates_per_query": float(work[:, 1].sum() / max(work[:, 0].sum(), 1.0)),
+                        "gpu_us_per_scan": {"queued_resident": ms_value * 1e3 / Kw, "queued_e2e": ms_e2e * 1e3 / Kw,
+                                            "blocking_resident": legs["blocking_resident"][1] * 1e3 / Kw, "blocking_e2e": legs["blocking_e2e"][1] * 1e3 / Kw},
+                        "phase_us_note": "from a separate untimed pass of blocking calls with in-kernel %globaltimer stamps ON (they add ~1 us per phase/iteration); "
+                                         "icp = candidate-list pass over the map + iterations on the ICP team",
+                        "phase_us": dict(zip(["preprocess", "downsample_0.5v", "downsample_1.5v", "icp", "map_update", "epilogue"],
+                                             [float(x) for x in prof.mean(0)])),
+                        "call_latency_ms": {"resident": {"p50": float(np.percentile(wall_dev_a, 50) * 1e3), "p99": float(np.percentile(wall_dev_a, 99) * 1e3), "max": float(wall_dev_a.max() * 1e3)},
+                                            "e2e": {"p50": float(np.percentile(wall_e2e_a, 50) * 1e3), "p99": float(np.percentile(wall_e2e_a, 99) * 1e3), "max": float(wall_e2e_a.max() * 1e3)}},
+                        "deterministic_replay": same, "gathered_trajectories": list(all_poses.shape),
+                        "trajectory_quality": quality},
             "roofline": roofline, "nn_kernel": nn, "multi_stream": ms_leg, "cpu_baseline": cpu}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
-def multi_stream_leg(args, K, N, L, torch, dev, S):
+def multi_stream_leg(args, K, N, L, torch, dev, S, cfg):
     """S independent sequences on ONE GPU: S pipelines, S host threads, S CUDA streams, each persistent grid
     sized to 1/S of the SMs. Reported beside the single-stream headline, never instead."""
     import threading
-    from kiss_icp_b200 import synthetic
     sms = torch.cuda.get_device_properties(dev).multi_processor_count
-    n_total = min(args.prime, 40) + args.steps
+    steps = args.steps * min(args.repeats, 3)
+    n_total = min(args.prime, 40) + steps
     data = []
     for sid in range(S):
-        lidar = synthetic.kitti_shape(seed=100 + sid, device=dev)
-        data.append([lidar.scan_torch(k)[0].contiguous() for k in range(n_total)])
+        lidar = make_lidar(args.workload, 100 + sid, dev)
+        data.append([tuple(x.contiguous() for x in lidar.scan_torch(k)) for k in range(n_total)])
     torch.cuda.synchronize()
     pipes = [None] * S
     barrier = threading.Barrier(S + 1)
     walls = [0.0] * S
+    errs = []
 
     def worker(sid):
-        N.check(L.kb_set_device(dev.index or 0))
-        N.check(L.kb_set_stream(None))                 # own non-blocking stream per pipeline
-        N.check(L.kb_set_grid_blocks(max(1, sms // S)))
-        icp = K.KissICP(K.load_config())
-        pipes[sid] = icp
-        for t in data[sid][: n_total - args.steps]:
-            N.check(L.kb_pipeline_register_frame_dev(icp._h, C.c_void_p(t.data_ptr()), t.shape[0], None, 0))
+        try:
+            N.check(L.kb_set_device(dev.index or 0))
+            N.check(L.kb_set_stream(None))                 # own non-blocking stream per pipeline
+            N.check(L.kb_set_grid_blocks(max(1, sms // S)))
+            icp = K.KissICP(cfg)
+            pipes[sid] = icp
+            seqs = data[sid]
+            icp._register_frames_raw([s[0].data_ptr() for s in seqs[: n_total - steps]], [s[0].shape[0] for s in seqs[: n_total - steps]],
+                                     [s[1].data_ptr() if s[1].numel() else None for s in seqs[: n_total - steps]], [s[1].numel() for s in seqs[: n_total - steps]], 2)
+        except Exception as e:
+            errs.append(repr(e))
         barrier.wait()
         t0 = time.perf_counter()
-        for t in data[sid][n_total - args.steps:]:
-            N.check(L.kb_pipeline_register_frame_dev(icp._h, C.c_void_p(t.data_ptr()), t.shape[0], None, 0))
+        try:
+            tail = data[sid][n_total - steps:]
+            pipes[sid]._register_frames_raw([s[0].data_ptr() for s in tail], [s[0].shape[0] for s in tail],
+                                            [s[1].data_ptr() if s[1].numel() else None for s in tail], [s[1].numel() for s in tail], 2)
+        except Exception as e:
+            errs.append(repr(e))
         walls[sid] = time.perf_counter() - t0
         barrier.wait()
 
@@ -484,24 +572,31 @@ def multi_stream_leg(args, K, N, L, torch, dev, S):
     dt = time.perf_counter() - t0
     for t in threads:
         t.join()
-    return {"streams": S, "grid_blocks_per_stream": max(1, sms // S), "scans_per_s": S * args.steps / dt,
-            "ms_per_scan_per_stream": float(np.mean(walls)) / args.steps * 1e3,
-            "note": "aggregate over S concurrent sequences on one GPU, inputs resident in HBM, host wall clock"}
+    N.check(L.kb_set_grid_blocks(0))
+    if errs:
+        return {"streams": S, "error": errs[0]}
+    return {"streams": S, "grid_blocks_per_stream": max(1, sms // S), "scans_per_s": S * steps / dt,
+            "ms_per_scan_per_stream": float(np.mean(walls)) / steps * 1e3,
+            "note": "aggregate over S concurrent sequences on one GPU (S pipelines on S streams, each launch on 1/S of the SMs), "
+                    "inputs resident in HBM, frames queued, host wall clock"}
 
 
 def profiled_traffic(tag):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full summary
-    (profiles/<tag>_ncu_raw_selected.csv, produced by tools/summarize_profiles.py); None when absent."""
+    (profiles/<tag>_ncu_raw_selected.csv, produced by tools/summarize_profiles.py) -> (bytes or None, source)."""
     import csv
-    path = os.path.join(ROOT, "profiles", f"{tag}_ncu_raw_selected.csv")
-    if not os.path.exists(path):
-        return None
-    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-    per_launch = {}
-    for r in csv.DictReader(open(path)):
-        if r["metric"] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
-            per_launch[r["launch"]] = per_launch.get(r["launch"], 0.0) + float(r["value"]) * scale.get(r["unit"], 1.0)
-    return float(np.mean(list(per_launch.values()))) if per_launch else None
+    for t in (tag, tag.replace("r2_", "r1_")):
+        path = os.path.join(ROOT, "profiles", f"{t}_ncu_raw_selected.csv")
+        if not os.path.exists(path):
+            continue
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        per_launch = {}
+        for r in csv.DictReader(open(path)):
+            if r["metric"] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                per_launch[r["launch"]] = per_launch.get(r["launch"], 0.0) + float(r["value"]) * scale.get(r["unit"], 1.0)
+        if per_launch:
+            return float(np.mean(list(per_launch.values()))), f"static: profiles/{t}_ncu_raw_selected.csv (a separate ncu --set full capture, bytes per launch)"
+    return None, None
 
 
 def nn_leg(K, N, L, torch, dev, peak):
@@ -534,9 +629,11 @@ def nn_leg(K, N, L, torch, dev, peak):
             times.append(e0.elapsed_time(e1))
     ms = float(np.mean(times))
     ach = b.value / (ms * 1e-3) / 1e9
-    return {"kernel": "k_nn_query", "map_points": int(stored.shape[0]), "map_voxels": m.num_voxels(), "queries": n_q, "points_per_voxel": float(stored.shape[0]) / max(m.num_voxels(), 1),
+    traffic, traffic_src = profiled_traffic("r2_nn_query")
+    kname = "k_nn_query (register-staged)" if os.environ.get("KB_NN_KERNEL") == "regs" else "k_nn_query_bulk (cp.async.bulk + mbarrier staging)"
+    return {"kernel": kname, "map_points": int(stored.shape[0]), "map_voxels": m.num_voxels(), "queries": n_q, "points_per_voxel": float(stored.shape[0]) / max(m.num_voxels(), 1),
             "algorithmic_bytes": b.value, "bytes_per_query": b.value / n_q, "ms": ms, "achieved": ach, "peak": peak,
-            "unit": "GB/s", "frac": ach / peak, "traffic": profiled_traffic("r1_nn_query"),
+            "unit": "GB/s", "frac": ach / peak, "traffic": traffic, "traffic_source": traffic_src,
             "l2": "flushed (256 MiB write) before every timed launch", "reps": len(times)}
 
 
@@ -568,12 +665,14 @@ def trajectory_quality(lidar, traj, cpu_poses):
 
 
 def cpu_leg(args, lidar):
-    """oracle (port of the reference CPU path) on the host cores, bounded sample of the same stream."""
+    """oracle (port of the reference CPU path) on the host cores, bounded sample of the same stream; best OpenMP
+    thread count and the 1-thread figure."""
     from oracle import oracle as O
-    n = min(args.cpu_sample, args.steps)
+    kw = oracle_kwargs(args.workload)
+    n = min(args.cpu_sample, args.steps * args.repeats)
     scans = [lidar.scan(k) for k in range(args.prime + n)]
-    nt = best_thread_count(O, scans, thread_candidates())
-    icp = O.KissICP(max_num_threads=nt)
+    nt = best_thread_count(O, scans, thread_candidates(), **kw)
+    icp = O.KissICP(max_num_threads=nt, **kw)
     poses = []
     for p, t in scans[:args.prime]:
         icp.register_frame(p, t, want_clouds=False)
@@ -583,7 +682,17 @@ def cpu_leg(args, lidar):
         icp.register_frame(p, t, want_clouds=False)
         poses.append(np.array(icp.pose))
     dt = time.perf_counter() - t0
+    # 1 thread: a short sample on a map primed with 30 scans (bounded: ~1-2 s)
+    n1 = min(12, n)
+    one = O.KissICP(max_num_threads=1, **kw)
+    for p, t in scans[:30]:
+        one.register_frame(p, t, want_clouds=False)
+    t1 = time.perf_counter()
+    for p, t in scans[30:30 + n1]:
+        one.register_frame(p, t, want_clouds=False)
+    dt1 = time.perf_counter() - t1
     return {"poses": np.array(poses), "value": n / dt, "unit": "scans/s", "cores": nt, "kind": "port", "ms_per_scan": dt / n * 1e3,
+            "one_thread": {"value": n1 / dt1, "ms_per_scan": dt1 / n1 * 1e3, "sample": f"{n1} scans after 30 priming scans, 1 OpenMP thread"},
             "sample": f"{n} scans after {args.prime} untimed priming scans of the same stream (seed 0); OpenMP threads "
                       f"picked as fastest of {thread_candidates()} on {os.cpu_count()} cpus"}
 

@@ -115,7 +115,7 @@ struct Exec {
     int grid = 0;
     Scratch sc{};  // all pointers null, profiling off
     TeamScratch team{};  // ll / out (qrec belongs to the caller's workspace)
-    int icp_team_q = TQ_PER_PASS;  // source points per CTA of the ICP team (KB_ICP_TEAM_Q; 0 = whole-grid ICP loop)
+    int icp_team_q = TQ_PER_CTA;  // source points per CTA of the ICP team (KB_ICP_TEAM_Q; 0 = whole-grid ICP loop)
     unsigned tag_seq = 0;  // launch sequence number of the tagged ICP protocol
     unsigned long long launches = 0;
     bool bar_dirty = true;  // the barrier words may be non-zero (a kernel without Grid::finish() ran last)

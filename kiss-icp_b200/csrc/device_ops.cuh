@@ -387,6 +387,8 @@ struct Shared {
     double cache_stats[3];           // NN-cache hits / fills / overflows summed over the iterations
     int flag;
     int is_last;
+    int refill_n, refill_over;   // op_icp_team: source points whose candidate list went stale this iteration
+    int refill_q[512];
 };
 
 // `in` is double[n][3], or float[n][3] when in_f32 (KITTI .bin / PointCloud2 payloads are float32; the reference

@@ -7,9 +7,9 @@
 //     runs the 27-voxel search of GetClosestNeighbor (core/VoxelHashMap.cpp:46-70) and leaves, per point, the
 //     short list of map points that can still become its nearest neighbour while it moves by <= R
 //     (exactness argument: QCache in device_ops.cuh);
-//   * the iterations then run on a small team (T = ceil(n / 128) CTAs, 22 for a KITTI scan): FOUR lanes per
-//     source point walk its list (8 points per warp, 128 per CTA and pass), the 16 accumulators of J^T w J /
-//     J^T w r are split over those four lanes, and the T partial systems meet in ONE all-gather of epoch-tagged
+//   * the iterations then run on a small team (T = ceil(n / 128) CTAs, 22 for a KITTI scan): ONE thread per
+//     source point walks its list (the iteration is a dependent chain: cross-lane merges per point would only
+//     lengthen it), one 32-shuffle sum per warp, and the T partial systems meet in ONE all-gather of epoch-tagged
 //     16-byte chunks: every team CTA polls all T partials, adds them in the same fixed order and solves the
 //     6x6 itself, so there is no coordinator, no broadcast hop and one L2 round trip per iteration;
 //   * the rest of the launch (the other ~126 SMs) is free meanwhile: k_register_frame runs the NEXT scan's
@@ -23,9 +23,7 @@
 namespace kb {
 
 constexpr int TEAM_MAX = 128;  // CTAs of an ICP team (one tagged chunk per value and member; a lane gathers 4 members)
-constexpr int TQ_LANES = 4;    // lanes that share one source point in the list walk
-constexpr int TQ_PER_WARP = 32 / TQ_LANES;
-constexpr int TQ_PER_PASS = BLOCK / TQ_LANES;  // source points one CTA handles per pass
+constexpr int TQ_PER_CTA = 128;  // source points per team CTA by default (one thread each: 4 warps)
 
 // one source point of the ICP loop: candidate list + state. Lives in global memory after the fill pass and in
 // the owning team CTA's shared memory during the iterations. The list holds POINT INDICES (slot * cap + k) in the
@@ -46,7 +44,7 @@ struct QList {
 };
 static_assert(sizeof(QList) % 16 == 0, "QList is copied as int4");
 constexpr int TQ_CAP = static_cast<int>(QC_BYTES / sizeof(QList));  // source points per team CTA (same dynamic smem as op_icp)
-static_assert(TQ_CAP >= TQ_PER_PASS, "one pass of source points must fit in shared memory");
+static_assert(TQ_CAP >= TQ_PER_CTA && TQ_CAP <= BLOCK, "a team CTA holds its source points in shared memory, one thread each");
 
 struct TeamScratch {
     uint4 *ll;        // [2][NPART][TEAM_MAX] epoch-tagged partial systems, ping-pong by iteration parity
@@ -161,217 +159,205 @@ __device__ __noinline__ void icp_fill_pass(const Grid &g, Shared &sh, const MapV
     }
 }
 
-// the 16 distinct entries of one correspondence's J^T w J / J^T w r (icp_term's formulas); lane g4 of the
-// point's four lanes keeps entries 4 g4 .. 4 g4 + 3
-__device__ __forceinline__ void icp_term4(int g4, const V3 &s, const V3 &t, double kscale, double acc[4]) {
+// the 16 distinct entries of one correspondence's J^T w J / J^T w r, each formed exactly as Eigen forms
+// (J^T * w) * J entry by entry (icp_term's formulas, device_ops.cuh)
+__device__ __forceinline__ void icp_term16(const V3 &s, const V3 &t, double kscale, double a[NACC]) {
     const V3 r = s - t;
     const double r2 = sqnorm(r);
-    const double w = (kscale * kscale) * fast_rcp((kscale + r2) * (kscale + r2));
+    const double w = (kscale * kscale) * fast_rcp((kscale + r2) * (kscale + r2));  // ~1 ulp from the reference's division
     const double xw = s.x * w, yw = s.y * w, zw = s.z * w;
-    double a0, a1, a2, a3;
-    if (g4 == 0) {
-        a0 = w;
-        a1 = xw;
-        a2 = yw;
-        a3 = zw;
-    } else if (g4 == 1) {
-        a0 = zw * s.z + yw * s.y;  // (3,3)
-        a1 = -(xw * s.y);          // (4,3)
-        a2 = zw * s.z + xw * s.x;  // (4,4)
-        a3 = -(xw * s.z);          // (5,3)
-    } else if (g4 == 2) {
-        a0 = -(yw * s.z);          // (5,4)
-        a1 = yw * s.y + xw * s.x;  // (5,5)
-        a2 = w * r.x;
-        a3 = w * r.y;
-    } else {
-        a0 = w * r.z;
-        a1 = -(zw * r.y) + yw * r.z;
-        a2 = zw * r.x - xw * r.z;
-        a3 = -(yw * r.x) + xw * r.y;
-    }
-    acc[0] += a0;
-    acc[1] += a1;
-    acc[2] += a2;
-    acc[3] += a3;
+    a[0] = w;
+    a[1] = xw;
+    a[2] = yw;
+    a[3] = zw;
+    a[4] = zw * s.z + yw * s.y;  // (3,3)
+    a[5] = -(xw * s.y);          // (4,3)
+    a[6] = zw * s.z + xw * s.x;  // (4,4)
+    a[7] = -(xw * s.z);          // (5,3)
+    a[8] = -(yw * s.z);          // (5,4)
+    a[9] = yw * s.y + xw * s.x;  // (5,5)
+    a[10] = w * r.x;
+    a[11] = w * r.y;
+    a[12] = w * r.z;
+    a[13] = -(zw * r.y) + yw * r.z;
+    a[14] = zw * r.x - xw * r.z;
+    a[15] = -(yw * r.x) + xw * r.y;
 }
 
-// merge two (minimum, second minimum, position, point) records of a list walk; symmetric, so both sides of a
-// butterfly end with the same record. Equal squares keep the smaller list position (= reference order).
-__device__ __forceinline__ void tq_merge(double &b2, double &s2, int &bk, V3 &bp, int o) {
-    const double ob2 = __shfl_xor_sync(FULL, b2, o), os2 = __shfl_xor_sync(FULL, s2, o);
-    const int ok = __shfl_xor_sync(FULL, bk, o);
-    const V3 obp{__shfl_xor_sync(FULL, bp.x, o), __shfl_xor_sync(FULL, bp.y, o), __shfl_xor_sync(FULL, bp.z, o)};
-    const double hi = fmax(b2, ob2), lo = fmin(b2, ob2);
-    double ns2 = fmin(s2, os2);
-    if (hi > lo) ns2 = fmin(ns2, hi);
-    if ((ob2 < b2) || (ob2 == b2 && ok < bk)) {
-        bk = ok;
-        bp = obp;
-    }
-    b2 = lo;
-    s2 = ns2;
-}
-
-// DataAssociation + BuildLinearSystem (Registration.cpp:60-121) for this CTA's source points, iteration j:
-// the partial system goes out as tagged chunks ll[parity][value][member]
-__device__ __noinline__ void team_queries(const TeamScratch &ts, Shared &sh, const MapView &m, QList *tq, int nq, int j,
-                                          double max_dist, double kscale, int member, unsigned tag) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int g4 = lane & (TQ_LANES - 1), grp = lane / TQ_LANES;
-    const double radius = 0.2 * m.voxel_size, r2max = radius * radius;
-    double acc[4] = {0.0, 0.0, 0.0, 0.0};
-    int corr = 0, n_hit = 0, n_fill = 0, n_over = 0;
-    double cand = 0.0;
-    for (int base = warp * TQ_PER_WARP; base < nq; base += NWARPS * TQ_PER_WARP) {  // warp-uniform trip count
-        const int li = base + grp;
-        const bool have = li < nq;
-        QList &t = tq[have ? li : base];
-        V3 p{0.0, 0.0, 0.0};
-        bool valid = false;
-        if (have) {
-            p = V3{t.p[0], t.p[1], t.p[2]};
-            if (j > 0) p = se3_act(sh.pending, p);  // TransformPoints(estimation, source)  Registration.cpp:160
-            const V3 moved = p - V3{t.pf[0], t.pf[1], t.pf[2]};
-            const int3 v = point_to_voxel(p.x, p.y, p.z, m.vdiv);
-            valid = t.count >= 0 && sqnorm(moved) <= r2max && (t.any_voxel || (t.vx == v.x && t.vy == v.y && t.vz == v.z));
+// sum of 16 values per lane over the 32 lanes of a warp in 32 shuffles instead of 160: at every level a lane keeps
+// one half of its values and hands the other half to its partner. On return a[0] of lanes 2k and 2k+1 holds the warp
+// total of value k. Fixed order -> deterministic.
+__device__ __forceinline__ void warp_sum16(double a[NACC], int lane) {
+#pragma unroll
+    for (int half = 8, mask = 16; half >= 1; half >>= 1, mask >>= 1) {
+        const bool up = (lane & mask) != 0;
+#pragma unroll
+        for (int i = 0; i < half; ++i) {
+            const double send = up ? a[i] : a[i + half];
+            const double keep = up ? a[i + half] : a[i];
+            a[i] = keep + __shfl_xor_sync(FULL, send, mask);
         }
-        __syncwarp();  // all four lanes have read t.p
-        if (have && g4 == 0 && j > 0) {
+    }
+    a[0] += __shfl_xor_sync(FULL, a[0], 1);
+}
+
+// T_icp = estimation * T_icp (Registration.cpp:161) + work counters of the iteration that was just solved. Run by the
+// solver thread (BLOCK - 1, owns no source point) while the other warps walk their lists for the NEXT iteration.
+__device__ __forceinline__ void team_accumulate(Shared &sh) {
+    sh.t_icp = se3_mul_fast(sh.pending, sh.t_icp);
+    sh.cand_total += sh.red[NACC + 1];
+    for (int i = 0; i < 3; ++i) sh.cache_stats[i] += sh.red[NACC + 2 + i];
+}
+
+#define KB_TCYC(i) \
+    if (dbg != nullptr && threadIdx.x == 0) dbg[16 + (i)] = static_cast<unsigned long long>(clock64())
+
+// DataAssociation + BuildLinearSystem (Registration.cpp:60-121) for this CTA's source points, iteration j, ONE THREAD
+// PER SOURCE POINT: the loop is a dependent chain, so what counts is the length of the per-point instruction chain,
+// not issue slots — a thread walks its own candidate list with independent loads/distances in flight and no
+// cross-lane merges; the only cross-lane work is one 32-shuffle sum per warp. Stale lists are collected in a queue
+// and searched again by ALL warps of the CTA (the warps without source points have nothing else to do).
+// The CTA's partial system goes out as tagged chunks ll[parity][value][member].
+__device__ __noinline__ void team_queries(const TeamScratch &ts, Shared &sh, const MapView &m, QList *tq, int nq, int j,
+                                          double max_dist, double kscale, int member, unsigned tag,
+                                          unsigned long long *dbg) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const double radius = 0.2 * m.voxel_size, r2max = radius * radius;
+    const bool have = tid < nq;
+    QList &t = tq[have ? tid : 0];
+    V3 p{0.0, 0.0, 0.0};
+    if (have) {
+        p = V3{t.p[0], t.p[1], t.p[2]};
+        if (j > 0) {  // TransformPoints(estimation, source)  Registration.cpp:160
+            p = se3_act(sh.pending, p);
             t.p[0] = p.x;
             t.p[1] = p.y;
             t.p[2] = p.z;
         }
-        // points whose list is stale are searched again by the whole warp, one after the other
-        unsigned need = __ballot_sync(FULL, have && !valid && g4 == 0);
-        const unsigned hits = __ballot_sync(FULL, have && valid && g4 == 0);
-        if (lane == 0) {
-            n_fill += __popc(need);
-            n_hit += __popc(hits);
-        }
-        while (need) {
-            const int b = __ffs(need) - 1;
-            need &= need - 1;
-            const V3 pq{__shfl_sync(FULL, p.x, b), __shfl_sync(FULL, p.y, b), __shfl_sync(FULL, p.z, b)};
-            QList *tr = &tq[base + b / TQ_LANES];
-            const NNResult r = nn_search_list(m, pq, lane, sh.wnn[warp], tr, radius);
-            if (lane == 0) {
-                tr->nn[0] = r.p.x;
-                tr->nn[1] = r.p.y;
-                tr->nn[2] = r.p.z;
-                tr->nn[3] = r.d;
-                tr->direct = 1;
-                n_over += (tr->count < 0 && r.d < DBL_MAX) ? 1 : 0;
-            }
-            __syncwarp();
-        }
-        // nearest neighbour from the list: four lanes stride it, first strict minimum of the squared distance
-        const bool direct = have && t.direct != 0;
-        const int cnt = (have && !direct) ? t.count : 0;
-        double b2 = DBL_MAX, s2 = DBL_MAX;
-        int bk = INT_MAX;
-        V3 bp{0.0, 0.0, 0.0};
-        for (int k0 = g4; k0 < cnt; k0 += 4 * TQ_LANES) {
-            V3 c[4];
-            bool ok[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {  // four independent loads in flight per lane
-                const int k = k0 + u * TQ_LANES;
-                ok[u] = k < cnt;
-                if (ok[u]) c[u] = ld_point24(m.points + static_cast<size_t>(t.idx[k]) * 3);
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u)
-                if (ok[u]) {
-                    const double d2 = sqnorm(c[u] - p);
-                    if (d2 < b2) {
-                        s2 = b2;
-                        b2 = d2;
-                        bk = k0 + u * TQ_LANES;
-                        bp = c[u];
-                    } else if (d2 > b2 && d2 < s2) {
-                        s2 = d2;
-                    }
-                }
-        }
-        tq_merge(b2, s2, bk, bp, 1);
-        tq_merge(b2, s2, bk, bp, 2);
-        double d = (cnt > 0) ? sqrt(b2) : DBL_MAX;
-        V3 np = bp;
-        // two squares within a few ulps could round to the same root: then compare rounded roots in reference
-        // order like GetClosestNeighbor does (in practice never)
-        const bool near = cnt > 0 && s2 <= b2 * (1.0 + 8.8817841970012523e-16);
-        if (__any_sync(FULL, near)) {
-            double best = DBL_MAX;
-            int ek = INT_MAX;
-            V3 ep{0.0, 0.0, 0.0};
-            if (near)
-                for (int k = g4; k < cnt; k += TQ_LANES) {
-                    const V3 c = ld_point24(m.points + static_cast<size_t>(t.idx[k]) * 3);
-                    const double dd = norm(c - p);
-                    if (dd < best) {
-                        best = dd;
-                        ek = k;
-                        ep = c;
-                    }
-                }
-#pragma unroll
-            for (int o = 1; o < TQ_LANES; o <<= 1) {
-                const double ob = __shfl_xor_sync(FULL, best, o);
-                const int ok2 = __shfl_xor_sync(FULL, ek, o);
-                const V3 op{__shfl_xor_sync(FULL, ep.x, o), __shfl_xor_sync(FULL, ep.y, o), __shfl_xor_sync(FULL, ep.z, o)};
-                if ((ob < best) || (ob == best && ok2 < ek)) {
-                    best = ob;
-                    ek = ok2;
-                    ep = op;
-                }
-            }
-            if (near) {
-                d = best;
-                np = ep;
-            }
-        }
-        if (direct) {
-            d = t.nn[3];
-            np = V3{t.nn[0], t.nn[1], t.nn[2]};
-        }
-        __syncwarp();  // all four lanes have read the direct answer
-        if (direct && g4 == 0) t.direct = 0;
-        if (have && g4 == 0) cand += t.full;
-        if (have && d < max_dist) {  // DataAssociation's gate, Registration.cpp:72
-            icp_term4(g4, p, np, kscale, acc);
-            corr += (g4 == 0) ? 1 : 0;
-        }
-    }
-    // eight points of a warp -> one partial per accumulator (lane g4 holds entries 4 g4 ..)
-#pragma unroll
-    for (int o = TQ_LANES; o < 32; o <<= 1) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) acc[i] += __shfl_xor_sync(FULL, acc[i], o);
-        corr += __shfl_xor_sync(FULL, corr, o);
-        cand += __shfl_xor_sync(FULL, cand, o);
-    }
-    if (lane < TQ_LANES) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) sh.warp_d[warp][4 * lane + i] = acc[i];
-    }
-    if (lane == 0) {
-        sh.warp_d[warp][NACC] = static_cast<double>(corr);
-        sh.warp_d[warp][NACC + 1] = cand;
-        sh.warp_d[warp][NACC + 2] = static_cast<double>(n_hit);
-        sh.warp_d[warp][NACC + 3] = static_cast<double>(n_fill);
-        sh.warp_d[warp][NACC + 4] = static_cast<double>(n_over);
+        const V3 moved = p - V3{t.pf[0], t.pf[1], t.pf[2]};
+        const int3 v = point_to_voxel(p.x, p.y, p.z, m.vdiv);
+        const bool valid = t.count >= 0 && sqnorm(moved) <= r2max && (t.any_voxel || (t.vx == v.x && t.vy == v.y && t.vz == v.z));
+        if (!valid) sh.refill_q[atomicAdd(&sh.refill_n, 1)] = tid;
     }
     __syncthreads();
-    // 16-warp tree per value: thread t -> value t / 16, warp t % 16
-    if (threadIdx.x < ((NPART * NWARPS + 31) / 32) * 32) {
-        const int val = min(static_cast<int>(threadIdx.x) / NWARPS, NPART - 1);
-        double v = sh.warp_d[threadIdx.x & (NWARPS - 1)][val];
-#pragma unroll
-        for (int o = NWARPS / 2; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
-        if ((threadIdx.x & (NWARPS - 1)) == 0 && threadIdx.x < NPART * NWARPS)
-            ll_store(&ts.ll[(static_cast<size_t>(tag & 1u) * NPART + val) * TEAM_MAX + member], v, tag);
+    KB_TCYC(1);
+    const int nref = sh.refill_n;
+    if (nref > 0) {  // uniform
+        for (int r = warp; r < nref; r += NWARPS) {
+            QList *tr = &tq[sh.refill_q[r]];
+            const V3 pq{tr->p[0], tr->p[1], tr->p[2]};
+            const NNResult res = nn_search_list(m, pq, lane, sh.wnn[warp], tr, radius);
+            if (lane == 0) {
+                tr->nn[0] = res.p.x;
+                tr->nn[1] = res.p.y;
+                tr->nn[2] = res.p.z;
+                tr->nn[3] = res.d;
+                tr->direct = 1;
+                if (tr->count < 0 && res.d < DBL_MAX) atomicAdd(&sh.refill_over, 1);
+            }
+        }
+        __syncthreads();
     }
+    KB_TCYC(2);
+    if (tid == BLOCK - 1 && j > 0) team_accumulate(sh);  // for iteration j - 1 (sh.red is rewritten behind the next barrier)
+    const int nwarps_q = (nq + 31) >> 5;  // warps that own source points
+    if (warp < nwarps_q) {
+        double a[NACC];
+#pragma unroll
+        for (int i = 0; i < NACC; ++i) a[i] = 0.0;
+        int corr = 0;
+        double cand = 0.0;
+        if (have) {
+            double d;
+            V3 np;
+            if (t.direct) {  // answered by the re-search above
+                d = t.nn[3];
+                np = V3{t.nn[0], t.nn[1], t.nn[2]};
+                t.direct = 0;
+            } else {
+                // first strict minimum of the squared distance over the list (= reference order)
+                const int cnt = t.count;
+                double b2 = DBL_MAX, s2 = DBL_MAX;
+                V3 bp{0.0, 0.0, 0.0};
+                constexpr int U = 4;
+                for (int k0 = 0; k0 < cnt; k0 += U) {
+                    V3 c[U];
+                    double d2[U];
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {  // independent loads and distances in flight
+                        const int k = min(k0 + u, cnt - 1);
+                        c[u] = ld_point24(m.points + static_cast<size_t>(t.idx[k]) * 3);
+                    }
+#pragma unroll
+                    for (int u = 0; u < U; ++u) d2[u] = (k0 + u < cnt) ? sqnorm(c[u] - p) : DBL_MAX;
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        if (d2[u] < b2) {
+                            s2 = b2;
+                            b2 = d2[u];
+                            bp = c[u];
+                        } else if (d2[u] > b2 && d2[u] < s2) {
+                            s2 = d2[u];
+                        }
+                    }
+                }
+                d = (cnt > 0) ? sqrt(b2) : DBL_MAX;
+                np = bp;
+                // two squares within a few ulps could round to the same root: then compare rounded roots in
+                // reference order like GetClosestNeighbor does (in practice never)
+                if (cnt > 0 && s2 <= b2 * (1.0 + 8.8817841970012523e-16)) {
+                    double best = DBL_MAX;
+                    for (int k = 0; k < cnt; ++k) {
+                        const V3 c = ld_point24(m.points + static_cast<size_t>(t.idx[k]) * 3);
+                        const double dd = norm(c - p);
+                        if (dd < best) {
+                            best = dd;
+                            np = c;
+                        }
+                    }
+                    d = best;
+                }
+            }
+            cand = t.full;
+            if (d < max_dist) {  // DataAssociation's gate, Registration.cpp:72
+                icp_term16(p, np, kscale, a);
+                corr = 1;
+            }
+        }
+        KB_TCYC(3);
+        warp_sum16(a, lane);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            corr += __shfl_xor_sync(FULL, corr, o);
+            cand += __shfl_xor_sync(FULL, cand, o);
+        }
+        if ((lane & 1) == 0) sh.warp_d[warp][lane >> 1] = a[0];
+        if (lane == 0) {
+            sh.warp_d[warp][NACC] = static_cast<double>(corr);
+            sh.warp_d[warp][NACC + 1] = cand;
+        }
+    }
+    __syncthreads();
+    KB_TCYC(4);
+    if (tid < NPART) {
+        double v = 0.0;
+        if (tid < NACC + 2) {
+            for (int w = 0; w < nwarps_q; ++w) v += sh.warp_d[w][tid];
+        } else if (tid == NACC + 2) {
+            v = static_cast<double>(nq - nref);  // lists that were still valid
+        } else if (tid == NACC + 3) {
+            v = static_cast<double>(nref);  // re-searched
+        } else {
+            v = static_cast<double>(sh.refill_over);  // re-searched and not cacheable
+        }
+        ll_store(&ts.ll[(static_cast<size_t>(tag & 1u) * NPART + tid) * TEAM_MAX + member], v, tag);
+    }
+    __syncthreads();
+    if (tid == 0) {  // (next use is behind at least one more barrier)
+        sh.refill_n = 0;
+        sh.refill_over = 0;
+    }
+    KB_TCYC(5);
 }
 
 // all-gather of the T tagged partial systems: warp w sums values w and w + 16 over the members (a lane polls
@@ -425,15 +411,20 @@ __device__ __noinline__ void op_icp_team(const TeamScratch &ts, const Scratch &s
         sh.t_icp = se3_identity();
         sh.cand_total = 0.0;
         sh.cache_stats[0] = sh.cache_stats[1] = sh.cache_stats[2] = 0.0;
+        sh.refill_n = 0;
+        sh.refill_over = 0;
     }
     __syncthreads();
     int j = 0;
     for (;; ++j) {
         if (sc.profile && member == 0 && threadIdx.x == 0 && j < 20) sc.dbg[41 + j] = globaltimer_ns();
         const unsigned tag = tag_base + static_cast<unsigned>(j) + 1u;
-        team_queries(ts, sh, m, tq, nq, j, max_dist, kscale, member, tag);
+        unsigned long long *dbg = (sc.profile && member == 0 && j == 4) ? sc.dbg : nullptr;
+        KB_TCYC(0);
+        team_queries(ts, sh, m, tq, nq, j, max_dist, kscale, member, tag, dbg);
         team_gather(ts, sh, T, tag);
-        if (threadIdx.x == 0) {
+        KB_TCYC(6);
+        if (threadIdx.x == BLOCK - 1) {  // a thread that owns no source point (TQ_CAP < BLOCK - 32)
             double sys[NACC];
 #pragma unroll
             for (int i = 0; i < NACC; ++i) sys[i] = sh.red[i];
@@ -451,14 +442,13 @@ __device__ __noinline__ void op_icp_team(const TeamScratch &ts, const Scratch &s
             for (int i = 0; i < 6; ++i) n2 += dx[i] * dx[i];
             sh.pending = est;
             sh.flag = ((sqrt(n2) < conv) || (j + 1 >= max_iter)) ? 1 : 0;  // :163 / :151
-            sh.t_icp = se3_mul_fast(est, sh.t_icp);                        // :161
-            sh.cand_total += sh.red[NACC + 1];
-            for (int i = 0; i < 3; ++i) sh.cache_stats[i] += sh.red[NACC + 2 + i];
         }
         __syncthreads();
-        if (sh.flag) break;
+        KB_TCYC(7);
+        if (sh.flag) break;  // (T_icp = estimation * T_icp of this iteration: team_accumulate, off the critical path)
     }
-    if (threadIdx.x == 0) {
+    if (threadIdx.x == BLOCK - 1) {
+        team_accumulate(sh);
         sh.result = se3_mul(sh.t_icp, guess);  // :166
         sh.iters = j + 1;
         sh.query_total = static_cast<double>(n) * (j + 1);

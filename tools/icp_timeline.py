@@ -27,6 +27,9 @@ for p, t in scans[prime:]:
     it = g.last_iterations
     st = ns[41:41 + min(it, 20)]
     d = np.diff(st) * 1e-3
+    cyc = np.diff(ns[16:24])
+    print("   cycles at iteration 4 (member 0, thread 0): transform+validity", cyc[0], "refills", cyc[1], "list walk+terms", cyc[2],
+          "warp sums", cyc[3], "store partial", cyc[4], "gather", cyc[5], "solve", cyc[6])
     print("iters", it, "phases_us", dict(zip(names, np.round(g.last_profile_us, 1))),
           "iter_us first", np.round(d[:3], 2), "median", round(float(np.median(d)), 2) if len(d) else None,
           "env", os.environ.get("KB_ICP_TEAM_Q", "default"))
