@@ -347,10 +347,8 @@ def main():
         return ms, sharding.max_over_ranks(float(np.median(ms)), dev)
 
     def win_scans(pool, r):
-        return pool[head - head_of(pool) + r * Kw: head - head_of(pool) + (r + 1) * Kw]
-
-    def head_of(pool):  # pools hold either the whole stream or only the timed part
-        return head if len(pool) == n_total else 0
+        off = head if len(pool) == n_total else 0  # pools hold either the whole stream or only the timed part
+        return pool[off + r * Kw: off + (r + 1) * Kw]
 
     warm = scans_dev[args.prime:head]
     legs = {}

@@ -115,6 +115,7 @@ struct Exec {
     int grid = 0;
     Scratch sc{};  // all pointers null, profiling off
     TeamScratch team{};  // ll / out (qrec belongs to the caller's workspace)
+    size_t icp_smem = 96 * 1024;  // dynamic shared memory of the ICP kernels: candidate coordinates of the team's source points (KB_ICP_SMEM_KB)
     int icp_team_q = TQ_PER_CTA;  // source points per CTA of the ICP team (KB_ICP_TEAM_Q; 0 = whole-grid ICP loop)
     unsigned tag_seq = 0;  // launch sequence number of the tagged ICP protocol
     unsigned long long launches = 0;
@@ -152,7 +153,9 @@ struct Exec {
         CK(cudaMalloc(&team.ll, sizeof(uint4) * 2 * NPART * TEAM_MAX));
         CK(cudaMemsetAsync(team.ll, 0, sizeof(uint4) * 2 * NPART * TEAM_MAX, stream));
         CK(cudaMalloc(&team.out, sizeof(double) * 16));
-        if (const char *e = std::getenv("KB_ICP_TEAM_Q")) icp_team_q = std::max(0, std::min(std::atoi(e), TQ_CAP));
+        if (const char *e = std::getenv("KB_ICP_TEAM_Q")) icp_team_q = std::max(0, std::min(std::atoi(e), TQ_MAX));
+        if (const char *e = std::getenv("KB_ICP_SMEM_KB")) icp_smem = static_cast<size_t>(std::max(60, std::min(std::atoi(e), 180))) * 1024;
+        team.smem_bytes = static_cast<int>(icp_smem);
         CK(cudaMalloc(&sc.dbg, sizeof(unsigned long long) * (64 + 4 * grid)));
         CK(cudaMemsetAsync(sc.dbg, 0, sizeof(unsigned long long) * (64 + 4 * grid), stream));
         return KB_OK;
@@ -885,7 +888,7 @@ static int registration_run(kb_registration *reg, const double *xyz, size_t n, k
     P.team = ex.team;
     P.team.qrec = reg->ws.qrec.p;
     P.icp_team_q = ex.icp_team_q;
-    return ex.coop(k_icp, P, system_only ? 0 : QC_BYTES);
+    return ex.coop(k_icp, P, system_only ? 0 : std::max<size_t>(QC_BYTES, ex.icp_smem));
 }
 int kb_registration_align_points_to_map(kb_registration *reg, const double *xyz, size_t n, const kb_map *cmap,
                                         const double initial_guess[16], double max_correspondence_distance,
@@ -1194,7 +1197,7 @@ static int pipeline_launch(kb_pipeline *p, long long id, const double *d_xyz, si
     P.use_qcache = 1;
     P.tag_base = ex.next_tag_base();
     P.in_f32 = in_f32 ? 1 : 0;
-    return ex.coop(k_register_frame, P, QC_BYTES, true);
+    return ex.coop(k_register_frame, P, std::max<size_t>(QC_BYTES, ex.icp_smem), true);
 }
 
 // take over the result of a frame that ran (not vetoed): host mirror of the counters, history

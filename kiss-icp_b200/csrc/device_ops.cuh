@@ -367,6 +367,9 @@ struct QCache {
 };
 constexpr size_t QC_BYTES = sizeof(QCache) * QC_SLOTS * NWARPS;
 
+struct alignas(16) QListRaw {
+    unsigned char bytes[32 + 24 + 4 * QC_MAX + 8];
+};
 struct Shared {
     int warp_i[NWARPS + 1];
     int two[2];
@@ -388,7 +391,8 @@ struct Shared {
     int flag;
     int is_last;
     int refill_n, refill_over;   // op_icp_team: source points whose candidate list went stale this iteration
-    int refill_q[512];
+    int refill_q[192];
+    QListRaw rlist[NWARPS];      // op_icp_team: candidate list of a re-search, before it is staged (QList, icp_team.cuh)
 };
 
 // `in` is double[n][3], or float[n][3] when in_f32 (KITTI .bin / PointCloud2 payloads are float32; the reference

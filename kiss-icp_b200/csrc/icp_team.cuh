@@ -22,44 +22,81 @@
 
 namespace kb {
 
-constexpr int TEAM_MAX = 128;  // CTAs of an ICP team (one tagged chunk per value and member; a lane gathers 4 members)
-constexpr int TQ_PER_CTA = 128;  // source points per team CTA by default (one thread each: 4 warps)
+constexpr int TEAM_MAX = 128;   // CTAs of an ICP team (one tagged chunk per value and member; a lane gathers 4 members)
+constexpr int TQ_PER_CTA = 64;  // source points per team CTA by default (one thread each: 2 warps)
+constexpr int TQ_MAX = 160;     // upper bound of source points per team CTA (threads 0..159; the solver is thread 511)
 
-// one source point of the ICP loop: candidate list + state. Lives in global memory after the fill pass and in
-// the owning team CTA's shared memory during the iterations. The list holds POINT INDICES (slot * cap + k) in the
+// Output of the fill pass for one source point (global memory): the list holds POINT INDICES (slot * cap + k) in the
 // reference's visiting order (voxel_shifts order, then insertion order), so the first strict minimum over the
-// list is the reference's answer, ties included; coordinates are read through L1 (the map is immutable
-// during AlignPointsToMap).
+// list is the reference's answer, ties included.
 struct QList {
     int count;      // >= 0: idx[0..count) valid; -1: not cacheable (too many candidates / max_points_per_voxel > 32)
     int full;       // points of the whole 27-voxel neighbourhood (bookkeeping of algorithmic bytes)
     int any_voxel;  // list valid whatever voxel the point is in (d* + 3R < voxel_size)
     int vx, vy, vz; // voxel at fill time
+    int pad[2];
+    double pf[3];   // position at fill time (= initial_guess * source point)
+    int idx[QC_MAX];
+    int tail[2];    // 320 bytes
+};
+static_assert(sizeof(QList) % 16 == 0 && sizeof(QList) == sizeof(QListRaw), "QList records are 16-byte aligned; Shared::rlist holds one per warp");
+
+// A source point inside its team CTA (shared memory): state + where its candidate COORDINATES are. The coordinates
+// of the 32 points of a warp are interleaved — candidate k, component c of the point in column q sits at
+// coords[((k * 3 + c) * 32 + ((q + k) & 31)] — so that (i) the thread-per-point walk (32 threads, same k) and
+// (ii) the warp that stages one point's list (32 lanes, consecutive k, same q) both hit 32 different banks.
+// (Reading the coordinates through L1 instead was measured: every thread's load is its own L1 wavefront and the
+// walk alone took 8000 cycles per iteration.)
+struct TQHead {
+    int count;      // >= 0: candidates staged; -1: not cacheable (searched again every iteration)
+    int full, any_voxel, vx, vy, vz;
     int direct;     // nn[] holds this iteration's answer (written by a re-search inside the iteration)
     int pad;
-    double pf[3];   // position at fill time
+    double pf[3];   // position when the list was made
     double p[3];    // current position (TransformPoints is applied in place, Registration.cpp:55-58,160)
     double nn[4];   // nearest neighbour and distance of a re-search
-    int idx[QC_MAX];
+    double pad2;    // 120 bytes: consecutive records start 30 words apart (no 8-byte bank conflict between 16 lanes)
 };
-static_assert(sizeof(QList) % 16 == 0, "QList is copied as int4");
-constexpr int TQ_CAP = static_cast<int>(QC_BYTES / sizeof(QList));  // source points per team CTA (same dynamic smem as op_icp)
-static_assert(TQ_CAP >= TQ_PER_CTA && TQ_CAP <= BLOCK, "a team CTA holds its source points in shared memory, one thread each");
+static_assert(sizeof(TQHead) == 120, "TQHead layout");
+
+struct TeamSmem {
+    TQHead *heads;   // [qmax]
+    double *coords;  // [warps][K][3][32]
+    int K;           // candidate slots per source point
+};
+// carve the dynamic shared memory of a team CTA for qmax source points; K < 16 means "does not fit"
+__device__ __forceinline__ TeamSmem team_smem(unsigned char *dyn, int dyn_bytes, int qmax) {
+    TeamSmem t;
+    const int head_bytes = (qmax * static_cast<int>(sizeof(TQHead)) + 15) & ~15;
+    const int warps = (qmax + 31) >> 5;
+    t.heads = reinterpret_cast<TQHead *>(dyn);
+    t.coords = reinterpret_cast<double *>(dyn + head_bytes);
+    t.K = (warps > 0 && dyn_bytes > head_bytes) ? min(QC_MAX, (dyn_bytes - head_bytes) / (warps * 768)) : 0;
+    return t;
+}
+__device__ __forceinline__ double *tq_coord(const TeamSmem &ts, int li, int k) {  // component c at [c * 32]
+    return ts.coords + (static_cast<size_t>(li >> 5) * ts.K + k) * 96 + (((li & 31) + k) & 31);
+}
 
 struct TeamScratch {
     uint4 *ll;        // [2][NPART][TEAM_MAX] epoch-tagged partial systems, ping-pong by iteration parity
     double *out;      // [16] result record: pose(7) iters cand_total query_total cache_stats(3)
     QList *qrec;      // [n] per source point, written by the fill pass
+    int smem_bytes;   // dynamic shared memory of the launch
 };
 
-// team size for n source points: q_per_cta points per CTA (one pass of four-lane groups by default)
-__device__ __forceinline__ int icp_team_size(int n, int q_per_cta, int grid) {
+// team size for n source points at q_per_cta points per CTA; 0 when the lists would not fit in shared memory
+__device__ __forceinline__ int icp_team_size(int n, int q_per_cta, int grid, int smem_bytes) {
+    q_per_cta = max(1, min(q_per_cta, TQ_MAX));
     int T = (n + q_per_cta - 1) / q_per_cta;
     T = max(T, 1);
-    T = min(T, min(grid, TEAM_MAX));
+    if (T > min(grid, TEAM_MAX)) return 0;
+    const int qmax = (n + T - 1) / T;
+    const int head_bytes = (qmax * static_cast<int>(sizeof(TQHead)) + 15) & ~15;
+    const int warps = (qmax + 31) >> 5;
+    if (warps > 0 && (smem_bytes - head_bytes) / (warps * 768) < 24) return 0;
     return T;
 }
-__device__ __forceinline__ bool icp_team_fits(int n, int T) { return (n + T - 1) / T <= TQ_CAP; }
 
 // GetClosestNeighbor for one point by one warp (like nn_search_warp) + its candidate list into *out
 // (generic pointer: global memory in the fill pass, shared memory inside an iteration).
@@ -148,14 +185,7 @@ __device__ __noinline__ void icp_fill_pass(const Grid &g, Shared &sh, const MapV
     const double radius = 0.2 * m.voxel_size;
     for (int qi = g.rank + g.size * warp; qi < n; qi += g.size * NWARPS) {
         const V3 p = se3_act(guess, V3{src[3 * qi], src[3 * qi + 1], src[3 * qi + 2]});
-        QList *rec = &qrec[qi];
-        nn_search_list(m, p, lane, sh.wnn[warp], rec, radius);
-        if (lane == 0) {
-            rec->p[0] = p.x;
-            rec->p[1] = p.y;
-            rec->p[2] = p.z;
-            rec->direct = 0;
-        }
+        nn_search_list(m, p, lane, sh.wnn[warp], &qrec[qi], radius);
     }
 }
 
@@ -201,6 +231,32 @@ __device__ __forceinline__ void warp_sum16(double a[NACC], int lane) {
     a[0] += __shfl_xor_sync(FULL, a[0], 1);
 }
 
+// stage one source point's candidate list (indices -> coordinates) into the interleaved block of its owner warp;
+// called by a whole warp. Lists longer than the K staged slots are not cacheable.
+__device__ __forceinline__ void team_stage(const TeamSmem &sm, const MapView &m, int li, const QList *src, int lane) {
+    int cnt = src->count;
+    if (cnt > sm.K) cnt = -1;
+    for (int k = lane; k < cnt; k += 32) {
+        const V3 c = ld_point24(m.points + static_cast<size_t>(src->idx[k]) * 3);
+        double *dst = tq_coord(sm, li, k);
+        dst[0] = c.x;
+        dst[32] = c.y;
+        dst[64] = c.z;
+    }
+    if (lane == 0) {
+        TQHead &h = sm.heads[li];
+        h.count = cnt;
+        h.full = src->full;
+        h.any_voxel = src->any_voxel;
+        h.vx = src->vx;
+        h.vy = src->vy;
+        h.vz = src->vz;
+        h.pf[0] = src->pf[0];
+        h.pf[1] = src->pf[1];
+        h.pf[2] = src->pf[2];
+    }
+}
+
 // T_icp = estimation * T_icp (Registration.cpp:161) + work counters of the iteration that was just solved. Run by the
 // solver thread (BLOCK - 1, owns no source point) while the other warps walk their lists for the NEXT iteration.
 __device__ __forceinline__ void team_accumulate(Shared &sh) {
@@ -214,17 +270,17 @@ __device__ __forceinline__ void team_accumulate(Shared &sh) {
 
 // DataAssociation + BuildLinearSystem (Registration.cpp:60-121) for this CTA's source points, iteration j, ONE THREAD
 // PER SOURCE POINT: the loop is a dependent chain, so what counts is the length of the per-point instruction chain,
-// not issue slots — a thread walks its own candidate list with independent loads/distances in flight and no
-// cross-lane merges; the only cross-lane work is one 32-shuffle sum per warp. Stale lists are collected in a queue
-// and searched again by ALL warps of the CTA (the warps without source points have nothing else to do).
-// The CTA's partial system goes out as tagged chunks ll[parity][value][member].
-__device__ __noinline__ void team_queries(const TeamScratch &ts, Shared &sh, const MapView &m, QList *tq, int nq, int j,
+// not issue slots — a thread walks its own candidate list (conflict-free shared memory, independent distances in
+// flight) with no cross-lane merges; the only cross-lane work is one 32-shuffle sum per warp. Stale lists are
+// collected in a queue and searched again by ALL warps of the CTA (the warps without source points have nothing else
+// to do). The CTA's partial system goes out as tagged chunks ll[parity][value][member].
+__device__ __noinline__ void team_queries(const TeamScratch &ts, Shared &sh, const MapView &m, const TeamSmem &sm, int nq, int j,
                                           double max_dist, double kscale, int member, unsigned tag,
                                           unsigned long long *dbg) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const double radius = 0.2 * m.voxel_size, r2max = radius * radius;
     const bool have = tid < nq;
-    QList &t = tq[have ? tid : 0];
+    TQHead &t = sm.heads[have ? tid : 0];
     V3 p{0.0, 0.0, 0.0};
     if (have) {
         p = V3{t.p[0], t.p[1], t.p[2]};
@@ -244,17 +300,21 @@ __device__ __noinline__ void team_queries(const TeamScratch &ts, Shared &sh, con
     const int nref = sh.refill_n;
     if (nref > 0) {  // uniform
         for (int r = warp; r < nref; r += NWARPS) {
-            QList *tr = &tq[sh.refill_q[r]];
-            const V3 pq{tr->p[0], tr->p[1], tr->p[2]};
-            const NNResult res = nn_search_list(m, pq, lane, sh.wnn[warp], tr, radius);
+            const int li = sh.refill_q[r];
+            TQHead &h = sm.heads[li];
+            const V3 pq{h.p[0], h.p[1], h.p[2]};
+            QList *scratch = reinterpret_cast<QList *>(&sh.rlist[warp]);
+            const NNResult res = nn_search_list(m, pq, lane, sh.wnn[warp], scratch, radius);
+            team_stage(sm, m, li, scratch, lane);
             if (lane == 0) {
-                tr->nn[0] = res.p.x;
-                tr->nn[1] = res.p.y;
-                tr->nn[2] = res.p.z;
-                tr->nn[3] = res.d;
-                tr->direct = 1;
-                if (tr->count < 0 && res.d < DBL_MAX) atomicAdd(&sh.refill_over, 1);
+                h.nn[0] = res.p.x;
+                h.nn[1] = res.p.y;
+                h.nn[2] = res.p.z;
+                h.nn[3] = res.d;
+                h.direct = 1;
+                if ((scratch->count < 0 || scratch->count > sm.K) && res.d < DBL_MAX) atomicAdd(&sh.refill_over, 1);
             }
+            __syncwarp();
         }
         __syncthreads();
     }
@@ -285,8 +345,8 @@ __device__ __noinline__ void team_queries(const TeamScratch &ts, Shared &sh, con
                     double d2[U];
 #pragma unroll
                     for (int u = 0; u < U; ++u) {  // independent loads and distances in flight
-                        const int k = min(k0 + u, cnt - 1);
-                        c[u] = ld_point24(m.points + static_cast<size_t>(t.idx[k]) * 3);
+                        const double *src = tq_coord(sm, tid, min(k0 + u, cnt - 1));
+                        c[u] = V3{src[0], src[32], src[64]};
                     }
 #pragma unroll
                     for (int u = 0; u < U; ++u) d2[u] = (k0 + u < cnt) ? sqnorm(c[u] - p) : DBL_MAX;
@@ -308,7 +368,8 @@ __device__ __noinline__ void team_queries(const TeamScratch &ts, Shared &sh, con
                 if (cnt > 0 && s2 <= b2 * (1.0 + 8.8817841970012523e-16)) {
                     double best = DBL_MAX;
                     for (int k = 0; k < cnt; ++k) {
-                        const V3 c = ld_point24(m.points + static_cast<size_t>(t.idx[k]) * 3);
+                        const double *src = tq_coord(sm, tid, k);
+                        const V3 c{src[0], src[32], src[64]};
                         const double dd = norm(c - p);
                         if (dd < best) {
                             best = dd;
@@ -394,17 +455,26 @@ __device__ __forceinline__ void team_gather(const TeamScratch &ts, Shared &sh, i
 }
 
 // the iterations, on CTAs [0, T) of the launch. Precondition: icp_fill_pass + a grid barrier, map not empty,
-// max_iter > 0, icp_team_fits(n, T). Output in sh.result / sh.iters / sh.cand_total / ... of every team CTA.
+// max_iter > 0, T = icp_team_size(...) > 0. Output in sh.result / sh.iters / sh.cand_total / ... of every team CTA.
 __device__ __noinline__ void op_icp_team(const TeamScratch &ts, const Scratch &sc, Shared &sh, const MapView &m, int n,
                                          const SE3 &guess, double max_dist, double kscale, int max_iter, double conv,
-                                         QList *tq, int T, unsigned tag_base) {
+                                         unsigned char *dyn_smem, int T, unsigned tag_base) {
     const int member = static_cast<int>(blockIdx.x);
     const int nq = member < n ? (n - member + T - 1) / T : 0;
+    const TeamSmem sm = team_smem(dyn_smem, ts.smem_bytes, (n + T - 1) / T);
     {
-        constexpr int W = static_cast<int>(sizeof(QList) / 16);
-        for (int i = threadIdx.x; i < nq * W; i += BLOCK) {
-            const int li = i / W, w = i - li * W;
-            reinterpret_cast<int4 *>(&tq[li])[w] = __ldcg(reinterpret_cast<const int4 *>(&ts.qrec[member + T * li]) + w);
+        // stage this CTA's source points (member, member + T, ...): one warp per point, all warps
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        for (int li = warp; li < nq; li += NWARPS) {
+            const QList *rec = &ts.qrec[member + T * li];
+            team_stage(sm, m, li, rec, lane);
+            if (lane == 0) {
+                TQHead &h = sm.heads[li];
+                h.p[0] = rec->pf[0];
+                h.p[1] = rec->pf[1];
+                h.p[2] = rec->pf[2];
+                h.direct = 0;
+            }
         }
     }
     if (threadIdx.x == 0) {
@@ -421,10 +491,10 @@ __device__ __noinline__ void op_icp_team(const TeamScratch &ts, const Scratch &s
         const unsigned tag = tag_base + static_cast<unsigned>(j) + 1u;
         unsigned long long *dbg = (sc.profile && member == 0 && j == 4) ? sc.dbg : nullptr;
         KB_TCYC(0);
-        team_queries(ts, sh, m, tq, nq, j, max_dist, kscale, member, tag, dbg);
+        team_queries(ts, sh, m, sm, nq, j, max_dist, kscale, member, tag, dbg);
         team_gather(ts, sh, T, tag);
         KB_TCYC(6);
-        if (threadIdx.x == BLOCK - 1) {  // a thread that owns no source point (TQ_CAP < BLOCK - 32)
+        if (threadIdx.x == BLOCK - 1) {  // a thread that owns no source point (TQ_MAX < BLOCK - 32)
             double sys[NACC];
 #pragma unroll
             for (int i = 0; i < NACC; ++i) sys[i] = sh.red[i];

@@ -98,7 +98,7 @@ __device__ __forceinline__ void threshold_update(const SE3 &dev, double min_moti
 #define KB_STAMP(i) \
     if (P.sc.profile && blockIdx.x == 0 && threadIdx.x == 0) P.res->t_ns[i] = globaltimer_ns()
 
-extern __shared__ __align__(16) unsigned char kb_dyn_smem[];  // QCache[NWARPS][QC_SLOTS] (op_icp) or QList[TQ_CAP] (op_icp_team)
+extern __shared__ __align__(16) unsigned char kb_dyn_smem[];  // QCache[NWARPS][QC_SLOTS] (op_icp) or the TeamSmem layout (op_icp_team)
 
 // Preprocess + Voxelize of one frame on the CTAs of `g` (the whole launch, or the front-end team), KissICP.cpp:38,41,70-75.
 // Three barriers of `g` inside; the caller provides the one behind it. No timestamps => `motion` is not used.
@@ -173,15 +173,14 @@ __global__ void __launch_bounds__(BLOCK, 1) k_register_frame(const FrameParams P
     const bool icp_runs = __ldcg(&P.m.counters[C_LIVE]) != 0 && P.max_iter > 0;  // voxel_map.Empty() -> initial_guess
     int T = 0;
     if (icp_runs && P.icp_team_q > 0 && P.m.cap <= NN_FLAT_CAP && (static_cast<unsigned long long>(P.m.mask) + 1) * P.m.cap < (1ull << 31)) {
-        T = icp_team_size(n_src, min(P.icp_team_q, TQ_CAP), G);
-        if (!icp_team_fits(n_src, T)) T = 0;
+        T = icp_team_size(n_src, P.icp_team_q, G, P.team.smem_bytes);
     }
     if (T > 0) {
         icp_fill_pass(g, sh, P.m, fr.src, n_src, guess, P.team.qrec);
         g.sync();
         if (static_cast<int>(blockIdx.x) < T) {
             op_icp_team(P.team, P.sc, sh, P.m, n_src, guess, 3.0 * sigma, sigma, P.max_iter, P.conv,
-                        reinterpret_cast<QList *>(kb_dyn_smem), T, P.tag_base);
+                        kb_dyn_smem, T, P.tag_base);
             if (blockIdx.x == 0 && threadIdx.x == 0) team_publish(P.team, sh);
         } else if (P.next_in != nullptr && 2 * (G - T) >= G) {
             // the CTAs the team does not need register nothing now: they run the next frame's front end
@@ -348,15 +347,14 @@ __global__ void __launch_bounds__(BLOCK, 1) k_icp(const IcpParams P) {
     int T = 0;
     if (__ldcg(&P.m.counters[C_LIVE]) != 0 && P.max_iter > 0 && P.icp_team_q > 0 && P.use_qcache && P.m.cap <= NN_FLAT_CAP &&
         (static_cast<unsigned long long>(P.m.mask) + 1) * P.m.cap < (1ull << 31)) {
-        T = icp_team_size(P.n, min(P.icp_team_q, TQ_CAP), static_cast<int>(gridDim.x));
-        if (!icp_team_fits(P.n, T)) T = 0;
+        T = icp_team_size(P.n, P.icp_team_q, static_cast<int>(gridDim.x), P.team.smem_bytes);
     }
     if (T > 0) {
         icp_fill_pass(g, sh, P.m, P.src, P.n, P.guess, P.team.qrec);
         g.sync();
         if (static_cast<int>(blockIdx.x) >= T) return;
         op_icp_team(P.team, P.sc, sh, P.m, P.n, P.guess, P.max_dist, P.kscale, P.max_iter, P.conv,
-                    reinterpret_cast<QList *>(kb_dyn_smem), T, P.tag_base);
+                    kb_dyn_smem, T, P.tag_base);
     } else {
         op_icp(g, P.sc, sh, P.m, P.src, P.work, P.n, P.guess, P.max_dist, P.kscale, P.max_iter, P.conv,
                P.use_qcache ? reinterpret_cast<QCache *>(kb_dyn_smem) : nullptr, P.tag_base);
