@@ -12,6 +12,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <memory>
+#include <mutex>
 #include <numeric>
 #include <string>
 #include <vector>
@@ -107,6 +108,9 @@ size_t pow2_at_least(size_t v) {
     return p;
 }
 
+int watchdog_check_fwd(int device);
+int watchdog_init_fwd(int device);
+
 // execution context: device, stream, persistent-grid size and the cross-CTA scratch
 struct Exec {
     int device = 0;
@@ -127,6 +131,7 @@ struct Exec {
         if (device_count() <= 0) return fail(KB_ERR_NO_DEVICE, "no CUDA device visible (this library has no CPU fallback)");
         device = tl_device;
         CK(cudaSetDevice(device));
+        RET(watchdog_init_fwd(device));
         if (tl_user_stream) {
             stream = tl_user_stream;
         } else {
@@ -203,9 +208,45 @@ struct Exec {
     }
     int sync() {
         CK(cudaStreamSynchronize(stream));
-        return KB_OK;
+        return watchdog_check_fwd(device);
     }
 };
+
+// the device watchdog's report (device_ops.cuh): mapped host words per device, checked after every synchronisation
+struct WatchdogHost {
+    unsigned *host = nullptr;  // [0] flag [1] code [2] block [3] thread [4] a [5] b
+};
+WatchdogHost g_wd[64];
+int watchdog_init(int device) {
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lock(mu);
+    if (device < 0 || device >= 64 || g_wd[device].host) return KB_OK;
+    unsigned *h = nullptr, *d = nullptr;
+    CK(cudaHostAlloc(&h, 8 * sizeof(unsigned), cudaHostAllocMapped));
+    std::memset(h, 0, 8 * sizeof(unsigned));
+    CK(cudaHostGetDevicePointer(&d, h, 0));
+    CK(cudaMemcpyToSymbol(g_kb_wd_host, &d, sizeof(d)));
+    unsigned init[8] = {0, 0, 0, 0, 0, 0, 0, 22};  // give up after 2^22 polls (seconds)
+    if (const char *e = std::getenv("KB_WATCHDOG_SHIFT")) init[7] = static_cast<unsigned>(std::max(10, std::min(std::atoi(e), 31)));
+    CK(cudaMemcpyToSymbol(g_kb_wd, init, sizeof(init)));
+    g_wd[device].host = h;
+    return KB_OK;
+}
+// after a synchronisation: did a spin loop of the last launches give up?
+int watchdog_check(int device) {
+    unsigned *h = (device >= 0 && device < 64) ? g_wd[device].host : nullptr;
+    if (!h || !*reinterpret_cast<volatile unsigned *>(h)) return KB_OK;
+    const unsigned code = h[1], block = h[2], thread = h[3], a = h[4], b = h[5];
+    h[0] = 0;
+    unsigned zero = 0;
+    cudaMemcpyToSymbol(g_kb_wd, &zero, sizeof(zero));  // re-arm
+    static const char *names[] = {"?", "grid barrier", "ICP gather", "ICP result record", "ICP team gather", "NN bulk copy"};
+    return fail(KB_ERR_CUDA, "device watchdog: a kernel gave up waiting at the %s (block %u, thread %u, a=%u, b=%u); the results of that launch are invalid",
+                names[code < 6 ? code : 0], block, thread, a, b);
+}
+
+int watchdog_check_fwd(int device) { return watchdog_check(device); }
+int watchdog_init_fwd(int device) { return watchdog_init(device); }
 
 int make_exec(std::shared_ptr<Exec> *out) {
     auto e = std::make_shared<Exec>();
@@ -1454,6 +1495,7 @@ int kb_pipeline_register_frames(kb_pipeline *p, const void *const *xyz, const si
             continue;
         }
         attempts = 0;
+        RET(watchdog_check(ex.device));
         p->next_id = id0 + static_cast<long long>(k) + 1;
         const int st = pipeline_absorb(p, r, n[k], id0 + static_cast<long long>(k));
         if (st != KB_OK) {

@@ -139,6 +139,37 @@ __device__ __forceinline__ bool ll_load(const uint4 *p, unsigned tag, double *v)
 
 __device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 
+// ------------------------------------------------------------------------------------------
+// watchdog of the spin loops: the kernels below wait for each other with hand-rolled barriers and tagged polls. A
+// protocol bug (or a CTA that died) would otherwise spin forever and take the GPU with it. Every spin loop counts
+// its polls; after 2^g_kb_wd[7] of them (seconds) the loop gives up, raises g_kb_wd[0] — which every other spin
+// loop checks every 1024 polls and then leaves too — and reports where it was stuck to a word of mapped host
+// memory. The launch then finishes with garbage and the host turns the flag into KB_ERR_CUDA.
+// ------------------------------------------------------------------------------------------
+__device__ unsigned g_kb_wd[8];          // [0] abort flag, [7] log2 of the poll limit (host-set)
+__device__ unsigned *g_kb_wd_host;       // mapped host memory: [0] flag, [1] code, [2] block, [3] thread, [4] a, [5] b
+enum WatchdogCode { WD_GRID_BARRIER = 1, WD_ICP_GATHER16 = 2, WD_ICP_RESULT = 3, WD_TEAM_GATHER = 4, WD_NN_BULK = 5 };
+
+__device__ __noinline__ bool kb_spin_giveup(unsigned spins, int code, unsigned a, unsigned b) {
+    if (*reinterpret_cast<volatile unsigned *>(&g_kb_wd[0]) != 0u) return true;  // somebody gave up: everybody leaves
+    if ((spins >> g_kb_wd[7]) == 0u) return false;
+    if (atomicCAS(&g_kb_wd[0], 0u, 1u) == 0u && g_kb_wd_host != nullptr) {
+        volatile unsigned *h = g_kb_wd_host;
+        h[1] = static_cast<unsigned>(code);
+        h[2] = blockIdx.x;
+        h[3] = threadIdx.x;
+        h[4] = a;
+        h[5] = b;
+        __threadfence_system();
+        h[0] = 1u;
+    }
+    return true;
+}
+// call once per poll; true = stop waiting
+__device__ __forceinline__ bool kb_spin_check(unsigned &spins, int code, unsigned a, unsigned b) {
+    return ((++spins & 0x3ffu) == 0u) && kb_spin_giveup(spins, code, a, b);
+}
+
 // A Grid is the set of CTAs that take part in a barrier: the whole launch (init) or a TEAM of consecutive
 // CTAs (init_team) with its own counter word — k_register_frame splits the launch into an ICP team and a
 // front-end team that work on different scans at the same time. rank/size replace blockIdx.x/gridDim.x in
@@ -166,7 +197,9 @@ struct Grid {
             target += static_cast<unsigned>(size);
             unsigned old;  // release our writes / acquire everybody else's
             asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(old) : "l"(bar) : "memory");
+            unsigned spins = 0;
             while (ld_relaxed_u32(bar) < target) {
+                if (kb_spin_check(spins, WD_GRID_BARRIER, target, static_cast<unsigned>(size))) break;
             }
             __threadfence();  // acquire side; a gpu-scope fence also drops this SM's L1 lines (plain loads follow)
         }
@@ -1188,8 +1221,10 @@ __device__ __forceinline__ double ll_gather16(const uint4 *base, int stride, int
     const bool active = e < NPART && m < count;
     double v = 0.0;
     bool ok = !active;
+    unsigned spins = 0;
     while (!__all_sync(FULL, ok)) {
         if (!ok) ok = ll_load(&base[static_cast<size_t>(e) * stride + first + m], tag, &v);
+        if (__any_sync(FULL, kb_spin_check(spins, WD_ICP_GATHER16, tag, static_cast<unsigned>(first)))) break;
     }
     if (!active) v = 0.0;
 #pragma unroll
@@ -1308,16 +1343,20 @@ __device__ __noinline__ void op_icp(Grid &g, const Scratch &sc, Shared &sh, cons
             const int l = threadIdx.x;
             double v = 0.0;
             bool ok = l >= 8;
+            unsigned spins = 0;
             while (!__all_sync(FULL, ok)) {
                 if (!ok) ok = ll_load(&sc.ll_res[l], tag, &v);
+                if (__any_sync(FULL, kb_spin_check(spins, WD_ICP_RESULT, tag, 0u))) break;
             }
             if (dbg_on) { KB_CYC(sc, 11); }
             const double dn = __shfl_sync(FULL, v, 7);
             if (dn != 0.0) {  // converged / out of iterations: the final pose rides in chunks 8..14
                 ok = l >= 7;
                 double f = 0.0;
+                spins = 0;
                 while (!__all_sync(FULL, ok)) {
                     if (!ok) ok = ll_load(&sc.ll_res[8 + l], tag, &f);
+                    if (__any_sync(FULL, kb_spin_check(spins, WD_ICP_RESULT, tag, 1u))) break;
                 }
                 const double qx = __shfl_sync(FULL, f, 0), qy = __shfl_sync(FULL, f, 1), qz = __shfl_sync(FULL, f, 2);
                 const double qw = __shfl_sync(FULL, f, 3), tx = __shfl_sync(FULL, f, 4), ty = __shfl_sync(FULL, f, 5);

@@ -435,6 +435,7 @@ __device__ __forceinline__ void team_gather(const TeamScratch &ts, Shared &sh, i
             ok[u] = lane + 32 * u >= T;
         }
         bool all = false;
+        unsigned spins = 0;
         while (!all) {
             all = true;
 #pragma unroll
@@ -443,6 +444,7 @@ __device__ __forceinline__ void team_gather(const TeamScratch &ts, Shared &sh, i
                 all = all && ok[u];
             }
             all = __all_sync(FULL, all);
+            if (!all && __any_sync(FULL, kb_spin_check(spins, WD_TEAM_GATHER, tag, static_cast<unsigned>(v)))) break;
         }
         double s = 0.0;
 #pragma unroll

@@ -660,7 +660,9 @@ __global__ void __launch_bounds__(NNB_WARPS * 32, 3) k_nn_query_bulk(const MapVi
         // (2) reduce query i
         NNResult r;
         if (cur.staged) {
+            unsigned spins = 0;
             while (!mbar_try_wait(bar, phase)) {
+                if (kb_spin_check(spins, WD_NN_BULK, static_cast<unsigned>(i), phase)) break;
             }
             phase ^= 1u;
             if (cur.cnt & 1) {  // pad slot of an odd voxel: can never win
