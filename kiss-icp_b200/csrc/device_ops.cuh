@@ -906,8 +906,10 @@ __device__ __forceinline__ V3 ld_point24(const double *rec) {
 // L2 round trip instead of one per occupied voxel. The minimum is taken on SQUARED distances (one sqrt per
 // query); if another candidate's square lies within a few ulps above the minimum (two squares that could round
 // to the same root) the search is redone comparing rounded roots exactly like the reference.
+// (the search proper: `w` already holds the slot / start / owner tables of the probed neighbourhood)
+__device__ __forceinline__ NNResult nn_flat_search_staged(const MapView &m, const V3 &q, int lane, WarpNN &w, int total);
+
 __device__ __forceinline__ NNResult nn_flat_search(const MapView &m, const V3 &q, int lane, WarpNN &w, int cnt, int slot) {
-    const int cap = m.cap;
     int incl = cnt;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -923,6 +925,11 @@ __device__ __forceinline__ NNResult nn_flat_search(const MapView &m, const V3 &q
         for (int k = 0; k < cnt; ++k) w.owner[start + k] = static_cast<unsigned char>(lane);
     }
     __syncwarp();
+    return nn_flat_search_staged(m, q, lane, w, total);
+}
+
+__device__ __forceinline__ NNResult nn_flat_search_staged(const MapView &m, const V3 &q, int lane, WarpNN &w, int total) {
+    const int cap = m.cap;
     double b2 = DBL_MAX, s2 = DBL_MAX;
     int bseq = INT_MAX;
     V3 bp{0, 0, 0};

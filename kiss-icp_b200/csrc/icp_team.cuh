@@ -7,9 +7,9 @@
 //     runs the 27-voxel search of GetClosestNeighbor (core/VoxelHashMap.cpp:46-70) and leaves, per point, the
 //     short list of map points that can still become its nearest neighbour while it moves by <= R
 //     (exactness argument: QCache in device_ops.cuh);
-//   * the iterations then run on a small team (T = ceil(n / 128) CTAs, 22 for a KITTI scan): ONE thread per
-//     source point walks its list (the iteration is a dependent chain: cross-lane merges per point would only
-//     lengthen it), one 32-shuffle sum per warp, and the T partial systems meet in ONE all-gather of epoch-tagged
+//   * the iterations then run on a small team (T = ceil(n / 64) CTAs, 43 for a KITTI scan): four lanes per source
+//     point walk its list — candidate COORDINATES staged in shared memory, interleaved so that the walk is
+//     bank-conflict free — and the T partial systems meet in ONE all-gather of epoch-tagged
 //     16-byte chunks: every team CTA polls all T partials, adds them in the same fixed order and solves the
 //     6x6 itself, so there is no coordinator, no broadcast hop and one L2 round trip per iteration;
 //   * the rest of the launch (the other ~126 SMs) is free meanwhile: k_register_frame runs the NEXT scan's
@@ -23,8 +23,10 @@
 namespace kb {
 
 constexpr int TEAM_MAX = 128;   // CTAs of an ICP team (one tagged chunk per value and member; a lane gathers 4 members)
-constexpr int TQ_PER_CTA = 64;  // source points per team CTA by default (one thread each: 2 warps)
-constexpr int TQ_MAX = 160;     // upper bound of source points per team CTA (threads 0..159; the solver is thread 511)
+constexpr int TQ_LANES = 4;     // lanes that share one source point in the list walk
+constexpr int TQ_PER_WARP = 32 / TQ_LANES;
+constexpr int TQ_PER_CTA = 64;  // source points per team CTA by default (8 warps)
+constexpr int TQ_MAX = 120;     // upper bound of source points per team CTA (warps 0..14; the solver is thread 511)
 
 // Output of the fill pass for one source point (global memory): the list holds POINT INDICES (slot * cap + k) in the
 // reference's visiting order (voxel_shifts order, then insertion order), so the first strict minimum over the
@@ -32,50 +34,51 @@ constexpr int TQ_MAX = 160;     // upper bound of source points per team CTA (th
 struct QList {
     int count;      // >= 0: idx[0..count) valid; -1: not cacheable (too many candidates / max_points_per_voxel > 32)
     int full;       // points of the whole 27-voxel neighbourhood (bookkeeping of algorithmic bytes)
-    int any_voxel;  // list valid whatever voxel the point is in (d* + 3R < voxel_size)
     int vx, vy, vz; // voxel at fill time
-    int pad[2];
+    int pad[3];
     double pf[3];   // position at fill time (= initial_guess * source point)
     int idx[QC_MAX];
     int tail[2];    // 320 bytes
 };
 static_assert(sizeof(QList) % 16 == 0 && sizeof(QList) == sizeof(QListRaw), "QList records are 16-byte aligned; Shared::rlist holds one per warp");
 
-// A source point inside its team CTA (shared memory): state + where its candidate COORDINATES are. The coordinates
-// of the 32 points of a warp are interleaved — candidate k, component c of the point in column q sits at
-// coords[((k * 3 + c) * 32 + ((q + k) & 31)] — so that (i) the thread-per-point walk (32 threads, same k) and
-// (ii) the warp that stages one point's list (32 lanes, consecutive k, same q) both hit 32 different banks.
-// (Reading the coordinates through L1 instead was measured: every thread's load is its own L1 wavefront and the
-// walk alone took 8000 cycles per iteration.)
+// A source point inside its team CTA (shared memory): state + where its candidate COORDINATES are. A warp owns 8
+// points, FOUR lanes per point: lane (q8, j) walks candidates k = j, j + 4, ... The coordinates of a warp's points
+// are interleaved — candidate k, component c of point q8 sits in row k / 4, column (4 q8 + k) & 31 of a
+// [rows][3][32] block — so that (i) the walk (32 lanes = 8 points x 4 consecutive k of the same row) and (ii) the
+// warp that stages one point's list (32 lanes = 32 consecutive k of one point) both hit 32 different banks.
+// (Reading the coordinates through L1 instead was measured: every lane's load is its own L1 wavefront and the walk
+// alone took 8000 cycles per iteration; one thread per point with this layout: 4500 cycles, a chain of ~30
+// candidates per thread.)
 struct TQHead {
     int count;      // >= 0: candidates staged; -1: not cacheable (searched again every iteration)
-    int full, any_voxel, vx, vy, vz;
-    int direct;     // nn[] holds this iteration's answer (written by a re-search inside the iteration)
-    int pad;
+    int full, vx, vy, vz;
+    int pad[3];
     double pf[3];   // position when the list was made
     double p[3];    // current position (TransformPoints is applied in place, Registration.cpp:55-58,160)
-    double nn[4];   // nearest neighbour and distance of a re-search
-    double pad2;    // 120 bytes: consecutive records start 30 words apart (no 8-byte bank conflict between 16 lanes)
+    double nn[4];   // nearest neighbour and distance found by a re-search inside the iteration
+    double pad2;    // 120 bytes
 };
 static_assert(sizeof(TQHead) == 120, "TQHead layout");
 
 struct TeamSmem {
     TQHead *heads;   // [qmax]
-    double *coords;  // [warps][K][3][32]
-    int K;           // candidate slots per source point
+    double *coords;  // [warps][K / 4][3][32]
+    int K;           // candidate slots per source point (multiple of 4)
 };
-// carve the dynamic shared memory of a team CTA for qmax source points; K < 16 means "does not fit"
+// carve the dynamic shared memory of a team CTA for qmax source points
 __device__ __forceinline__ TeamSmem team_smem(unsigned char *dyn, int dyn_bytes, int qmax) {
     TeamSmem t;
     const int head_bytes = (qmax * static_cast<int>(sizeof(TQHead)) + 15) & ~15;
-    const int warps = (qmax + 31) >> 5;
+    const int warps = (qmax + TQ_PER_WARP - 1) / TQ_PER_WARP;
     t.heads = reinterpret_cast<TQHead *>(dyn);
     t.coords = reinterpret_cast<double *>(dyn + head_bytes);
-    t.K = (warps > 0 && dyn_bytes > head_bytes) ? min(QC_MAX, (dyn_bytes - head_bytes) / (warps * 768)) : 0;
+    t.K = (warps > 0 && dyn_bytes > head_bytes) ? 4 * min(QC_MAX / 4, (dyn_bytes - head_bytes) / (warps * 768)) : 0;
     return t;
 }
-__device__ __forceinline__ double *tq_coord(const TeamSmem &ts, int li, int k) {  // component c at [c * 32]
-    return ts.coords + (static_cast<size_t>(li >> 5) * ts.K + k) * 96 + (((li & 31) + k) & 31);
+// candidate k of source point li: component c at [c * 32]
+__device__ __forceinline__ double *tq_coord(const TeamSmem &ts, int li, int k) {
+    return ts.coords + (static_cast<size_t>(li / TQ_PER_WARP) * (ts.K >> 2) + (k >> 2)) * 96 + ((4 * (li & (TQ_PER_WARP - 1)) + k) & 31);
 }
 
 struct TeamScratch {
@@ -93,13 +96,18 @@ __device__ __forceinline__ int icp_team_size(int n, int q_per_cta, int grid, int
     if (T > min(grid, TEAM_MAX)) return 0;
     const int qmax = (n + T - 1) / T;
     const int head_bytes = (qmax * static_cast<int>(sizeof(TQHead)) + 15) & ~15;
-    const int warps = (qmax + 31) >> 5;
-    if (warps > 0 && (smem_bytes - head_bytes) / (warps * 768) < 24) return 0;
+    const int warps = (qmax + TQ_PER_WARP - 1) / TQ_PER_WARP;
+    if (warps > 0 && 4 * ((smem_bytes - head_bytes) / (warps * 768)) < 24) return 0;
     return T;
 }
 
-// GetClosestNeighbor for one point by one warp (like nn_search_warp) + its candidate list into *out
+// GetClosestNeighbor (core/VoxelHashMap.cpp:46-70) for one point by one warp + the list of candidates that can
+// still become its nearest neighbour while it moves by <= R (QCache's exactness argument, device_ops.cuh) into *out
 // (generic pointer: global memory in the fill pass, shared memory inside an iteration).
+// ONE pass over the neighbourhood: every lane keeps the squared distances and point indices of its <= 8 candidates
+// in registers (all loads of the neighbourhood are in flight together: one L2 round trip), the warp takes the
+// minimum, and the list is filtered from the registers. Neighbourhoods with more than 256 points take two passes.
+constexpr int NNL_R = 8;
 __device__ __noinline__ NNResult nn_search_list(const MapView &m, const V3 &q, int lane, WarpNN &w, QList *out,
                                                 double cache_radius) {
     const int3 v = point_to_voxel(q.x, q.y, q.z, m.vdiv);
@@ -131,41 +139,130 @@ __device__ __noinline__ NNResult nn_search_list(const MapView &m, const V3 &q, i
         nn_reduce(best, bseq, bp);
         r = NNResult{best, bp, total};
     } else {
-        r = nn_flat_search(m, q, lane, w, cnt, slot);
-        const int total = r.candidates;
-        // second pass (L1-hot): the candidates within d* + 2R of the point, in reference order
-        if (r.d < DBL_MAX) {
-            const double thr = r.d + 2.0 * cache_radius;
-            const double thr2 = thr * thr * (1.0 + 1e-12);
-            count = 0;
-            constexpr int U2 = 4;
-            for (int base = 0; base < total; base += 32 * U2) {
+        // flatten the neighbourhood over the lanes: candidate j (reference order) -> lane j % 32, register j / 32
+        int incl = cnt;
 #pragma unroll
-                for (int u = 0; u < U2; ++u) {
-                    const int j = base + u * 32 + lane;
-                    bool keep = false;
-                    int gi = 0;
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(FULL, incl, o);
+            if (lane >= o) incl += t;
+        }
+        const int start = incl - cnt;
+        const int total = __shfl_sync(FULL, incl, 31);
+        __syncwarp();
+        if (lane < 27) {
+            w.slot[lane] = slot;
+            w.start[lane] = start;
+            for (int k = 0; k < cnt; ++k) w.owner[start + k] = static_cast<unsigned char>(lane);
+        }
+        __syncwarp();
+        if (total <= 32 * NNL_R) {
+            double d2[NNL_R];
+            int gi[NNL_R];
+#pragma unroll
+            for (int h = 0; h < NNL_R; h += 4) {  // (the loads of both halves are independent: one round trip)
+                V3 c[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int j = (h + u) * 32 + lane;
+                    gi[h + u] = -1;
                     if (j < total) {
                         const int vi = w.owner[j];
-                        gi = w.slot[vi] * cap + (j - w.start[vi]);
-                        const V3 c = ld_point24(m.points + static_cast<size_t>(gi) * 3);
-                        keep = sqnorm(c - q) <= thr2;
+                        gi[h + u] = w.slot[vi] * cap + (j - w.start[vi]);
+                        c[u] = ld_point24(m.points + static_cast<size_t>(gi[h + u]) * 3);
                     }
-                    const unsigned mask = __ballot_sync(FULL, keep);
-                    const int pos = count + __popc(mask & ((1u << lane) - 1u));
-                    if (keep && pos < QC_MAX) out->idx[pos] = gi;
-                    count += __popc(mask);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) d2[h + u] = (gi[h + u] >= 0) ? sqnorm(c[u] - q) : DBL_MAX;
+            }
+            double b2 = DBL_MAX, s2 = DBL_MAX;
+            int bseq = INT_MAX, bg = -1;
+#pragma unroll
+            for (int u = 0; u < NNL_R; ++u) {
+                if (d2[u] < b2) {
+                    s2 = b2;
+                    b2 = d2[u];
+                    bseq = u * 32 + lane;
+                    bg = gi[u];
+                } else if (d2[u] > b2 && d2[u] < s2) {
+                    s2 = d2[u];
                 }
             }
-            if (count > QC_MAX) count = -1;
+            const double mine = b2;
+            V3 bp{0, 0, 0};
+            nn_reduce(b2, bseq, bp);  // (bp is a dummy: the winner's point is re-read below, it is L1-hot)
+            const double lim = b2 * (1.0 + 8.8817841970012523e-16);
+            const bool near = (mine > b2 && mine <= lim) || (s2 <= lim);
+            if (!__any_sync(FULL, near)) {
+                if (total > 0) {
+                    const int gw = __shfl_sync(FULL, bg, bseq & 31);  // the winning lane's own minimum IS the warp minimum
+                    bp = ld_point24(m.points + static_cast<size_t>(gw) * 3);
+                }
+                r = NNResult{total > 0 ? sqrt(b2) : DBL_MAX, bp, total};
+            } else {  // near tie of squared distances: compare rounded roots in reference order, like the reference
+                double best = DBL_MAX, best_d2 = DBL_MAX;
+                bseq = INT_MAX;
+                bp = V3{0, 0, 0};
+#pragma unroll
+                for (int u = 0; u < NNL_R; ++u)
+                    if (gi[u] >= 0) {
+                        const double *pp = m.points + static_cast<size_t>(gi[u]) * 3;
+                        nn_consider(V3{pp[0], pp[1], pp[2]}, q, u * 32 + lane, best, best_d2, bseq, bp);
+                    }
+                nn_reduce(best, bseq, bp);
+                r = NNResult{best, bp, total};
+            }
+            // the candidates within d* + 2R of the point, in reference order
+            if (r.d < DBL_MAX) {
+                const double thr = r.d + 2.0 * cache_radius;
+                const double thr2 = thr * thr * (1.0 + 1e-12);
+                count = 0;
+#pragma unroll
+                for (int u = 0; u < NNL_R; ++u) {
+                    if (u * 32 < total) {  // warp-uniform
+                        const bool keep = d2[u] <= thr2;  // (DBL_MAX where there is no candidate)
+                        const unsigned mask = __ballot_sync(FULL, keep);
+                        const int pos = count + __popc(mask & ((1u << lane) - 1u));
+                        if (keep && pos < QC_MAX) out->idx[pos] = gi[u];
+                        count += __popc(mask);
+                    }
+                }
+                if (count > QC_MAX) count = -1;
+            } else {
+                count = 0;  // empty neighbourhood: stays empty while the point stays in its voxel
+            }
         } else {
-            count = 0;  // empty neighbourhood: stays empty while the point stays in its voxel
+            r = nn_flat_search_staged(m, q, lane, w, total);
+            if (r.d < DBL_MAX) {  // second pass (L1-hot)
+                const double thr = r.d + 2.0 * cache_radius;
+                const double thr2 = thr * thr * (1.0 + 1e-12);
+                count = 0;
+                constexpr int U2 = 4;
+                for (int base = 0; base < total; base += 32 * U2) {
+#pragma unroll
+                    for (int u = 0; u < U2; ++u) {
+                        const int j = base + u * 32 + lane;
+                        bool keep = false;
+                        int g = 0;
+                        if (j < total) {
+                            const int vi = w.owner[j];
+                            g = w.slot[vi] * cap + (j - w.start[vi]);
+                            keep = sqnorm(ld_point24(m.points + static_cast<size_t>(g) * 3) - q) <= thr2;
+                        }
+                        const unsigned mask = __ballot_sync(FULL, keep);
+                        const int pos = count + __popc(mask & ((1u << lane) - 1u));
+                        if (keep && pos < QC_MAX) out->idx[pos] = g;
+                        count += __popc(mask);
+                    }
+                }
+                if (count > QC_MAX) count = -1;
+            } else {
+                count = 0;
+            }
         }
     }
     if (lane == 0) {
         out->count = count;
         out->full = r.candidates;
-        out->any_voxel = (r.d < DBL_MAX && r.d + 3.0 * cache_radius < m.voxel_size) ? 1 : 0;
         out->vx = v.x;
         out->vy = v.y;
         out->vz = v.z;
@@ -190,45 +287,39 @@ __device__ __noinline__ void icp_fill_pass(const Grid &g, Shared &sh, const MapV
 }
 
 // the 16 distinct entries of one correspondence's J^T w J / J^T w r, each formed exactly as Eigen forms
-// (J^T * w) * J entry by entry (icp_term's formulas, device_ops.cuh)
-__device__ __forceinline__ void icp_term16(const V3 &s, const V3 &t, double kscale, double a[NACC]) {
+// (J^T * w) * J entry by entry (icp_term's formulas, device_ops.cuh); lane j of the point's four lanes adds
+// entries 4 j .. 4 j + 3 to acc
+__device__ __forceinline__ void icp_term4(int j, const V3 &s, const V3 &t, double kscale, double acc[4]) {
     const V3 r = s - t;
     const double r2 = sqnorm(r);
     const double w = (kscale * kscale) * fast_rcp((kscale + r2) * (kscale + r2));  // ~1 ulp from the reference's division
     const double xw = s.x * w, yw = s.y * w, zw = s.z * w;
-    a[0] = w;
-    a[1] = xw;
-    a[2] = yw;
-    a[3] = zw;
-    a[4] = zw * s.z + yw * s.y;  // (3,3)
-    a[5] = -(xw * s.y);          // (4,3)
-    a[6] = zw * s.z + xw * s.x;  // (4,4)
-    a[7] = -(xw * s.z);          // (5,3)
-    a[8] = -(yw * s.z);          // (5,4)
-    a[9] = yw * s.y + xw * s.x;  // (5,5)
-    a[10] = w * r.x;
-    a[11] = w * r.y;
-    a[12] = w * r.z;
-    a[13] = -(zw * r.y) + yw * r.z;
-    a[14] = zw * r.x - xw * r.z;
-    a[15] = -(yw * r.x) + xw * r.y;
-}
-
-// sum of 16 values per lane over the 32 lanes of a warp in 32 shuffles instead of 160: at every level a lane keeps
-// one half of its values and hands the other half to its partner. On return a[0] of lanes 2k and 2k+1 holds the warp
-// total of value k. Fixed order -> deterministic.
-__device__ __forceinline__ void warp_sum16(double a[NACC], int lane) {
-#pragma unroll
-    for (int half = 8, mask = 16; half >= 1; half >>= 1, mask >>= 1) {
-        const bool up = (lane & mask) != 0;
-#pragma unroll
-        for (int i = 0; i < half; ++i) {
-            const double send = up ? a[i] : a[i + half];
-            const double keep = up ? a[i + half] : a[i];
-            a[i] = keep + __shfl_xor_sync(FULL, send, mask);
-        }
+    double a0, a1, a2, a3;
+    if (j == 0) {
+        a0 = w;
+        a1 = xw;
+        a2 = yw;
+        a3 = zw;
+    } else if (j == 1) {
+        a0 = zw * s.z + yw * s.y;  // (3,3)
+        a1 = -(xw * s.y);          // (4,3)
+        a2 = zw * s.z + xw * s.x;  // (4,4)
+        a3 = -(xw * s.z);          // (5,3)
+    } else if (j == 2) {
+        a0 = -(yw * s.z);          // (5,4)
+        a1 = yw * s.y + xw * s.x;  // (5,5)
+        a2 = w * r.x;
+        a3 = w * r.y;
+    } else {
+        a0 = w * r.z;
+        a1 = -(zw * r.y) + yw * r.z;
+        a2 = zw * r.x - xw * r.z;
+        a3 = -(yw * r.x) + xw * r.y;
     }
-    a[0] += __shfl_xor_sync(FULL, a[0], 1);
+    acc[0] += a0;
+    acc[1] += a1;
+    acc[2] += a2;
+    acc[3] += a3;
 }
 
 // stage one source point's candidate list (indices -> coordinates) into the interleaved block of its owner warp;
@@ -247,7 +338,6 @@ __device__ __forceinline__ void team_stage(const TeamSmem &sm, const MapView &m,
         TQHead &h = sm.heads[li];
         h.count = cnt;
         h.full = src->full;
-        h.any_voxel = src->any_voxel;
         h.vx = src->vx;
         h.vy = src->vy;
         h.vz = src->vz;
@@ -258,7 +348,7 @@ __device__ __forceinline__ void team_stage(const TeamSmem &sm, const MapView &m,
 }
 
 // T_icp = estimation * T_icp (Registration.cpp:161) + work counters of the iteration that was just solved. Run by the
-// solver thread (BLOCK - 1, owns no source point) while the other warps walk their lists for the NEXT iteration.
+// solver thread (BLOCK - 1, its warp owns no source point) while the other warps walk their lists for the NEXT iteration.
 __device__ __forceinline__ void team_accumulate(Shared &sh) {
     sh.t_icp = se3_mul_fast(sh.pending, sh.t_icp);
     sh.cand_total += sh.red[NACC + 1];
@@ -268,131 +358,168 @@ __device__ __forceinline__ void team_accumulate(Shared &sh) {
 #define KB_TCYC(i) \
     if (dbg != nullptr && threadIdx.x == 0) dbg[16 + (i)] = static_cast<unsigned long long>(clock64())
 
-// DataAssociation + BuildLinearSystem (Registration.cpp:60-121) for this CTA's source points, iteration j, ONE THREAD
-// PER SOURCE POINT: the loop is a dependent chain, so what counts is the length of the per-point instruction chain,
-// not issue slots — a thread walks its own candidate list (conflict-free shared memory, independent distances in
-// flight) with no cross-lane merges; the only cross-lane work is one 32-shuffle sum per warp. Stale lists are
-// collected in a queue and searched again by ALL warps of the CTA (the warps without source points have nothing else
-// to do). The CTA's partial system goes out as tagged chunks ll[parity][value][member].
+// DataAssociation + BuildLinearSystem (Registration.cpp:60-121) for this CTA's source points, iteration j. The loop is a
+// dependent chain, so what counts is the length of the per-point instruction chain: four lanes share a point (8
+// points per warp), each walks a quarter of the candidate list from conflict-free shared memory, two shuffle levels
+// merge them, and the 16 accumulators are split over the four lanes (one 3-level shuffle sum per warp).
+//
+// When is the staged list still exact? Let p_f be where it was made (d* the nearest distance then, the list = all
+// points of the 27 voxels around p_f within d* + 2R of p_f), p the current position with |p - p_f| <= R, and d_S the
+// smallest distance from p to the list. A point x of the CURRENT 27-voxel neighbourhood that is not in the list is
+// either in the old neighbourhood, then |x - p_f| > d* + 2R and |x - p| > d* + R >= d_S; or outside it, then
+// |x - p_f| >= voxel_size and |x - p| >= voxel_size - R. So the list answers exactly when the voxel is unchanged, or
+// when d_S < voxel_size - R (its minimiser is then within one voxel of p, i.e. inside the current neighbourhood).
+// Otherwise (moved > R, or a far match that changed voxel) the point is queued and searched again by a whole warp —
+// ALL warps of the CTA serve that queue.
 __device__ __noinline__ void team_queries(const TeamScratch &ts, Shared &sh, const MapView &m, const TeamSmem &sm, int nq, int j,
                                           double max_dist, double kscale, int member, unsigned tag,
                                           unsigned long long *dbg) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int l4 = lane & (TQ_LANES - 1), li = tid / TQ_LANES;
     const double radius = 0.2 * m.voxel_size, r2max = radius * radius;
-    const bool have = tid < nq;
-    TQHead &t = sm.heads[have ? tid : 0];
+    const bool have = li < nq;
+    if (tid == BLOCK - 1 && j > 0) team_accumulate(sh);  // for iteration j - 1 (sh.red is rewritten behind two barriers)
+    TQHead &t = sm.heads[have ? li : 0];
     V3 p{0.0, 0.0, 0.0};
-    if (have) {
-        p = V3{t.p[0], t.p[1], t.p[2]};
-        if (j > 0) {  // TransformPoints(estimation, source)  Registration.cpp:160
-            p = se3_act(sh.pending, p);
+    double d = DBL_MAX;
+    V3 np{0.0, 0.0, 0.0};
+    bool ok = false;
+    const int nwarps_q = (nq + TQ_PER_WARP - 1) / TQ_PER_WARP;  // warps that own source points
+    if (warp < nwarps_q) {
+        int cnt = 0;
+        bool same_voxel = false;
+        if (have) {
+            p = V3{t.p[0], t.p[1], t.p[2]};
+            if (j > 0) p = se3_act(sh.pending, p);  // TransformPoints(estimation, source)  Registration.cpp:160
+            const V3 moved = p - V3{t.pf[0], t.pf[1], t.pf[2]};
+            const int3 v = point_to_voxel(p.x, p.y, p.z, m.vdiv);
+            same_voxel = t.vx == v.x && t.vy == v.y && t.vz == v.z;
+            ok = t.count >= 0 && sqnorm(moved) <= r2max;
+            cnt = ok ? t.count : 0;
+        }
+        __syncwarp();  // all four lanes have read t.p
+        if (have && l4 == 0 && j > 0) {
             t.p[0] = p.x;
             t.p[1] = p.y;
             t.p[2] = p.z;
         }
-        const V3 moved = p - V3{t.pf[0], t.pf[1], t.pf[2]};
-        const int3 v = point_to_voxel(p.x, p.y, p.z, m.vdiv);
-        const bool valid = t.count >= 0 && sqnorm(moved) <= r2max && (t.any_voxel || (t.vx == v.x && t.vy == v.y && t.vz == v.z));
-        if (!valid) sh.refill_q[atomicAdd(&sh.refill_n, 1)] = tid;
+        // first strict minimum of the squared distance over the list (= reference order); s2 = second smallest
+        // (equal squares count: an exact tie takes the slow exact path below)
+        double b2 = DBL_MAX, s2 = DBL_MAX;
+        int bk = INT_MAX;
+        constexpr int U = 4;
+        for (int k0 = l4; k0 < cnt; k0 += U * TQ_LANES) {
+            double d2[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {  // independent loads and distances in flight
+                const int k = k0 + u * TQ_LANES;
+                const double *src = tq_coord(sm, li, min(k, cnt - 1));
+                const V3 c{src[0], src[32], src[64]};
+                d2[u] = (k < cnt) ? sqnorm(c - p) : DBL_MAX;
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                s2 = fmin(s2, fmax(b2, d2[u]));
+                if (d2[u] < b2) bk = k0 + u * TQ_LANES;
+                b2 = fmin(b2, d2[u]);
+            }
+        }
+#pragma unroll
+        for (int o = 1; o < TQ_LANES; o <<= 1) {
+            const double ob2 = __shfl_xor_sync(FULL, b2, o), os2 = __shfl_xor_sync(FULL, s2, o);
+            const int ok2 = __shfl_xor_sync(FULL, bk, o);
+            s2 = fmin(fmin(s2, os2), fmax(b2, ob2));
+            if ((ob2 < b2) || (ob2 == b2 && ok2 < bk)) bk = ok2;
+            b2 = fmin(b2, ob2);
+        }
+        if (cnt > 0) {
+            const double *src = tq_coord(sm, li, bk);
+            np = V3{src[0], src[32], src[64]};
+            d = sqrt(b2);
+        }
+        // two squares within a few ulps could round to the same root: then compare rounded roots in reference
+        // order like GetClosestNeighbor does (in practice never)
+        const bool near = cnt > 0 && s2 <= b2 * (1.0 + 8.8817841970012523e-16);
+        if (__any_sync(FULL, near)) {
+            double best = DBL_MAX;
+            int ek = INT_MAX;
+            if (near)
+                for (int k = l4; k < cnt; k += TQ_LANES) {
+                    const double *src = tq_coord(sm, li, k);
+                    const double dd = norm(V3{src[0], src[32], src[64]} - p);
+                    if (dd < best) {
+                        best = dd;
+                        ek = k;
+                    }
+                }
+#pragma unroll
+            for (int o = 1; o < TQ_LANES; o <<= 1) {
+                const double ob = __shfl_xor_sync(FULL, best, o);
+                const int ok2 = __shfl_xor_sync(FULL, ek, o);
+                if ((ob < best) || (ob == best && ok2 < ek)) {
+                    best = ob;
+                    ek = ok2;
+                }
+            }
+            if (near) {
+                const double *src = tq_coord(sm, li, ek);
+                np = V3{src[0], src[32], src[64]};
+                d = best;
+            }
+        }
+        ok = ok && (same_voxel || d < (m.voxel_size - radius) * (1.0 - 1e-12));
+        if (have && !ok && l4 == 0) sh.refill_q[atomicAdd(&sh.refill_n, 1)] = li;
     }
     __syncthreads();
     KB_TCYC(1);
     const int nref = sh.refill_n;
     if (nref > 0) {  // uniform
         for (int r = warp; r < nref; r += NWARPS) {
-            const int li = sh.refill_q[r];
-            TQHead &h = sm.heads[li];
+            const int rl = sh.refill_q[r];
+            TQHead &h = sm.heads[rl];
             const V3 pq{h.p[0], h.p[1], h.p[2]};
             QList *scratch = reinterpret_cast<QList *>(&sh.rlist[warp]);
             const NNResult res = nn_search_list(m, pq, lane, sh.wnn[warp], scratch, radius);
-            team_stage(sm, m, li, scratch, lane);
+            team_stage(sm, m, rl, scratch, lane);
             if (lane == 0) {
                 h.nn[0] = res.p.x;
                 h.nn[1] = res.p.y;
                 h.nn[2] = res.p.z;
                 h.nn[3] = res.d;
-                h.direct = 1;
                 if ((scratch->count < 0 || scratch->count > sm.K) && res.d < DBL_MAX) atomicAdd(&sh.refill_over, 1);
             }
             __syncwarp();
         }
         __syncthreads();
+        if (have && !ok) {  // answered by the re-search
+            d = t.nn[3];
+            np = V3{t.nn[0], t.nn[1], t.nn[2]};
+        }
     }
     KB_TCYC(2);
-    if (tid == BLOCK - 1 && j > 0) team_accumulate(sh);  // for iteration j - 1 (sh.red is rewritten behind the next barrier)
-    const int nwarps_q = (nq + 31) >> 5;  // warps that own source points
     if (warp < nwarps_q) {
-        double a[NACC];
-#pragma unroll
-        for (int i = 0; i < NACC; ++i) a[i] = 0.0;
+        double acc[4] = {0.0, 0.0, 0.0, 0.0};
         int corr = 0;
         double cand = 0.0;
         if (have) {
-            double d;
-            V3 np;
-            if (t.direct) {  // answered by the re-search above
-                d = t.nn[3];
-                np = V3{t.nn[0], t.nn[1], t.nn[2]};
-                t.direct = 0;
-            } else {
-                // first strict minimum of the squared distance over the list (= reference order)
-                const int cnt = t.count;
-                double b2 = DBL_MAX, s2 = DBL_MAX;
-                V3 bp{0.0, 0.0, 0.0};
-                constexpr int U = 4;
-                for (int k0 = 0; k0 < cnt; k0 += U) {
-                    V3 c[U];
-                    double d2[U];
-#pragma unroll
-                    for (int u = 0; u < U; ++u) {  // independent loads and distances in flight
-                        const double *src = tq_coord(sm, tid, min(k0 + u, cnt - 1));
-                        c[u] = V3{src[0], src[32], src[64]};
-                    }
-#pragma unroll
-                    for (int u = 0; u < U; ++u) d2[u] = (k0 + u < cnt) ? sqnorm(c[u] - p) : DBL_MAX;
-#pragma unroll
-                    for (int u = 0; u < U; ++u) {
-                        if (d2[u] < b2) {
-                            s2 = b2;
-                            b2 = d2[u];
-                            bp = c[u];
-                        } else if (d2[u] > b2 && d2[u] < s2) {
-                            s2 = d2[u];
-                        }
-                    }
-                }
-                d = (cnt > 0) ? sqrt(b2) : DBL_MAX;
-                np = bp;
-                // two squares within a few ulps could round to the same root: then compare rounded roots in
-                // reference order like GetClosestNeighbor does (in practice never)
-                if (cnt > 0 && s2 <= b2 * (1.0 + 8.8817841970012523e-16)) {
-                    double best = DBL_MAX;
-                    for (int k = 0; k < cnt; ++k) {
-                        const double *src = tq_coord(sm, tid, k);
-                        const V3 c{src[0], src[32], src[64]};
-                        const double dd = norm(c - p);
-                        if (dd < best) {
-                            best = dd;
-                            np = c;
-                        }
-                    }
-                    d = best;
-                }
-            }
-            cand = t.full;
+            if (l4 == 0) cand = t.full;
             if (d < max_dist) {  // DataAssociation's gate, Registration.cpp:72
-                icp_term16(p, np, kscale, a);
-                corr = 1;
+                icp_term4(l4, p, np, kscale, acc);
+                corr = (l4 == 0) ? 1 : 0;
             }
         }
         KB_TCYC(3);
-        warp_sum16(a, lane);
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
+        for (int o = TQ_LANES; o < 32; o <<= 1) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[i] += __shfl_xor_sync(FULL, acc[i], o);
             corr += __shfl_xor_sync(FULL, corr, o);
             cand += __shfl_xor_sync(FULL, cand, o);
         }
-        if ((lane & 1) == 0) sh.warp_d[warp][lane >> 1] = a[0];
+        if (lane < TQ_LANES) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) sh.warp_d[warp][4 * lane + i] = acc[i];
+        }
         if (lane == 0) {
             sh.warp_d[warp][NACC] = static_cast<double>(corr);
             sh.warp_d[warp][NACC + 1] = cand;
@@ -475,7 +602,6 @@ __device__ __noinline__ void op_icp_team(const TeamScratch &ts, const Scratch &s
                 h.p[0] = rec->pf[0];
                 h.p[1] = rec->pf[1];
                 h.p[2] = rec->pf[2];
-                h.direct = 0;
             }
         }
     }
@@ -487,6 +613,7 @@ __device__ __noinline__ void op_icp_team(const TeamScratch &ts, const Scratch &s
         sh.refill_over = 0;
     }
     __syncthreads();
+    if (sc.profile && member == 0 && threadIdx.x == 0) sc.dbg[33] = globaltimer_ns();
     int j = 0;
     for (;; ++j) {
         if (sc.profile && member == 0 && threadIdx.x == 0 && j < 20) sc.dbg[41 + j] = globaltimer_ns();
@@ -496,7 +623,7 @@ __device__ __noinline__ void op_icp_team(const TeamScratch &ts, const Scratch &s
         team_queries(ts, sh, m, sm, nq, j, max_dist, kscale, member, tag, dbg);
         team_gather(ts, sh, T, tag);
         KB_TCYC(6);
-        if (threadIdx.x == BLOCK - 1) {  // a thread that owns no source point (TQ_MAX < BLOCK - 32)
+        if (threadIdx.x == BLOCK - 1) {  // warp 15 owns no source point (TQ_MAX = 120)
             double sys[NACC];
 #pragma unroll
             for (int i = 0; i < NACC; ++i) sys[i] = sh.red[i];
@@ -519,6 +646,7 @@ __device__ __noinline__ void op_icp_team(const TeamScratch &ts, const Scratch &s
         KB_TCYC(7);
         if (sh.flag) break;  // (T_icp = estimation * T_icp of this iteration: team_accumulate, off the critical path)
     }
+    if (sc.profile && member == 0 && threadIdx.x == 0) sc.dbg[34] = globaltimer_ns();
     if (threadIdx.x == BLOCK - 1) {
         team_accumulate(sh);
         sh.result = se3_mul(sh.t_icp, guess);  // :166

@@ -176,8 +176,11 @@ __global__ void __launch_bounds__(BLOCK, 1) k_register_frame(const FrameParams P
         T = icp_team_size(n_src, P.icp_team_q, G, P.team.smem_bytes);
     }
     if (T > 0) {
+        if (P.sc.profile && blockIdx.x == 0 && threadIdx.x == 0) P.sc.dbg[30] = globaltimer_ns();
         icp_fill_pass(g, sh, P.m, fr.src, n_src, guess, P.team.qrec);
+        if (P.sc.profile && blockIdx.x == 0 && threadIdx.x == 0) P.sc.dbg[31] = globaltimer_ns();
         g.sync();
+        if (P.sc.profile && blockIdx.x == 0 && threadIdx.x == 0) P.sc.dbg[32] = globaltimer_ns();
         if (static_cast<int>(blockIdx.x) < T) {
             op_icp_team(P.team, P.sc, sh, P.m, n_src, guess, 3.0 * sigma, sigma, P.max_iter, P.conv,
                         kb_dyn_smem, T, P.tag_base);

@@ -19,6 +19,12 @@ g = K.KissICP(K.load_config())
 for p, t in scans[:prime]:
     g.register_frame(p, t, return_clouds=False)
 g.set_profiling(True)
+def g_stats(g):
+    out = np.zeros(3)
+    N.check(N.lib().kb_pipeline_last_cache_stats(g._h, N.ptr(out)))
+    return out
+
+
 names = ["pre", "ds1", "ds2", "icp", "map", "epi"]
 for p, t in scans[prime:]:
     g.register_frame(p, t, return_clouds=False)
@@ -27,8 +33,11 @@ for p, t in scans[prime:]:
     it = g.last_iterations
     st = ns[41:41 + min(it, 20)]
     d = np.diff(st) * 1e-3
+    f = ns[30:35]
+    print("   us: fill pass (CTA 0)", round((f[1] - f[0]) * 1e-3, 1), "barrier", round((f[2] - f[1]) * 1e-3, 1), "stage lists", round((f[3] - f[2]) * 1e-3, 1),
+          "iterations", round((f[4] - f[3]) * 1e-3, 1), "cache hits/refills/overflows", g_stats(g))
     cyc = np.diff(ns[16:24])
-    print("   cycles at iteration 4 (member 0, thread 0): transform+validity", cyc[0], "refills", cyc[1], "list walk+terms", cyc[2],
+    print("   cycles at iteration 4 (member 0, thread 0): transform+validity", cyc[0], "walk -> barrier", cyc[0], "refills", cyc[1], "terms", cyc[2],
           "warp sums", cyc[3], "store partial", cyc[4], "gather", cyc[5], "solve", cyc[6])
     print("iters", it, "phases_us", dict(zip(names, np.round(g.last_profile_us, 1))),
           "iter_us first", np.round(d[:3], 2), "median", round(float(np.median(d)), 2) if len(d) else None,
