@@ -406,7 +406,7 @@ struct alignas(16) QListRaw {
 struct Shared {
     int warp_i[NWARPS + 1];
     int two[2];
-    int chunk_pref[DS_MAX_CHUNKS];  // exclusive prefix of the downsample chunk counts
+    alignas(16) int chunk_pref[DS_MAX_CHUNKS];  // exclusive prefix of the downsample chunk counts; op_icp_team: 2048 doubles of reduction scratch
     double warp_d[NWARPS][NPART];
     double warp_c[NWARPS];
     double red[NPART];
@@ -423,7 +423,7 @@ struct Shared {
     double cache_stats[3];           // NN-cache hits / fills / overflows summed over the iterations
     int flag;
     int is_last;
-    int refill_n, refill_over;   // op_icp_team: source points whose candidate list went stale this iteration
+    int refill_n[2], refill_over[2];  // op_icp_team: source points whose candidate list went stale (by iteration parity)
     int refill_q[192];
     QListRaw rlist[NWARPS];      // op_icp_team: candidate list of a re-search, before it is staged (QList, icp_team.cuh)
 };

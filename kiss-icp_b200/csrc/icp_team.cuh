@@ -27,6 +27,8 @@ constexpr int TQ_LANES = 4;     // lanes that share one source point in the list
 constexpr int TQ_PER_WARP = 32 / TQ_LANES;
 constexpr int TQ_PER_CTA = 64;  // source points per team CTA by default (8 warps)
 constexpr int TQ_MAX = 120;     // upper bound of source points per team CTA (warps 0..14; the solver is thread 511)
+constexpr int TRED_STRIDE = NACC + 1;  // row of the per-point reduction scratch: 16 entries + the gate flag (odd: conflict-free)
+static_assert(TQ_MAX * TRED_STRIDE * 8 <= DS_MAX_CHUNKS * 4, "the reduction scratch lives in Shared::chunk_pref");
 
 // Output of the fill pass for one source point (global memory): the list holds POINT INDICES (slot * cap + k) in the
 // reference's visiting order (voxel_shifts order, then insertion order), so the first strict minimum over the
@@ -75,6 +77,16 @@ __device__ __forceinline__ TeamSmem team_smem(unsigned char *dyn, int dyn_bytes,
     t.coords = reinterpret_cast<double *>(dyn + head_bytes);
     t.K = (warps > 0 && dyn_bytes > head_bytes) ? 4 * min(QC_MAX / 4, (dyn_bytes - head_bytes) / (warps * 768)) : 0;
     return t;
+}
+// (explicit shared-space loads: through the generic pointer the compiler emits LD.E with a branch per candidate)
+__device__ __forceinline__ double lds_f64(unsigned addr) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ unsigned tq_coord_addr(unsigned coords_base, int K, int li, int k) {
+    return coords_base + (static_cast<unsigned>((li / TQ_PER_WARP) * (K >> 2) + (k >> 2)) * 96u +
+                          static_cast<unsigned>((4 * (li & (TQ_PER_WARP - 1)) + k) & 31)) * 8u;
 }
 // candidate k of source point li: component c at [c * 32]
 __device__ __forceinline__ double *tq_coord(const TeamSmem &ts, int li, int k) {
@@ -378,6 +390,8 @@ __device__ __noinline__ void team_queries(const TeamScratch &ts, Shared &sh, con
     const int l4 = lane & (TQ_LANES - 1), li = tid / TQ_LANES;
     const double radius = 0.2 * m.voxel_size, r2max = radius * radius;
     const bool have = li < nq;
+    const int par = j & 1;
+    double *red = reinterpret_cast<double *>(sh.chunk_pref);  // [TQ_MAX][TRED_STRIDE], free during the ICP
     if (tid == BLOCK - 1 && j > 0) team_accumulate(sh);  // for iteration j - 1 (sh.red is rewritten behind two barriers)
     TQHead &t = sm.heads[have ? li : 0];
     V3 p{0.0, 0.0, 0.0};
@@ -404,37 +418,50 @@ __device__ __noinline__ void team_queries(const TeamScratch &ts, Shared &sh, con
             t.p[2] = p.z;
         }
         // first strict minimum of the squared distance over the list (= reference order); s2 = second smallest
-        // (equal squares count: an exact tie takes the slow exact path below)
+        // (equal squares count: an exact tie takes the slow exact path below). Lane l4 takes candidates l4, l4 + 4, ...:
+        // row i of the warp's block, column (4 q8 + l4 + 4 i) & 31.
         double b2 = DBL_MAX, s2 = DBL_MAX;
         int bk = INT_MAX;
+        const unsigned cbase = static_cast<unsigned>(__cvta_generic_to_shared(sm.coords));
+        const unsigned wbase = cbase + static_cast<unsigned>((li / TQ_PER_WARP) * (sm.K >> 2)) * 768u;
+        const int c0 = 4 * (li & (TQ_PER_WARP - 1)) + l4;
         constexpr int U = 4;
-        for (int k0 = l4; k0 < cnt; k0 += U * TQ_LANES) {
+        for (int i0 = 0; 4 * i0 + l4 < cnt; i0 += U) {
             double d2[U];
 #pragma unroll
-            for (int u = 0; u < U; ++u) {  // independent loads and distances in flight
-                const int k = k0 + u * TQ_LANES;
-                const double *src = tq_coord(sm, li, min(k, cnt - 1));
-                const V3 c{src[0], src[32], src[64]};
-                d2[u] = (k < cnt) ? sqnorm(c - p) : DBL_MAX;
+            for (int u = 0; u < U; ++u) {  // independent loads and distances in flight, no branches
+                const int i = i0 + u;
+                const bool in = 4 * i + l4 < cnt;
+                const int ii = in ? i : 0;
+                const unsigned a = wbase + static_cast<unsigned>(ii) * 768u + (static_cast<unsigned>((c0 + 4 * ii) & 31) << 3);
+                const V3 c{lds_f64(a), lds_f64(a + 256u), lds_f64(a + 512u)};
+                const double dd = sqnorm(c - p);
+                d2[u] = in ? dd : DBL_MAX;
             }
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                s2 = fmin(s2, fmax(b2, d2[u]));
-                if (d2[u] < b2) bk = k0 + u * TQ_LANES;
-                b2 = fmin(b2, d2[u]);
+            for (int u = 0; u < U; ++u) {  // (no NaNs here: plain compare + select instead of fmin / fmax)
+                const bool lt = d2[u] < b2;
+                const double hi = lt ? b2 : d2[u];
+                b2 = lt ? d2[u] : b2;
+                bk = lt ? 4 * (i0 + u) + l4 : bk;
+                s2 = hi < s2 ? hi : s2;
             }
         }
 #pragma unroll
         for (int o = 1; o < TQ_LANES; o <<= 1) {
             const double ob2 = __shfl_xor_sync(FULL, b2, o), os2 = __shfl_xor_sync(FULL, s2, o);
             const int ok2 = __shfl_xor_sync(FULL, bk, o);
-            s2 = fmin(fmin(s2, os2), fmax(b2, ob2));
-            if ((ob2 < b2) || (ob2 == b2 && ok2 < bk)) bk = ok2;
-            b2 = fmin(b2, ob2);
+            const bool take = (ob2 < b2) || (ob2 == b2 && ok2 < bk);
+            const double hi = (ob2 < b2) ? b2 : ob2;  // max(b2, ob2)
+            double ns2 = os2 < s2 ? os2 : s2;
+            ns2 = hi < ns2 ? hi : ns2;
+            bk = take ? ok2 : bk;
+            b2 = (ob2 < b2) ? ob2 : b2;
+            s2 = ns2;
         }
         if (cnt > 0) {
-            const double *src = tq_coord(sm, li, bk);
-            np = V3{src[0], src[32], src[64]};
+            const unsigned a = tq_coord_addr(cbase, sm.K, li, bk);
+            np = V3{lds_f64(a), lds_f64(a + 256u), lds_f64(a + 512u)};
             d = sqrt(b2);
         }
         // two squares within a few ulps could round to the same root: then compare rounded roots in reference
@@ -468,12 +495,23 @@ __device__ __noinline__ void team_queries(const TeamScratch &ts, Shared &sh, con
             }
         }
         ok = ok && (same_voxel || d < (m.voxel_size - radius) * (1.0 - 1e-12));
-        if (have && !ok && l4 == 0) sh.refill_q[atomicAdd(&sh.refill_n, 1)] = li;
+        if (have && !ok && l4 == 0) sh.refill_q[atomicAdd(&sh.refill_n[par], 1)] = li;
+        // this point's 16 entries of J^T w J / J^T w r (lane l4: entries 4 l4 ..) + the gate flag -> row li of the
+        // reduction scratch; a stale point writes zeros now and its row again after the re-search
+        if (have) {
+            double acc[4] = {0.0, 0.0, 0.0, 0.0};
+            const bool gate = ok && d < max_dist;  // DataAssociation's gate, Registration.cpp:72
+            if (gate) icp_term4(l4, p, np, kscale, acc);
+            double *row = red + li * TRED_STRIDE;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) row[4 * l4 + i] = acc[i];
+            if (l4 == 0) row[NACC] = gate ? 1.0 : 0.0;
+        }
     }
     __syncthreads();
     KB_TCYC(1);
-    const int nref = sh.refill_n;
-    if (nref > 0) {  // uniform
+    const int nref = sh.refill_n[par];
+    if (nref > 0) {  // uniform; rare
         for (int r = warp; r < nref; r += NWARPS) {
             const int rl = sh.refill_q[r];
             TQHead &h = sm.heads[rl];
@@ -486,7 +524,7 @@ __device__ __noinline__ void team_queries(const TeamScratch &ts, Shared &sh, con
                 h.nn[1] = res.p.y;
                 h.nn[2] = res.p.z;
                 h.nn[3] = res.d;
-                if ((scratch->count < 0 || scratch->count > sm.K) && res.d < DBL_MAX) atomicAdd(&sh.refill_over, 1);
+                if ((scratch->count < 0 || scratch->count > sm.K) && res.d < DBL_MAX) atomicAdd(&sh.refill_over[par], 1);
             }
             __syncwarp();
         }
@@ -494,93 +532,115 @@ __device__ __noinline__ void team_queries(const TeamScratch &ts, Shared &sh, con
         if (have && !ok) {  // answered by the re-search
             d = t.nn[3];
             np = V3{t.nn[0], t.nn[1], t.nn[2]};
+            double acc[4] = {0.0, 0.0, 0.0, 0.0};
+            const bool gate = d < max_dist;
+            if (gate) icp_term4(l4, p, np, kscale, acc);
+            double *row = red + li * TRED_STRIDE;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) row[4 * l4 + i] = acc[i];
+            if (l4 == 0) row[NACC] = gate ? 1.0 : 0.0;
         }
+        __syncthreads();
     }
     KB_TCYC(2);
-    if (warp < nwarps_q) {
-        double acc[4] = {0.0, 0.0, 0.0, 0.0};
-        int corr = 0;
-        double cand = 0.0;
-        if (have) {
-            if (l4 == 0) cand = t.full;
-            if (d < max_dist) {  // DataAssociation's gate, Registration.cpp:72
-                icp_term4(l4, p, np, kscale, acc);
-                corr = (l4 == 0) ? 1 : 0;
-            }
+    if (tid == 0) {  // the other parity's counters are idle now: re-arm them for the next iteration
+        sh.refill_n[par ^ 1] = 0;
+        sh.refill_over[par ^ 1] = 0;
+    }
+    // column sums without shuffles (their throughput is per SM: 8 warps x 33 shuffles cost 800 cycles): 16 parts x
+    // 17 columns (16 entries + the gate flag), part g adds rows g, g + 16, ... in order; column 17 = candidate counts
+    if (tid < 16 * (NACC + 1)) {
+        const int part = tid / (NACC + 1), col = tid - part * (NACC + 1);
+        double v = 0.0, c = 0.0;
+        for (int r = part; r < nq; r += 16) {
+            v += red[r * TRED_STRIDE + col];
+            if (col == NACC) c += static_cast<double>(sm.heads[r].full);
         }
-        KB_TCYC(3);
-#pragma unroll
-        for (int o = TQ_LANES; o < 32; o <<= 1) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) acc[i] += __shfl_xor_sync(FULL, acc[i], o);
-            corr += __shfl_xor_sync(FULL, corr, o);
-            cand += __shfl_xor_sync(FULL, cand, o);
-        }
-        if (lane < TQ_LANES) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) sh.warp_d[warp][4 * lane + i] = acc[i];
-        }
-        if (lane == 0) {
-            sh.warp_d[warp][NACC] = static_cast<double>(corr);
-            sh.warp_d[warp][NACC + 1] = cand;
-        }
+        sh.warp_d[part][col] = v;
+        if (col == NACC) sh.warp_d[part][NACC + 1] = c;
     }
     __syncthreads();
-    KB_TCYC(4);
+    KB_TCYC(3);
     if (tid < NPART) {
         double v = 0.0;
         if (tid < NACC + 2) {
-            for (int w = 0; w < nwarps_q; ++w) v += sh.warp_d[w][tid];
+            double v2 = 0.0;
+#pragma unroll
+            for (int g = 0; g < 16; g += 2) {
+                v += sh.warp_d[g][tid];
+                v2 += sh.warp_d[g + 1][tid];
+            }
+            v += v2;
         } else if (tid == NACC + 2) {
             v = static_cast<double>(nq - nref);  // lists that were still valid
         } else if (tid == NACC + 3) {
             v = static_cast<double>(nref);  // re-searched
         } else {
-            v = static_cast<double>(sh.refill_over);  // re-searched and not cacheable
+            v = static_cast<double>(sh.refill_over[par]);  // re-searched and not cacheable
         }
         ll_store(&ts.ll[(static_cast<size_t>(tag & 1u) * NPART + tid) * TEAM_MAX + member], v, tag);
     }
-    __syncthreads();
-    if (tid == 0) {  // (next use is behind at least one more barrier)
-        sh.refill_n = 0;
-        sh.refill_over = 0;
-    }
-    KB_TCYC(5);
+    KB_TCYC(4);
 }
 
-// all-gather of the T tagged partial systems: warp w sums values w and w + 16 over the members (a lane polls
-// members lane, lane + 32, lane + 64, lane + 96), fixed order -> the same bits in every team CTA
+// all-gather of the T tagged partial systems: warp w < 11 polls values 2w and 2w + 1 of all members (a lane polls
+// members lane, lane + 32, lane + 64, lane + 96 of both values in one loop), adds its members in order and leaves
+// the 32 lane partials of each value in shared memory; after one barrier warp 15 adds them (fixed order: the same
+// bits in every team CTA) and its last lane solves. No shuffles: 16 warps x 20 of them would cost ~700 cycles.
 __device__ __forceinline__ void team_gather(const TeamScratch &ts, Shared &sh, int T, unsigned tag) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint4 *base = ts.ll + static_cast<size_t>(tag & 1u) * NPART * TEAM_MAX;
-    for (int v = warp; v < NPART; v += NWARPS) {
-        double x[TEAM_MAX / 32];
-        bool ok[TEAM_MAX / 32];
+    double *g = reinterpret_cast<double *>(sh.chunk_pref);  // [NPART][32] (the reduction scratch is done with)
+    if (2 * warp < NPART) {
+        const uint4 *base = ts.ll + static_cast<size_t>(tag & 1u) * NPART * TEAM_MAX;
+        const int v0 = 2 * warp, nv = min(2, NPART - v0);
+        constexpr int M = TEAM_MAX / 32;
+        double x[2][M];
+        bool ok[2][M];
 #pragma unroll
-        for (int u = 0; u < TEAM_MAX / 32; ++u) {
-            x[u] = 0.0;
-            ok[u] = lane + 32 * u >= T;
-        }
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+            for (int u = 0; u < M; ++u) {
+                x[a][u] = 0.0;
+                ok[a][u] = a >= nv || lane + 32 * u >= T;
+            }
         bool all = false;
         unsigned spins = 0;
         while (!all) {
             all = true;
 #pragma unroll
-            for (int u = 0; u < TEAM_MAX / 32; ++u) {
-                if (!ok[u]) ok[u] = ll_load(&base[static_cast<size_t>(v) * TEAM_MAX + lane + 32 * u], tag, &x[u]);
-                all = all && ok[u];
-            }
+            for (int a = 0; a < 2; ++a)
+#pragma unroll
+                for (int u = 0; u < M; ++u) {
+                    if (!ok[a][u]) ok[a][u] = ll_load(&base[static_cast<size_t>(v0 + a) * TEAM_MAX + lane + 32 * u], tag, &x[a][u]);
+                    all = all && ok[a][u];
+                }
             all = __all_sync(FULL, all);
-            if (!all && __any_sync(FULL, kb_spin_check(spins, WD_TEAM_GATHER, tag, static_cast<unsigned>(v)))) break;
+            if (!all && __any_sync(FULL, kb_spin_check(spins, WD_TEAM_GATHER, tag, static_cast<unsigned>(v0)))) break;
         }
-        double s = 0.0;
 #pragma unroll
-        for (int u = 0; u < TEAM_MAX / 32; ++u) s += (lane + 32 * u < T) ? x[u] : 0.0;
+        for (int a = 0; a < 2; ++a)
+            if (a < nv) {
+                double sum = 0.0;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
-        if (lane == 0) sh.red[v] = s;
+                for (int u = 0; u < M; ++u) sum += (lane + 32 * u < T) ? x[a][u] : 0.0;
+                g[(v0 + a) * 32 + lane] = sum;
+            }
     }
     __syncthreads();
+    if (warp == NWARPS - 1) {
+        if (lane < NPART) {
+            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll
+            for (int k = 0; k < 32; k += 4) {
+                s0 += g[lane * 32 + k];
+                s1 += g[lane * 32 + k + 1];
+                s2 += g[lane * 32 + k + 2];
+                s3 += g[lane * 32 + k + 3];
+            }
+            sh.red[lane] = (s0 + s1) + (s2 + s3);
+        }
+        __syncwarp();
+    }
 }
 
 // the iterations, on CTAs [0, T) of the launch. Precondition: icp_fill_pass + a grid barrier, map not empty,
@@ -609,8 +669,8 @@ __device__ __noinline__ void op_icp_team(const TeamScratch &ts, const Scratch &s
         sh.t_icp = se3_identity();
         sh.cand_total = 0.0;
         sh.cache_stats[0] = sh.cache_stats[1] = sh.cache_stats[2] = 0.0;
-        sh.refill_n = 0;
-        sh.refill_over = 0;
+        sh.refill_n[0] = sh.refill_n[1] = 0;
+        sh.refill_over[0] = sh.refill_over[1] = 0;
     }
     __syncthreads();
     if (sc.profile && member == 0 && threadIdx.x == 0) sc.dbg[33] = globaltimer_ns();
@@ -621,7 +681,7 @@ __device__ __noinline__ void op_icp_team(const TeamScratch &ts, const Scratch &s
         unsigned long long *dbg = (sc.profile && member == 0 && j == 4) ? sc.dbg : nullptr;
         KB_TCYC(0);
         team_queries(ts, sh, m, sm, nq, j, max_dist, kscale, member, tag, dbg);
-        team_gather(ts, sh, T, tag);
+        team_gather(ts, sh, T, tag);  // (warp 15 holds the sums: no barrier between them and its solver lane)
         KB_TCYC(6);
         if (threadIdx.x == BLOCK - 1) {  // warp 15 owns no source point (TQ_MAX = 120)
             double sys[NACC];

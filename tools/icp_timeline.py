@@ -36,9 +36,9 @@ for p, t in scans[prime:]:
     f = ns[30:35]
     print("   us: fill pass (CTA 0)", round((f[1] - f[0]) * 1e-3, 1), "barrier", round((f[2] - f[1]) * 1e-3, 1), "stage lists", round((f[3] - f[2]) * 1e-3, 1),
           "iterations", round((f[4] - f[3]) * 1e-3, 1), "cache hits/refills/overflows", g_stats(g))
-    cyc = np.diff(ns[16:24])
-    print("   cycles at iteration 4 (member 0, thread 0): transform+validity", cyc[0], "walk -> barrier", cyc[0], "refills", cyc[1], "terms", cyc[2],
-          "warp sums", cyc[3], "store partial", cyc[4], "gather", cyc[5], "solve", cyc[6])
+    c = ns[16:24]
+    print("   cycles at iteration 4 (member 0, thread 0): transform+walk+terms -> barrier", c[1] - c[0], "refills", c[2] - c[1],
+          "column sums", c[3] - c[2], "store partial", c[4] - c[3], "gather+sums", c[6] - c[4], "solve", c[7] - c[6])
     print("iters", it, "phases_us", dict(zip(names, np.round(g.last_profile_us, 1))),
           "iter_us first", np.round(d[:3], 2), "median", round(float(np.median(d)), 2) if len(d) else None,
           "env", os.environ.get("KB_ICP_TEAM_Q", "default"))
