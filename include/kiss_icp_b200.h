@@ -261,7 +261,8 @@ typedef struct kb_frame_stats {
     double icp_candidates; /* map points examined */
     int iterations;
     int n_points_in, n_preprocessed, n_downsampled, n_source;
-    int map_points, map_voxels, pad;
+    int map_points, map_voxels;
+    int team;             /* CTAs of the ICP team that ran the iterations (0: whole-grid loop) */
 } kb_frame_stats;
 int kb_pipeline_set_history(kb_pipeline *p, size_t capacity);
 int kb_pipeline_get_history(const kb_pipeline *p, kb_frame_stats *out, size_t capacity, size_t *n_out);

@@ -77,7 +77,7 @@ class FrameStats(C.Structure):
     """kb_frame_stats"""
     _fields_ = [("pose", dbl * 16), ("phase_us", dbl * 6), ("icp_queries", dbl), ("icp_candidates", dbl),
                 ("iterations", i32), ("n_points_in", i32), ("n_preprocessed", i32), ("n_downsampled", i32),
-                ("n_source", i32), ("map_points", i32), ("map_voxels", i32), ("pad", i32)]
+                ("n_source", i32), ("map_points", i32), ("map_voxels", i32), ("team", i32)]
 
 
 # every exported symbol of include/kiss_icp_b200.h: name -> (restype, argtypes)

@@ -1264,7 +1264,7 @@ static int pipeline_absorb(kb_pipeline *p, const FrameResult &r, size_t n, long 
         st.n_source = p->last.n_src;
         st.map_points = p->last.map_points;
         st.map_voxels = p->last.map_live;
-        st.pad = 0;
+        st.team = p->last.team;
         p->history.push_back(st);
     }
     if (p->last.map_status & ST_TABLE_FULL) return fail(KB_ERR_CUDA, "voxel table overflow (internal capacity bug)");

@@ -590,6 +590,28 @@ __device__ __noinline__ void team_queries(const TeamScratch &ts, Shared &sh, con
 __device__ __forceinline__ void team_gather(const TeamScratch &ts, Shared &sh, int T, unsigned tag) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double *g = reinterpret_cast<double *>(sh.chunk_pref);  // [NPART][32] (the reduction scratch is done with)
+    // Every member stores its 21 chunks with one instruction (21 threads), so they land together: the pollers first
+    // wait on ONE chunk per member (value NACC) and only then read the others — polling all 21 x T chunks from 11 warps
+    // of every CTA was 2 MB of L2 reads per round and made the hop itself the longest part of an iteration.
+    if (2 * warp < NPART) {
+        const uint4 *fl = ts.ll + (static_cast<size_t>(tag & 1u) * NPART + NACC) * TEAM_MAX;
+        bool okf[TEAM_MAX / 32];
+#pragma unroll
+        for (int u = 0; u < TEAM_MAX / 32; ++u) okf[u] = lane + 32 * u >= T;
+        bool all = false;
+        unsigned spins = 0;
+        double dummy;
+        while (!all) {
+            all = true;
+#pragma unroll
+            for (int u = 0; u < TEAM_MAX / 32; ++u) {
+                if (!okf[u]) okf[u] = ll_load(&fl[lane + 32 * u], tag, &dummy);
+                all = all && okf[u];
+            }
+            all = __all_sync(FULL, all);
+            if (!all && __any_sync(FULL, kb_spin_check(spins, WD_TEAM_GATHER, tag, 999u))) break;
+        }
+    }
     if (2 * warp < NPART) {
         const uint4 *base = ts.ll + static_cast<size_t>(tag & 1u) * NPART * TEAM_MAX;
         const int v0 = 2 * warp, nv = min(2, NPART - v0);
@@ -679,9 +701,13 @@ __device__ __noinline__ void op_icp_team(const TeamScratch &ts, const Scratch &s
         if (sc.profile && member == 0 && threadIdx.x == 0 && j < 20) sc.dbg[41 + j] = globaltimer_ns();
         const unsigned tag = tag_base + static_cast<unsigned>(j) + 1u;
         unsigned long long *dbg = (sc.profile && member == 0 && j == 4) ? sc.dbg : nullptr;
+        const bool stamp = sc.profile && j == 4 && threadIdx.x == 0;
+        if (stamp) sc.dbg[64 + 4 * member] = globaltimer_ns();
         KB_TCYC(0);
         team_queries(ts, sh, m, sm, nq, j, max_dist, kscale, member, tag, dbg);
+        if (stamp) sc.dbg[64 + 4 * member + 1] = globaltimer_ns();
         team_gather(ts, sh, T, tag);  // (warp 15 holds the sums: no barrier between them and its solver lane)
+        if (stamp) sc.dbg[64 + 4 * member + 2] = globaltimer_ns();
         KB_TCYC(6);
         if (threadIdx.x == BLOCK - 1) {  // warp 15 owns no source point (TQ_MAX = 120)
             double sys[NACC];

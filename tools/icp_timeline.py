@@ -19,6 +19,12 @@ g = K.KissICP(K.load_config())
 for p, t in scans[:prime]:
     g.register_frame(p, t, return_clouds=False)
 g.set_profiling(True)
+g.start_history(frames)
+def last_team(g):
+    h = g.history()
+    return h[-1].team if h else 0
+
+
 def g_stats(g):
     out = np.zeros(3)
     N.check(N.lib().kb_pipeline_last_cache_stats(g._h, N.ptr(out)))
@@ -36,6 +42,16 @@ for p, t in scans[prime:]:
     f = ns[30:35]
     print("   us: fill pass (CTA 0)", round((f[1] - f[0]) * 1e-3, 1), "barrier", round((f[2] - f[1]) * 1e-3, 1), "stage lists", round((f[3] - f[2]) * 1e-3, 1),
           "iterations", round((f[4] - f[3]) * 1e-3, 1), "cache hits/refills/overflows", g_stats(g))
+    T = int(last_team(g))
+    if T > 0:
+        nsb = np.zeros(64 + 4 * 148)
+        N.check(N.lib().kb_pipeline_debug_stamps(g._h, N.ptr(nsb), len(nsb)))
+        mm = nsb[64:64 + 4 * T].reshape(T, 4)
+        comp = (mm[:, 1] - mm[:, 0]) * 1e-3
+        wait = (mm[:, 2] - mm[:, 1]) * 1e-3
+        skew = (mm[:, 1] - mm[:, 1].min()) * 1e-3
+        print("   per member at iteration 4 [us]: compute min/med/max", np.round([comp.min(), np.median(comp), comp.max()], 2),
+              "store-time skew med/max", np.round([np.median(skew), skew.max()], 2), "gather wait min/med/max", np.round([wait.min(), np.median(wait), wait.max()], 2), "T", T)
     c = ns[16:24]
     print("   cycles at iteration 4 (member 0, thread 0): transform+walk+terms -> barrier", c[1] - c[0], "refills", c[2] - c[1],
           "column sums", c[3] - c[2], "store partial", c[4] - c[3], "gather+sums", c[6] - c[4], "solve", c[7] - c[6])

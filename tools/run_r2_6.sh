@@ -1,6 +1,6 @@
 set -u
 mkdir -p gpurun_out
-for q in 64 32; do
+for q in 64; do
 echo "== timeline team q=$q"
 KB_ICP_TEAM_Q=$q timeout -k 10 200 python tools/icp_timeline.py 100 3 2>&1 | tail -9
 done
