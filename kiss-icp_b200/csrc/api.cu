@@ -155,8 +155,8 @@ struct Exec {
         CK(cudaMemsetAsync(sc.ll_group, 0, sizeof(uint4) * NPART * 16, stream));
         CK(cudaMemsetAsync(sc.ll_part, 0, sizeof(uint4) * NPART * grid, stream));
         CK(cudaMemsetAsync(sc.ll_res, 0, sizeof(uint4) * LL_RES, stream));
-        CK(cudaMalloc(&team.ll, sizeof(uint4) * 2 * NPART * TEAM_MAX));
-        CK(cudaMemsetAsync(team.ll, 0, sizeof(uint4) * 2 * NPART * TEAM_MAX, stream));
+        CK(cudaMalloc(&team.ll, sizeof(uint4) * 2 * NPART * TEAM_MAX * TEAM_MAX));  // 11 MB: one copy of the partials per reader
+        CK(cudaMemsetAsync(team.ll, 0, sizeof(uint4) * 2 * NPART * TEAM_MAX * TEAM_MAX, stream));
         CK(cudaMalloc(&team.out, sizeof(double) * 16));
         if (const char *e = std::getenv("KB_ICP_TEAM_Q")) icp_team_q = std::max(0, std::min(std::atoi(e), TQ_MAX));
         if (const char *e = std::getenv("KB_ICP_SMEM_KB")) icp_smem = static_cast<size_t>(std::max(60, std::min(std::atoi(e), 180))) * 1024;

@@ -94,7 +94,7 @@ __device__ __forceinline__ double *tq_coord(const TeamSmem &ts, int li, int k) {
 }
 
 struct TeamScratch {
-    uint4 *ll;        // [2][NPART][TEAM_MAX] epoch-tagged partial systems, ping-pong by iteration parity
+    uint4 *ll;        // [2][TEAM_MAX readers][TEAM_MAX members][NPART] epoch-tagged partial systems, ping-pong by iteration parity
     double *out;      // [16] result record: pose(7) iters cand_total query_total cache_stats(3)
     QList *qrec;      // [n] per source point, written by the fill pass
     int smem_bytes;   // dynamic shared memory of the launch
@@ -384,7 +384,7 @@ __device__ __forceinline__ void team_accumulate(Shared &sh) {
 // Otherwise (moved > R, or a far match that changed voxel) the point is queued and searched again by a whole warp —
 // ALL warps of the CTA serve that queue.
 __device__ __noinline__ void team_queries(const TeamScratch &ts, Shared &sh, const MapView &m, const TeamSmem &sm, int nq, int j,
-                                          double max_dist, double kscale, int member, unsigned tag,
+                                          double max_dist, double kscale, int member, int T, unsigned tag,
                                           unsigned long long *dbg) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int l4 = lane & (TQ_LANES - 1), li = tid / TQ_LANES;
@@ -578,42 +578,26 @@ __device__ __noinline__ void team_queries(const TeamScratch &ts, Shared &sh, con
         } else {
             v = static_cast<double>(sh.refill_over[par]);  // re-searched and not cacheable
         }
-        ll_store(&ts.ll[(static_cast<size_t>(tag & 1u) * NPART + tid) * TEAM_MAX + member], v, tag);
+        // one copy per reader (row [reader][member] = 21 consecutive chunks: the 21 lanes store one 336-byte row at a time)
+        uint4 *dst = ts.ll + (static_cast<size_t>(tag & 1u) * TEAM_MAX * TEAM_MAX + member) * NPART + tid;
+        for (int reader = 0; reader < T; ++reader) ll_store(dst + static_cast<size_t>(reader) * TEAM_MAX * NPART, v, tag);
     }
     KB_TCYC(4);
 }
 
-// all-gather of the T tagged partial systems: warp w < 11 polls values 2w and 2w + 1 of all members (a lane polls
+// all-gather of the T tagged partial systems. Every member WRITES its partial once per reader (ll[parity][reader][member]
+// [value]: 21 x T stores of 16 bytes, coalesced 336-byte rows) so that every reader polls lines nobody else reads:
+// with one shared copy the 42 x 352 polling lanes of all CTAs hammered the same few L2 lines and the hop took 5 us
+// (measured; the members themselves arrived within 0.5 us of each other).
+// Warp w < 11 polls values 2w and 2w + 1 of all members (a lane polls
 // members lane, lane + 32, lane + 64, lane + 96 of both values in one loop), adds its members in order and leaves
 // the 32 lane partials of each value in shared memory; after one barrier warp 15 adds them (fixed order: the same
 // bits in every team CTA) and its last lane solves. No shuffles: 16 warps x 20 of them would cost ~700 cycles.
 __device__ __forceinline__ void team_gather(const TeamScratch &ts, Shared &sh, int T, unsigned tag) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double *g = reinterpret_cast<double *>(sh.chunk_pref);  // [NPART][32] (the reduction scratch is done with)
-    // Every member stores its 21 chunks with one instruction (21 threads), so they land together: the pollers first
-    // wait on ONE chunk per member (value NACC) and only then read the others — polling all 21 x T chunks from 11 warps
-    // of every CTA was 2 MB of L2 reads per round and made the hop itself the longest part of an iteration.
     if (2 * warp < NPART) {
-        const uint4 *fl = ts.ll + (static_cast<size_t>(tag & 1u) * NPART + NACC) * TEAM_MAX;
-        bool okf[TEAM_MAX / 32];
-#pragma unroll
-        for (int u = 0; u < TEAM_MAX / 32; ++u) okf[u] = lane + 32 * u >= T;
-        bool all = false;
-        unsigned spins = 0;
-        double dummy;
-        while (!all) {
-            all = true;
-#pragma unroll
-            for (int u = 0; u < TEAM_MAX / 32; ++u) {
-                if (!okf[u]) okf[u] = ll_load(&fl[lane + 32 * u], tag, &dummy);
-                all = all && okf[u];
-            }
-            all = __all_sync(FULL, all);
-            if (!all && __any_sync(FULL, kb_spin_check(spins, WD_TEAM_GATHER, tag, 999u))) break;
-        }
-    }
-    if (2 * warp < NPART) {
-        const uint4 *base = ts.ll + static_cast<size_t>(tag & 1u) * NPART * TEAM_MAX;
+        const uint4 *base = ts.ll + (static_cast<size_t>(tag & 1u) * TEAM_MAX + blockIdx.x) * TEAM_MAX * NPART;  // my private copy
         const int v0 = 2 * warp, nv = min(2, NPART - v0);
         constexpr int M = TEAM_MAX / 32;
         double x[2][M];
@@ -633,7 +617,7 @@ __device__ __forceinline__ void team_gather(const TeamScratch &ts, Shared &sh, i
             for (int a = 0; a < 2; ++a)
 #pragma unroll
                 for (int u = 0; u < M; ++u) {
-                    if (!ok[a][u]) ok[a][u] = ll_load(&base[static_cast<size_t>(v0 + a) * TEAM_MAX + lane + 32 * u], tag, &x[a][u]);
+                    if (!ok[a][u]) ok[a][u] = ll_load(&base[static_cast<size_t>(lane + 32 * u) * NPART + v0 + a], tag, &x[a][u]);
                     all = all && ok[a][u];
                 }
             all = __all_sync(FULL, all);
@@ -704,7 +688,7 @@ __device__ __noinline__ void op_icp_team(const TeamScratch &ts, const Scratch &s
         const bool stamp = sc.profile && j == 4 && threadIdx.x == 0;
         if (stamp) sc.dbg[64 + 4 * member] = globaltimer_ns();
         KB_TCYC(0);
-        team_queries(ts, sh, m, sm, nq, j, max_dist, kscale, member, tag, dbg);
+        team_queries(ts, sh, m, sm, nq, j, max_dist, kscale, member, T, tag, dbg);
         if (stamp) sc.dbg[64 + 4 * member + 1] = globaltimer_ns();
         team_gather(ts, sh, T, tag);  // (warp 15 holds the sums: no barrier between them and its solver lane)
         if (stamp) sc.dbg[64 + 4 * member + 2] = globaltimer_ns();
