@@ -266,6 +266,10 @@ typedef struct kb_frame_stats {
 } kb_frame_stats;
 int kb_pipeline_set_history(kb_pipeline *p, size_t capacity);
 int kb_pipeline_get_history(const kb_pipeline *p, kb_frame_stats *out, size_t capacity, size_t *n_out);
+/* the logged frames' in-kernel %globaltimer stamps (profiling on), ns modulo 2^40, 20 per frame: [0] kernel start, [1..3] front
+ * end phases, [7] candidate lists done, [10] ICP iterations done, [11] next frame's front end done (prefetch), [4] ICP result
+ * everywhere, [5] map updated, [6] kernel end, [8,9] map phases, [12..19] downsample phases */
+int kb_pipeline_history_stamps(const kb_pipeline *p, double *out, size_t capacity, size_t *n_out);
 /* kernels launched by this pipeline so far (bench "gpu_launches") */
 int kb_pipeline_launch_count(const kb_pipeline *p, unsigned long long *out);
 

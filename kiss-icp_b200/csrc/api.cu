@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <array>
 #include <chrono>
 #include <cmath>
 #include <cstdarg>
@@ -557,6 +558,7 @@ struct kb_pipeline {
     Work vox_ws;            // scratch of kb_pipeline_voxelize (must not clobber the clouds of the last frame)
     unsigned long long grow_retries = 0;
     std::vector<kb_frame_stats> history;
+    std::vector<std::array<double, 20>> history_stamps;  // the frames' %globaltimer stamps, ns modulo 2^40 (profiling on)
     size_t history_cap = 0;
     // frame queue of kb_pipeline_register_frames: frame k+1 is copied in while frame k is registered
     static constexpr int Q_DEPTH = 4;  // frame k registering, k+1 being prefetched by the same launch, k+2 / k+3 copying
@@ -1266,6 +1268,9 @@ static int pipeline_absorb(kb_pipeline *p, const FrameResult &r, size_t n, long 
         st.map_voxels = p->last.map_live;
         st.team = p->last.team;
         p->history.push_back(st);
+        std::array<double, 20> ts;
+        for (int i = 0; i < 20; ++i) ts[i] = static_cast<double>(p->last.t_ns[i] & ((1ull << 40) - 1));
+        p->history_stamps.push_back(ts);
     }
     if (p->last.map_status & ST_TABLE_FULL) return fail(KB_ERR_CUDA, "voxel table overflow (internal capacity bug)");
     return KB_OK;
@@ -1704,13 +1709,14 @@ int kb_pipeline_last_profile(const kb_pipeline *p, double *us, int n) {
 }
 int kb_pipeline_set_profiling(kb_pipeline *p, int enabled) {
     if (!p) return fail(KB_ERR_INVALID_ARG, "p == NULL");
-    p->ex->sc.profile = enabled ? 1 : 0;
+    p->ex->sc.profile = enabled;  // 1: all stamps (incl. one per ICP iteration, ~1 us each); 2: phase boundaries only
     std::memset(p->last.t_ns, 0, sizeof(p->last.t_ns));
     return KB_OK;
 }
 int kb_pipeline_set_history(kb_pipeline *p, size_t capacity) {
     if (!p) return fail(KB_ERR_INVALID_ARG, "p == NULL");
     p->history.clear();
+    p->history_stamps.clear();
     p->history.reserve(capacity);
     p->history_cap = capacity;
     return KB_OK;
@@ -1721,6 +1727,14 @@ int kb_pipeline_get_history(const kb_pipeline *p, kb_frame_stats *out, size_t ca
     if (!out) return KB_OK;
     if (capacity < p->history.size()) return fail(KB_ERR_CAPACITY, "history buffer too small");
     std::memcpy(out, p->history.data(), p->history.size() * sizeof(kb_frame_stats));
+    return KB_OK;
+}
+int kb_pipeline_history_stamps(const kb_pipeline *p, double *out, size_t capacity, size_t *n_out) {
+    if (!p || !n_out) return fail(KB_ERR_INVALID_ARG, "NULL argument");
+    *n_out = p->history_stamps.size();
+    if (!out) return KB_OK;
+    if (capacity < p->history_stamps.size()) return fail(KB_ERR_CAPACITY, "stamp buffer too small");
+    for (size_t i = 0; i < p->history_stamps.size(); ++i) std::memcpy(out + 20 * i, p->history_stamps[i].data(), 20 * sizeof(double));
     return KB_OK;
 }
 int kb_pipeline_launch_count(const kb_pipeline *p, unsigned long long *out) {

@@ -578,9 +578,17 @@ __device__ __noinline__ void team_queries(const TeamScratch &ts, Shared &sh, con
         } else {
             v = static_cast<double>(sh.refill_over[par]);  // re-searched and not cacheable
         }
-        // one copy per reader (row [reader][member] = 21 consecutive chunks: the 21 lanes store one 336-byte row at a time)
-        uint4 *dst = ts.ll + (static_cast<size_t>(tag & 1u) * TEAM_MAX * TEAM_MAX + member) * NPART + tid;
-        for (int reader = 0; reader < T; ++reader) ll_store(dst + static_cast<size_t>(reader) * TEAM_MAX * NPART, v, tag);
+        sh.red[tid] = v;  // (the solver's copy of the previous iteration is consumed: it was read before the last barrier)
+    }
+    __syncthreads();
+    // one copy per reader, all threads storing (21 lanes doing the T rows one after the other took 2400 cycles):
+    // element e = reader * 21 + value -> row [reader][member], 21 consecutive 16-byte chunks
+    {
+        uint4 *dst = ts.ll + (static_cast<size_t>(tag & 1u) * TEAM_MAX * TEAM_MAX + member) * NPART;
+        for (int e = tid; e < T * NPART; e += BLOCK) {
+            const int reader = e / NPART, val = e - reader * NPART;
+            ll_store(dst + static_cast<size_t>(reader) * TEAM_MAX * NPART + val, sh.red[val], tag);
+        }
     }
     KB_TCYC(4);
 }
@@ -682,10 +690,10 @@ __device__ __noinline__ void op_icp_team(const TeamScratch &ts, const Scratch &s
     if (sc.profile && member == 0 && threadIdx.x == 0) sc.dbg[33] = globaltimer_ns();
     int j = 0;
     for (;; ++j) {
-        if (sc.profile && member == 0 && threadIdx.x == 0 && j < 20) sc.dbg[41 + j] = globaltimer_ns();
+        if (sc.profile == 1 && member == 0 && threadIdx.x == 0 && j < 20) sc.dbg[41 + j] = globaltimer_ns();
         const unsigned tag = tag_base + static_cast<unsigned>(j) + 1u;
-        unsigned long long *dbg = (sc.profile && member == 0 && j == 4) ? sc.dbg : nullptr;
-        const bool stamp = sc.profile && j == 4 && threadIdx.x == 0;
+        unsigned long long *dbg = (sc.profile == 1 && member == 0 && j == 4) ? sc.dbg : nullptr;
+        const bool stamp = sc.profile == 1 && j == 4 && threadIdx.x == 0;
         if (stamp) sc.dbg[64 + 4 * member] = globaltimer_ns();
         KB_TCYC(0);
         team_queries(ts, sh, m, sm, nq, j, max_dist, kscale, member, T, tag, dbg);

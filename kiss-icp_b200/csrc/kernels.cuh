@@ -180,11 +180,14 @@ __global__ void __launch_bounds__(BLOCK, 1) k_register_frame(const FrameParams P
         icp_fill_pass(g, sh, P.m, fr.src, n_src, guess, P.team.qrec);
         if (P.sc.profile && blockIdx.x == 0 && threadIdx.x == 0) P.sc.dbg[31] = globaltimer_ns();
         g.sync();
-        if (P.sc.profile && blockIdx.x == 0 && threadIdx.x == 0) P.sc.dbg[32] = globaltimer_ns();
+        if (P.sc.profile && blockIdx.x == 0 && threadIdx.x == 0) P.sc.dbg[32] = P.res->t_ns[7] = globaltimer_ns();
         if (static_cast<int>(blockIdx.x) < T) {
             op_icp_team(P.team, P.sc, sh, P.m, n_src, guess, 3.0 * sigma, sigma, P.max_iter, P.conv,
                         kb_dyn_smem, T, P.tag_base);
-            if (blockIdx.x == 0 && threadIdx.x == 0) team_publish(P.team, sh);
+            if (blockIdx.x == 0 && threadIdx.x == 0) {
+                team_publish(P.team, sh);
+                if (P.sc.profile) P.res->t_ns[10] = globaltimer_ns();  // iterations done (team member 0)
+            }
         } else if (P.next_in != nullptr && 2 * (G - T) >= G) {
             // the CTAs the team does not need register nothing now: they run the next frame's front end
             Grid gf;
@@ -192,7 +195,10 @@ __global__ void __launch_bounds__(BLOCK, 1) k_register_frame(const FrameParams P
             const Front nf = P.ws.fr[(P.id + 1) & 1];
             op_front(gf, P.sc, sh, P.ws, nf, P.next_in, P.next_n, nullptr, 0, false, last_delta, P.max_range, P.min_range,
                      P.voxel_size, P.next_in_f32 != 0, nullptr);
-            if (gf.rank == 0 && threadIdx.x == 0) P.st->front_id = P.id + 1;  // visible to the next launch
+            if (gf.rank == 0 && threadIdx.x == 0) {
+                P.st->front_id = P.id + 1;  // visible to the next launch
+                if (P.sc.profile) P.res->t_ns[11] = globaltimer_ns();  // (rank 0's own end: the other CTAs may still be emitting)
+            }
         }
         g.sync();
         if (threadIdx.x == 0) team_collect(P.team, sh);
