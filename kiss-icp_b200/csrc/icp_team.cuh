@@ -367,6 +367,72 @@ __device__ __forceinline__ void team_accumulate(Shared &sh) {
     for (int i = 0; i < 3; ++i) sh.cache_stats[i] += sh.red[NACC + 2 + i];
 }
 
+// COLD paths of the iteration live in their own functions: the loop is a latency chain executed by a handful of
+// warps, and every instruction-cache line it has to skip over or fetch is paid in full (the iteration's code was
+// spread over ~80 KB before this split and ran at ~15 cycles per instruction in its straight-line parts).
+
+// two squared distances within a few ulps could round to the same root: compare rounded roots in reference order like
+// GetClosestNeighbor does (whole warp calls; lanes with `near` redo their point's list)
+__device__ __noinline__ void tq_exact_nn(const TeamSmem &sm, int li, int l4, int cnt, bool near, const V3 &p, double *d, V3 *np) {
+    double best = DBL_MAX;
+    int ek = INT_MAX;
+    if (near)
+        for (int k = l4; k < cnt; k += TQ_LANES) {
+            const double *src = tq_coord(sm, li, k);
+            const double dd = norm(V3{src[0], src[32], src[64]} - p);
+            if (dd < best) {
+                best = dd;
+                ek = k;
+            }
+        }
+#pragma unroll
+    for (int o = 1; o < TQ_LANES; o <<= 1) {
+        const double ob = __shfl_xor_sync(FULL, best, o);
+        const int ok2 = __shfl_xor_sync(FULL, ek, o);
+        if ((ob < best) || (ob == best && ok2 < ek)) {
+            best = ob;
+            ek = ok2;
+        }
+    }
+    if (near) {
+        const double *src = tq_coord(sm, li, ek);
+        *np = V3{src[0], src[32], src[64]};
+        *d = best;
+    }
+}
+
+// the stale points of this iteration (queue sh.refill_q) are searched again by all warps of the CTA and their lists
+// staged again; the threads that own such a point get its answer
+__device__ __noinline__ void team_refill(Shared &sh, const MapView &m, const TeamSmem &sm, int nref, int par, bool mine, int li,
+                                         double *d, V3 *np) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const double radius = 0.2 * m.voxel_size;
+    for (int r = warp; r < nref; r += NWARPS) {
+        const int rl = sh.refill_q[r];
+        TQHead &h = sm.heads[rl];
+        const V3 pq{h.p[0], h.p[1], h.p[2]};
+        QList *scratch = reinterpret_cast<QList *>(&sh.rlist[warp]);
+        const NNResult res = nn_search_list(m, pq, lane, sh.wnn[warp], scratch, radius);
+        team_stage(sm, m, rl, scratch, lane);
+        if (lane == 0) {
+            h.nn[0] = res.p.x;
+            h.nn[1] = res.p.y;
+            h.nn[2] = res.p.z;
+            h.nn[3] = res.d;
+            if ((scratch->count < 0 || scratch->count > sm.K) && res.d < DBL_MAX) atomicAdd(&sh.refill_over[par], 1);
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+    if (mine) {
+        const TQHead &t = sm.heads[li];
+        *d = t.nn[3];
+        *np = V3{t.nn[0], t.nn[1], t.nn[2]};
+    }
+}
+
+#define KB_WCYC(i) \
+    if (dbg != nullptr && threadIdx.x == 0) dbg[24 + (i)] = static_cast<unsigned long long>(clock64())
 #define KB_TCYC(i) \
     if (dbg != nullptr && threadIdx.x == 0) dbg[16 + (i)] = static_cast<unsigned long long>(clock64())
 
@@ -411,6 +477,7 @@ __device__ __noinline__ void team_queries(const TeamScratch &ts, Shared &sh, con
             ok = t.count >= 0 && sqnorm(moved) <= r2max;
             cnt = ok ? t.count : 0;
         }
+        KB_WCYC(0);
         __syncwarp();  // all four lanes have read t.p
         if (have && l4 == 0 && j > 0) {
             t.p[0] = p.x;
@@ -447,6 +514,7 @@ __device__ __noinline__ void team_queries(const TeamScratch &ts, Shared &sh, con
                 s2 = hi < s2 ? hi : s2;
             }
         }
+        KB_WCYC(1);
 #pragma unroll
         for (int o = 1; o < TQ_LANES; o <<= 1) {
             const double ob2 = __shfl_xor_sync(FULL, b2, o), os2 = __shfl_xor_sync(FULL, s2, o);
@@ -464,36 +532,12 @@ __device__ __noinline__ void team_queries(const TeamScratch &ts, Shared &sh, con
             np = V3{lds_f64(a), lds_f64(a + 256u), lds_f64(a + 512u)};
             d = sqrt(b2);
         }
+        KB_WCYC(2);
         // two squares within a few ulps could round to the same root: then compare rounded roots in reference
         // order like GetClosestNeighbor does (in practice never)
         const bool near = cnt > 0 && s2 <= b2 * (1.0 + 8.8817841970012523e-16);
-        if (__any_sync(FULL, near)) {
-            double best = DBL_MAX;
-            int ek = INT_MAX;
-            if (near)
-                for (int k = l4; k < cnt; k += TQ_LANES) {
-                    const double *src = tq_coord(sm, li, k);
-                    const double dd = norm(V3{src[0], src[32], src[64]} - p);
-                    if (dd < best) {
-                        best = dd;
-                        ek = k;
-                    }
-                }
-#pragma unroll
-            for (int o = 1; o < TQ_LANES; o <<= 1) {
-                const double ob = __shfl_xor_sync(FULL, best, o);
-                const int ok2 = __shfl_xor_sync(FULL, ek, o);
-                if ((ob < best) || (ob == best && ok2 < ek)) {
-                    best = ob;
-                    ek = ok2;
-                }
-            }
-            if (near) {
-                const double *src = tq_coord(sm, li, ek);
-                np = V3{src[0], src[32], src[64]};
-                d = best;
-            }
-        }
+        if (__any_sync(FULL, near)) tq_exact_nn(sm, li, l4, cnt, near, p, &d, &np);
+        KB_WCYC(3);
         ok = ok && (same_voxel || d < (m.voxel_size - radius) * (1.0 - 1e-12));
         if (have && !ok && l4 == 0) sh.refill_q[atomicAdd(&sh.refill_n[par], 1)] = li;
         // this point's 16 entries of J^T w J / J^T w r (lane l4: entries 4 l4 ..) + the gate flag -> row li of the
@@ -507,34 +551,19 @@ __device__ __noinline__ void team_queries(const TeamScratch &ts, Shared &sh, con
             for (int i = 0; i < 4; ++i) row[4 * l4 + i] = acc[i];
             if (l4 == 0) row[NACC] = gate ? 1.0 : 0.0;
         }
+        KB_WCYC(4);
     }
     __syncthreads();
     KB_TCYC(1);
     const int nref = sh.refill_n[par];
     if (nref > 0) {  // uniform; rare
-        for (int r = warp; r < nref; r += NWARPS) {
-            const int rl = sh.refill_q[r];
-            TQHead &h = sm.heads[rl];
-            const V3 pq{h.p[0], h.p[1], h.p[2]};
-            QList *scratch = reinterpret_cast<QList *>(&sh.rlist[warp]);
-            const NNResult res = nn_search_list(m, pq, lane, sh.wnn[warp], scratch, radius);
-            team_stage(sm, m, rl, scratch, lane);
-            if (lane == 0) {
-                h.nn[0] = res.p.x;
-                h.nn[1] = res.p.y;
-                h.nn[2] = res.p.z;
-                h.nn[3] = res.d;
-                if ((scratch->count < 0 || scratch->count > sm.K) && res.d < DBL_MAX) atomicAdd(&sh.refill_over[par], 1);
-            }
-            __syncwarp();
-        }
-        __syncthreads();
+        double rd = 0.0;
+        V3 rp{0.0, 0.0, 0.0};
+        team_refill(sh, m, sm, nref, par, have && !ok, li, &rd, &rp);
         if (have && !ok) {  // answered by the re-search
-            d = t.nn[3];
-            np = V3{t.nn[0], t.nn[1], t.nn[2]};
             double acc[4] = {0.0, 0.0, 0.0, 0.0};
-            const bool gate = d < max_dist;
-            if (gate) icp_term4(l4, p, np, kscale, acc);
+            const bool gate = rd < max_dist;
+            if (gate) icp_term4(l4, p, rp, kscale, acc);
             double *row = red + li * TRED_STRIDE;
 #pragma unroll
             for (int i = 0; i < 4; ++i) row[4 * l4 + i] = acc[i];
@@ -657,6 +686,38 @@ __device__ __forceinline__ void team_gather(const TeamScratch &ts, Shared &sh, i
     }
 }
 
+// degenerate normal equations (no correspondences, rank-deficient geometry): the pivoted LDL^T with Eigen's zero-pivot
+// rule, like the reference's JTJ.ldlt().solve(-JTr)
+__device__ __noinline__ void team_solve_ldlt(const double sys[NACC], double dx[6]) {
+    double JTJ[36], JTr[6], rhs[6];
+    icp_expand(sys, JTJ, JTr);
+#pragma unroll
+    for (int i = 0; i < 6; ++i) rhs[i] = -JTr[i];
+    ldlt6_solve_fast(JTJ, rhs, dx);
+}
+__device__ __noinline__ SE3 team_exp_large(const double dx[6]) { return se3_exp_fast(dx); }
+
+// one thread: dx = JTJ.ldlt().solve(-JTr), estimation = SE3::exp(dx), convergence test (Registration.cpp:156-157,163)
+__device__ __forceinline__ void team_solve(Shared &sh, double conv, bool last_allowed) {
+    double sys[NACC];
+#pragma unroll
+    for (int i = 0; i < NACC; ++i) sys[i] = sh.red[i];
+    double dx[6];
+    if (!icp_solve_schur(sys, dx)) team_solve_ldlt(sys, dx);  // structured 3x3 Schur solve; cold: pivoted LDL^T
+    const double theta_sq = (dx[3] * dx[3] + dx[4] * dx[4]) + dx[5] * dx[5];
+    SE3 est;
+    if (theta_sq >= kEps * kEps && theta_sq < 0.01) {
+        est = se3_exp_small(dx, theta_sq);
+    } else {
+        est = team_exp_large(dx);  // cold
+    }
+    double n2 = 0.0;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) n2 += dx[i] * dx[i];
+    sh.pending = est;
+    sh.flag = ((sqrt(n2) < conv) || last_allowed) ? 1 : 0;
+}
+
 // the iterations, on CTAs [0, T) of the launch. Precondition: icp_fill_pass + a grid barrier, map not empty,
 // max_iter > 0, T = icp_team_size(...) > 0. Output in sh.result / sh.iters / sh.cand_total / ... of every team CTA.
 __device__ __noinline__ void op_icp_team(const TeamScratch &ts, const Scratch &sc, Shared &sh, const MapView &m, int n,
@@ -701,25 +762,7 @@ __device__ __noinline__ void op_icp_team(const TeamScratch &ts, const Scratch &s
         team_gather(ts, sh, T, tag);  // (warp 15 holds the sums: no barrier between them and its solver lane)
         if (stamp) sc.dbg[64 + 4 * member + 2] = globaltimer_ns();
         KB_TCYC(6);
-        if (threadIdx.x == BLOCK - 1) {  // warp 15 owns no source point (TQ_MAX = 120)
-            double sys[NACC];
-#pragma unroll
-            for (int i = 0; i < NACC; ++i) sys[i] = sh.red[i];
-            double dx[6];
-            if (!icp_solve_schur(sys, dx)) {      // Registration.cpp:156 — structured 3x3 Schur solve; degenerate
-                double JTJ[36], JTr[6], rhs[6];   // systems take the pivoted LDL^T with Eigen's zero-pivot rule
-                icp_expand(sys, JTJ, JTr);
-#pragma unroll
-                for (int i = 0; i < 6; ++i) rhs[i] = -JTr[i];
-                ldlt6_solve_fast(JTJ, rhs, dx);
-            }
-            const SE3 est = se3_exp_fast(dx);  // :157
-            double n2 = 0.0;
-#pragma unroll
-            for (int i = 0; i < 6; ++i) n2 += dx[i] * dx[i];
-            sh.pending = est;
-            sh.flag = ((sqrt(n2) < conv) || (j + 1 >= max_iter)) ? 1 : 0;  // :163 / :151
-        }
+        if (threadIdx.x == BLOCK - 1) team_solve(sh, conv, j + 1 >= max_iter);  // warp 15 owns no source point (TQ_MAX = 120)
         __syncthreads();
         KB_TCYC(7);
         if (sh.flag) break;  // (T_icp = estimation * T_icp of this iteration: team_accumulate, off the critical path)

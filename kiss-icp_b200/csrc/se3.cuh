@@ -656,27 +656,33 @@ KB_HD void ldlt6_solve_fast(const double A_in[36], const double b[6], double x[6
     for (int i = 0; i < N; ++i) x[i] = d[i];
 }
 
+// SE3::exp for a small rotation (kEps^2 <= |omega|^2 < 0.01).
+// ICP steps are tiny rotations: sin(t/2)/t, cos(t/2), (1 - cos t)/t^2 and (t - sin t)/t^3 are even power series
+// in t — evaluated in t^2 (Horner, FMA) there is no square root, no division and no sincos on the solver's
+// dependent chain (~70 cycles instead of ~450). Truncation < 1e-19 relative for t < 0.1 rad.
+KB_HD SE3 se3_exp_small(const double a[6], double theta_sq) {
+    const V3 upsilon{a[0], a[1], a[2]};
+    const V3 omega{a[3], a[4], a[5]};
+    SE3 r;
+    const double h2 = 0.25 * theta_sq;  // (t/2)^2
+    const double sinc = fma(h2, fma(h2, fma(h2, fma(h2, fma(h2, -1.0 / 39916800.0, 1.0 / 362880.0), -1.0 / 5040.0), 1.0 / 120.0), -1.0 / 6.0), 1.0);
+    const double ch = fma(h2, fma(h2, fma(h2, fma(h2, fma(h2, fma(h2, 1.0 / 479001600.0, -1.0 / 3628800.0), 1.0 / 40320.0), -1.0 / 720.0), 1.0 / 24.0), -0.5), 1.0);
+    const double imag = 0.5 * sinc;  // sin(t/2) / t
+    r.q = Q4{imag * omega.x, imag * omega.y, imag * omega.z, ch};
+    const double t2 = theta_sq;
+    const double ca = fma(t2, fma(t2, fma(t2, fma(t2, fma(t2, -1.0 / 479001600.0, 1.0 / 3628800.0), -1.0 / 40320.0), 1.0 / 720.0), -1.0 / 24.0), 0.5);
+    const double cb = fma(t2, fma(t2, fma(t2, fma(t2, fma(t2, -1.0 / 6227020800.0, 1.0 / 39916800.0), -1.0 / 362880.0), 1.0 / 5040.0), -1.0 / 120.0), 1.0 / 6.0);
+    r.t = apply_I_aW_bW2(omega, ca, cb, true, upsilon);
+    return r;
+}
+
 KB_HD SE3 se3_exp_fast(const double a[6]) {
     const V3 upsilon{a[0], a[1], a[2]};
     const V3 omega{a[3], a[4], a[5]};
     const double theta_sq = sqnorm(omega);
     SE3 r;
     if (theta_sq < kEps * kEps) return se3_exp(a);
-    if (theta_sq < 0.01) {
-        // ICP steps are tiny rotations: sin(t/2)/t, cos(t/2), (1 - cos t)/t^2 and (t - sin t)/t^3 are even power series
-        // in t — evaluated in t^2 (Horner, FMA) there is no square root, no division and no sincos on the solver's
-        // dependent chain (~70 cycles instead of ~450). Truncation < 1e-19 relative for t < 0.1 rad.
-        const double h2 = 0.25 * theta_sq;  // (t/2)^2
-        const double sinc = fma(h2, fma(h2, fma(h2, fma(h2, fma(h2, -1.0 / 39916800.0, 1.0 / 362880.0), -1.0 / 5040.0), 1.0 / 120.0), -1.0 / 6.0), 1.0);
-        const double ch = fma(h2, fma(h2, fma(h2, fma(h2, fma(h2, fma(h2, 1.0 / 479001600.0, -1.0 / 3628800.0), 1.0 / 40320.0), -1.0 / 720.0), 1.0 / 24.0), -0.5), 1.0);
-        const double imag = 0.5 * sinc;  // sin(t/2) / t
-        r.q = Q4{imag * omega.x, imag * omega.y, imag * omega.z, ch};
-        const double t2 = theta_sq;
-        const double ca = fma(t2, fma(t2, fma(t2, fma(t2, fma(t2, -1.0 / 479001600.0, 1.0 / 3628800.0), -1.0 / 40320.0), 1.0 / 720.0), -1.0 / 24.0), 0.5);
-        const double cb = fma(t2, fma(t2, fma(t2, fma(t2, fma(t2, -1.0 / 6227020800.0, 1.0 / 39916800.0), -1.0 / 362880.0), 1.0 / 5040.0), -1.0 / 120.0), 1.0 / 6.0);
-        r.t = apply_I_aW_bW2(omega, ca, cb, true, upsilon);
-        return r;
-    }
+    if (theta_sq < 0.01) return se3_exp_small(a, theta_sq);
     const double theta = sqrt(theta_sq);
     const double inv_theta = fast_rcp(theta);
     double sh, ch;

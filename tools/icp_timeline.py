@@ -55,6 +55,9 @@ for p, t in scans[prime:]:
     c = ns[16:24]
     print("   cycles at iteration 4 (member 0, thread 0): transform+walk+terms -> barrier", c[1] - c[0], "refills", c[2] - c[1],
           "column sums", c[3] - c[2], "store partial", c[4] - c[3], "gather+sums", c[6] - c[4], "solve", c[7] - c[6])
+    w = ns[24:29]
+    print("   warp 0 inside the first phase: transform+validity", w[0] - c[0], "walk", w[1] - w[0], "merge+reload+sqrt", w[2] - w[1], "near check", w[3] - w[2],
+          "terms+row", w[4] - w[3], "wait at barrier", c[1] - w[4])
     print("iters", it, "phases_us", dict(zip(names, np.round(g.last_profile_us, 1))),
           "iter_us first", np.round(d[:3], 2), "median", round(float(np.median(d)), 2) if len(d) else None,
           "env", os.environ.get("KB_ICP_TEAM_Q", "default"))
