@@ -373,7 +373,8 @@ __device__ __forceinline__ void team_accumulate(Shared &sh) {
 
 // two squared distances within a few ulps could round to the same root: compare rounded roots in reference order like
 // GetClosestNeighbor does (whole warp calls; lanes with `near` redo their point's list)
-__device__ __noinline__ void tq_exact_nn(const TeamSmem &sm, int li, int l4, int cnt, bool near, const V3 &p, double *d, V3 *np) {
+__device__ __noinline__ void tq_exact_nn(const TeamSmem sm, int li, int l4, int cnt, bool near, double px, double py, double pz) {
+    const V3 p{px, py, pz};
     double best = DBL_MAX;
     int ek = INT_MAX;
     if (near)
@@ -394,17 +395,20 @@ __device__ __noinline__ void tq_exact_nn(const TeamSmem &sm, int li, int l4, int
             ek = ok2;
         }
     }
-    if (near) {
+    if (near && l4 == 0) {  // the answer goes through the point's header (out-pointers would put the caller's d / np in local memory)
         const double *src = tq_coord(sm, li, ek);
-        *np = V3{src[0], src[32], src[64]};
-        *d = best;
+        TQHead &h = sm.heads[li];
+        h.nn[0] = src[0];
+        h.nn[1] = src[32];
+        h.nn[2] = src[64];
+        h.nn[3] = best;
     }
+    __syncwarp();
 }
 
 // the stale points of this iteration (queue sh.refill_q) are searched again by all warps of the CTA and their lists
 // staged again; the threads that own such a point get its answer
-__device__ __noinline__ void team_refill(Shared &sh, const MapView &m, const TeamSmem &sm, int nref, int par, bool mine, int li,
-                                         double *d, V3 *np) {
+__device__ __noinline__ void team_refill(Shared &sh, const MapView &m, const TeamSmem sm, int nref, int par) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const double radius = 0.2 * m.voxel_size;
     for (int r = warp; r < nref; r += NWARPS) {
@@ -424,11 +428,6 @@ __device__ __noinline__ void team_refill(Shared &sh, const MapView &m, const Tea
         __syncwarp();
     }
     __syncthreads();
-    if (mine) {
-        const TQHead &t = sm.heads[li];
-        *d = t.nn[3];
-        *np = V3{t.nn[0], t.nn[1], t.nn[2]};
-    }
 }
 
 #define KB_WCYC(i) \
@@ -449,12 +448,13 @@ __device__ __noinline__ void team_refill(Shared &sh, const MapView &m, const Tea
 // when d_S < voxel_size - R (its minimiser is then within one voxel of p, i.e. inside the current neighbourhood).
 // Otherwise (moved > R, or a far match that changed voxel) the point is queued and searched again by a whole warp —
 // ALL warps of the CTA serve that queue.
-__device__ __noinline__ void team_queries(const TeamScratch &ts, Shared &sh, const MapView &m, const TeamSmem &sm, int nq, int j,
+__device__ __forceinline__ void team_queries(uint4 *ll, Shared &sh, const MapView &m, const TeamSmem sm, const VoxelDiv vdiv, int nq, int j,
                                           double max_dist, double kscale, int member, int T, unsigned tag,
                                           unsigned long long *dbg) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int l4 = lane & (TQ_LANES - 1), li = tid / TQ_LANES;
-    const double radius = 0.2 * m.voxel_size, r2max = radius * radius;
+    const double voxel_size = vdiv.v;
+    const double radius = 0.2 * voxel_size, r2max = radius * radius;
     const bool have = li < nq;
     const int par = j & 1;
     double *red = reinterpret_cast<double *>(sh.chunk_pref);  // [TQ_MAX][TRED_STRIDE], free during the ICP
@@ -472,7 +472,7 @@ __device__ __noinline__ void team_queries(const TeamScratch &ts, Shared &sh, con
             p = V3{t.p[0], t.p[1], t.p[2]};
             if (j > 0) p = se3_act(sh.pending, p);  // TransformPoints(estimation, source)  Registration.cpp:160
             const V3 moved = p - V3{t.pf[0], t.pf[1], t.pf[2]};
-            const int3 v = point_to_voxel(p.x, p.y, p.z, m.vdiv);
+            const int3 v = point_to_voxel(p.x, p.y, p.z, vdiv);
             same_voxel = t.vx == v.x && t.vy == v.y && t.vz == v.z;
             ok = t.count >= 0 && sqnorm(moved) <= r2max;
             cnt = ok ? t.count : 0;
@@ -536,9 +536,15 @@ __device__ __noinline__ void team_queries(const TeamScratch &ts, Shared &sh, con
         // two squares within a few ulps could round to the same root: then compare rounded roots in reference
         // order like GetClosestNeighbor does (in practice never)
         const bool near = cnt > 0 && s2 <= b2 * (1.0 + 8.8817841970012523e-16);
-        if (__any_sync(FULL, near)) tq_exact_nn(sm, li, l4, cnt, near, p, &d, &np);
+        if (__any_sync(FULL, near)) {
+            tq_exact_nn(sm, li, l4, cnt, near, p.x, p.y, p.z);
+            if (near) {
+                d = t.nn[3];
+                np = V3{t.nn[0], t.nn[1], t.nn[2]};
+            }
+        }
         KB_WCYC(3);
-        ok = ok && (same_voxel || d < (m.voxel_size - radius) * (1.0 - 1e-12));
+        ok = ok && (same_voxel || d < (voxel_size - radius) * (1.0 - 1e-12));
         if (have && !ok && l4 == 0) sh.refill_q[atomicAdd(&sh.refill_n[par], 1)] = li;
         // this point's 16 entries of J^T w J / J^T w r (lane l4: entries 4 l4 ..) + the gate flag -> row li of the
         // reduction scratch; a stale point writes zeros now and its row again after the re-search
@@ -557,10 +563,10 @@ __device__ __noinline__ void team_queries(const TeamScratch &ts, Shared &sh, con
     KB_TCYC(1);
     const int nref = sh.refill_n[par];
     if (nref > 0) {  // uniform; rare
-        double rd = 0.0;
-        V3 rp{0.0, 0.0, 0.0};
-        team_refill(sh, m, sm, nref, par, have && !ok, li, &rd, &rp);
+        team_refill(sh, m, sm, nref, par);
         if (have && !ok) {  // answered by the re-search
+            const double rd = t.nn[3];
+            const V3 rp{t.nn[0], t.nn[1], t.nn[2]};
             double acc[4] = {0.0, 0.0, 0.0, 0.0};
             const bool gate = rd < max_dist;
             if (gate) icp_term4(l4, p, rp, kscale, acc);
@@ -613,10 +619,13 @@ __device__ __noinline__ void team_queries(const TeamScratch &ts, Shared &sh, con
     // one copy per reader, all threads storing (21 lanes doing the T rows one after the other took 2400 cycles):
     // element e = reader * 21 + value -> row [reader][member], 21 consecutive 16-byte chunks
     {
-        uint4 *dst = ts.ll + (static_cast<size_t>(tag & 1u) * TEAM_MAX * TEAM_MAX + member) * NPART;
-        for (int e = tid; e < T * NPART; e += BLOCK) {
-            const int reader = e / NPART, val = e - reader * NPART;
-            ll_store(dst + static_cast<size_t>(reader) * TEAM_MAX * NPART + val, sh.red[val], tag);
+        uint4 *dst = ll + (static_cast<size_t>(tag & 1u) * TEAM_MAX * TEAM_MAX + member) * NPART;
+        // thread -> (value = tid % 32 if < 21, readers tid / 32, tid / 32 + 16, ...): a warp stores one reader's row at a time
+        const int val = lane;
+        if (val < NPART) {
+            const double v = sh.red[val];
+            for (int reader = warp; reader < T; reader += NWARPS)
+                ll_store(dst + static_cast<size_t>(reader) * TEAM_MAX * NPART + val, v, tag);
         }
     }
     KB_TCYC(4);
@@ -630,11 +639,11 @@ __device__ __noinline__ void team_queries(const TeamScratch &ts, Shared &sh, con
 // members lane, lane + 32, lane + 64, lane + 96 of both values in one loop), adds its members in order and leaves
 // the 32 lane partials of each value in shared memory; after one barrier warp 15 adds them (fixed order: the same
 // bits in every team CTA) and its last lane solves. No shuffles: 16 warps x 20 of them would cost ~700 cycles.
-__device__ __forceinline__ void team_gather(const TeamScratch &ts, Shared &sh, int T, unsigned tag) {
+__device__ __forceinline__ void team_gather(const uint4 *ll, Shared &sh, int T, unsigned tag) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double *g = reinterpret_cast<double *>(sh.chunk_pref);  // [NPART][32] (the reduction scratch is done with)
     if (2 * warp < NPART) {
-        const uint4 *base = ts.ll + (static_cast<size_t>(tag & 1u) * TEAM_MAX + blockIdx.x) * TEAM_MAX * NPART;  // my private copy
+        const uint4 *base = ll + (static_cast<size_t>(tag & 1u) * TEAM_MAX + blockIdx.x) * TEAM_MAX * NPART;  // my private copy
         const int v0 = 2 * warp, nv = min(2, NPART - v0);
         constexpr int M = TEAM_MAX / 32;
         double x[2][M];
@@ -726,6 +735,8 @@ __device__ __noinline__ void op_icp_team(const TeamScratch &ts, const Scratch &s
     const int member = static_cast<int>(blockIdx.x);
     const int nq = member < n ? (n - member + T - 1) / T : 0;
     const TeamSmem sm = team_smem(dyn_smem, ts.smem_bytes, (n + T - 1) / T);
+    const VoxelDiv vdiv = m.vdiv;  // (by value into the iteration: `m` itself sits in the kernel's local copy of its parameters)
+    uint4 *const ll = ts.ll;
     {
         // stage this CTA's source points (member, member + T, ...): one warp per point, all warps
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -757,9 +768,9 @@ __device__ __noinline__ void op_icp_team(const TeamScratch &ts, const Scratch &s
         const bool stamp = sc.profile == 1 && j == 4 && threadIdx.x == 0;
         if (stamp) sc.dbg[64 + 4 * member] = globaltimer_ns();
         KB_TCYC(0);
-        team_queries(ts, sh, m, sm, nq, j, max_dist, kscale, member, T, tag, dbg);
+        team_queries(ll, sh, m, sm, vdiv, nq, j, max_dist, kscale, member, T, tag, dbg);
         if (stamp) sc.dbg[64 + 4 * member + 1] = globaltimer_ns();
-        team_gather(ts, sh, T, tag);  // (warp 15 holds the sums: no barrier between them and its solver lane)
+        team_gather(ll, sh, T, tag);  // (warp 15 holds the sums: no barrier between them and its solver lane)
         if (stamp) sc.dbg[64 + 4 * member + 2] = globaltimer_ns();
         KB_TCYC(6);
         if (threadIdx.x == BLOCK - 1) team_solve(sh, conv, j + 1 >= max_iter);  // warp 15 owns no source point (TQ_MAX = 120)

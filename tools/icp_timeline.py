@@ -58,6 +58,9 @@ for p, t in scans[prime:]:
     w = ns[24:29]
     print("   warp 0 inside the first phase: transform+validity", w[0] - c[0], "walk", w[1] - w[0], "merge+reload+sqrt", w[2] - w[1], "near check", w[3] - w[2],
           "terms+row", w[4] - w[3], "wait at barrier", c[1] - w[4])
+    mp = np.zeros(3)
+    N.check(N.lib().kb_pipeline_last_map_profile(g._h, N.ptr(mp)))
+    print("   map update us: transform+claim+pending", round(mp[0], 1), "ordered insertion", round(mp[1], 1), "eviction scan", round(mp[2], 1))
     print("iters", it, "phases_us", dict(zip(names, np.round(g.last_profile_us, 1))),
           "iter_us first", np.round(d[:3], 2), "median", round(float(np.median(d)), 2) if len(d) else None,
           "env", os.environ.get("KB_ICP_TEAM_Q", "default"))
