@@ -22,7 +22,8 @@
 
 namespace kb {
 
-constexpr int TEAM_MAX = 128;   // CTAs of an ICP team (one tagged chunk per value and member; a lane gathers 4 members)
+constexpr int TEAM_MAX = 96;    // CTAs of an ICP team (the gathered partials, 21 x TEAM_MAX doubles, fit the 16 KB reduction scratch)
+static_assert(NPART * TEAM_MAX * 8 <= DS_MAX_CHUNKS * 4, "the gathered partials live in Shared::chunk_pref");
 constexpr int TQ_LANES = 4;     // lanes that share one source point in the list walk
 constexpr int TQ_PER_WARP = 32 / TQ_LANES;
 constexpr int TQ_PER_CTA = 64;  // source points per team CTA by default (8 warps)
@@ -98,6 +99,7 @@ struct TeamScratch {
     double *out;      // [16] result record: pose(7) iters cand_total query_total cache_stats(3)
     QList *qrec;      // [n] per source point, written by the fill pass
     int smem_bytes;   // dynamic shared memory of the launch
+    double radius_frac;  // R / voxel_size: a list stays exact while its point has moved by <= R (shorter lists for smaller R)
 };
 
 // team size for n source points at q_per_cta points per CTA; 0 when the lists would not fit in shared memory
@@ -289,9 +291,9 @@ __device__ __noinline__ NNResult nn_search_list(const MapView &m, const V3 &q, i
 // every CTA of `g`, one warp per source point: source = initial_guess * source (Registration.cpp:146-147),
 // 27-voxel search, candidate list -> qrec[point]
 __device__ __noinline__ void icp_fill_pass(const Grid &g, Shared &sh, const MapView &m, const double *src, int n,
-                                           const SE3 &guess, QList *qrec) {
+                                           const SE3 &guess, QList *qrec, double radius_frac) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const double radius = 0.2 * m.voxel_size;
+    const double radius = radius_frac * m.voxel_size;
     for (int qi = g.rank + g.size * warp; qi < n; qi += g.size * NWARPS) {
         const V3 p = se3_act(guess, V3{src[3 * qi], src[3 * qi + 1], src[3 * qi + 2]});
         nn_search_list(m, p, lane, sh.wnn[warp], &qrec[qi], radius);
@@ -361,7 +363,7 @@ __device__ __forceinline__ void team_stage(const TeamSmem &sm, const MapView &m,
 
 // T_icp = estimation * T_icp (Registration.cpp:161) + work counters of the iteration that was just solved. Run by the
 // solver thread (BLOCK - 1, its warp owns no source point) while the other warps walk their lists for the NEXT iteration.
-__device__ __forceinline__ void team_accumulate(Shared &sh) {
+__device__ __noinline__ void team_accumulate(Shared &sh) {
     sh.t_icp = se3_mul_fast(sh.pending, sh.t_icp);
     sh.cand_total += sh.red[NACC + 1];
     for (int i = 0; i < 3; ++i) sh.cache_stats[i] += sh.red[NACC + 2 + i];
@@ -408,9 +410,8 @@ __device__ __noinline__ void tq_exact_nn(const TeamSmem sm, int li, int l4, int 
 
 // the stale points of this iteration (queue sh.refill_q) are searched again by all warps of the CTA and their lists
 // staged again; the threads that own such a point get its answer
-__device__ __noinline__ void team_refill(Shared &sh, const MapView &m, const TeamSmem sm, int nref, int par) {
+__device__ __noinline__ void team_refill(Shared &sh, const MapView &m, const TeamSmem sm, int nref, int par, double radius) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const double radius = 0.2 * m.voxel_size;
     for (int r = warp; r < nref; r += NWARPS) {
         const int rl = sh.refill_q[r];
         TQHead &h = sm.heads[rl];
@@ -430,10 +431,19 @@ __device__ __noinline__ void team_refill(Shared &sh, const MapView &m, const Tea
     __syncthreads();
 }
 
+// cycle stamps inside the iteration: only in a profiling build (-DKB_PROFILE_TEAM). The iteration's code must stay small:
+// it is executed once per iteration by warps that are at different places, i.e. the instruction cache sees a cyclic
+// sweep over the whole loop body, and a body larger than the cache misses on every line (measured: 36 KB of loop body
+// ran at 7-15 cycles per instruction whatever the data was).
+#ifdef KB_PROFILE_TEAM
 #define KB_WCYC(i) \
     if (dbg != nullptr && threadIdx.x == 0) dbg[24 + (i)] = static_cast<unsigned long long>(clock64())
 #define KB_TCYC(i) \
     if (dbg != nullptr && threadIdx.x == 0) dbg[16 + (i)] = static_cast<unsigned long long>(clock64())
+#else
+#define KB_WCYC(i)
+#define KB_TCYC(i)
+#endif
 
 // DataAssociation + BuildLinearSystem (Registration.cpp:60-121) for this CTA's source points, iteration j. The loop is a
 // dependent chain, so what counts is the length of the per-point instruction chain: four lanes share a point (8
@@ -448,13 +458,13 @@ __device__ __noinline__ void team_refill(Shared &sh, const MapView &m, const Tea
 // when d_S < voxel_size - R (its minimiser is then within one voxel of p, i.e. inside the current neighbourhood).
 // Otherwise (moved > R, or a far match that changed voxel) the point is queued and searched again by a whole warp —
 // ALL warps of the CTA serve that queue.
-__device__ __forceinline__ void team_queries(uint4 *ll, Shared &sh, const MapView &m, const TeamSmem sm, const VoxelDiv vdiv, int nq, int j,
+__device__ __forceinline__ void team_queries(uint4 *ll, Shared &sh, const MapView &m, const TeamSmem sm, const VoxelDiv vdiv, double radius_frac, int nq, int j,
                                           double max_dist, double kscale, int member, int T, unsigned tag,
                                           unsigned long long *dbg) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int l4 = lane & (TQ_LANES - 1), li = tid / TQ_LANES;
     const double voxel_size = vdiv.v;
-    const double radius = 0.2 * voxel_size, r2max = radius * radius;
+    const double radius = radius_frac * voxel_size, r2max = radius * radius;
     const bool have = li < nq;
     const int par = j & 1;
     double *red = reinterpret_cast<double *>(sh.chunk_pref);  // [TQ_MAX][TRED_STRIDE], free during the ICP
@@ -492,7 +502,7 @@ __device__ __forceinline__ void team_queries(uint4 *ll, Shared &sh, const MapVie
         const unsigned cbase = static_cast<unsigned>(__cvta_generic_to_shared(sm.coords));
         const unsigned wbase = cbase + static_cast<unsigned>((li / TQ_PER_WARP) * (sm.K >> 2)) * 768u;
         const int c0 = 4 * (li & (TQ_PER_WARP - 1)) + l4;
-        constexpr int U = 4;
+        constexpr int U = 4;  // (kept small: code size of the loop body matters more than trips)
         for (int i0 = 0; 4 * i0 + l4 < cnt; i0 += U) {
             double d2[U];
 #pragma unroll
@@ -563,7 +573,7 @@ __device__ __forceinline__ void team_queries(uint4 *ll, Shared &sh, const MapVie
     KB_TCYC(1);
     const int nref = sh.refill_n[par];
     if (nref > 0) {  // uniform; rare
-        team_refill(sh, m, sm, nref, par);
+        team_refill(sh, m, sm, nref, par, radius);
         if (have && !ok) {  // answered by the re-search
             const double rd = t.nn[3];
             const V3 rp{t.nn[0], t.nn[1], t.nn[2]};
@@ -635,61 +645,35 @@ __device__ __forceinline__ void team_queries(uint4 *ll, Shared &sh, const MapVie
 // [value]: 21 x T stores of 16 bytes, coalesced 336-byte rows) so that every reader polls lines nobody else reads:
 // with one shared copy the 42 x 352 polling lanes of all CTAs hammered the same few L2 lines and the hop took 5 us
 // (measured; the members themselves arrived within 0.5 us of each other).
-// Warp w < 11 polls values 2w and 2w + 1 of all members (a lane polls
-// members lane, lane + 32, lane + 64, lane + 96 of both values in one loop), adds its members in order and leaves
-// the 32 lane partials of each value in shared memory; after one barrier warp 15 adds them (fixed order: the same
-// bits in every team CTA) and its last lane solves. No shuffles: 16 warps x 20 of them would cost ~700 cycles.
+// Reader: thread t polls chunks t, t + 512, ... of its T x 21 (a two-line loop: the iteration's code has to stay small)
+// and drops the values into shared memory; after one barrier 21 lanes of warp 15 add the members in order (the same
+// bits in every team CTA) and its last lane solves.
 __device__ __forceinline__ void team_gather(const uint4 *ll, Shared &sh, int T, unsigned tag) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double *g = reinterpret_cast<double *>(sh.chunk_pref);  // [NPART][32] (the reduction scratch is done with)
-    if (2 * warp < NPART) {
-        const uint4 *base = ll + (static_cast<size_t>(tag & 1u) * TEAM_MAX + blockIdx.x) * TEAM_MAX * NPART;  // my private copy
-        const int v0 = 2 * warp, nv = min(2, NPART - v0);
-        constexpr int M = TEAM_MAX / 32;
-        double x[2][M];
-        bool ok[2][M];
-#pragma unroll
-        for (int a = 0; a < 2; ++a)
-#pragma unroll
-            for (int u = 0; u < M; ++u) {
-                x[a][u] = 0.0;
-                ok[a][u] = a >= nv || lane + 32 * u >= T;
-            }
-        bool all = false;
-        unsigned spins = 0;
-        while (!all) {
-            all = true;
-#pragma unroll
-            for (int a = 0; a < 2; ++a)
-#pragma unroll
-                for (int u = 0; u < M; ++u) {
-                    if (!ok[a][u]) ok[a][u] = ll_load(&base[static_cast<size_t>(lane + 32 * u) * NPART + v0 + a], tag, &x[a][u]);
-                    all = all && ok[a][u];
-                }
-            all = __all_sync(FULL, all);
-            if (!all && __any_sync(FULL, kb_spin_check(spins, WD_TEAM_GATHER, tag, static_cast<unsigned>(v0)))) break;
+    double *g = reinterpret_cast<double *>(sh.chunk_pref);  // [T][NPART] (the reduction scratch is done with)
+    const uint4 *base = ll + (static_cast<size_t>(tag & 1u) * TEAM_MAX + blockIdx.x) * TEAM_MAX * NPART;  // my private copy
+    const int total = T * NPART;
+    unsigned spins = 0;
+#pragma unroll 1
+    for (int e = threadIdx.x; e < total; e += BLOCK) {
+        double v;
+        while (!ll_load(&base[e], tag, &v)) {
+            if (kb_spin_check(spins, WD_TEAM_GATHER, tag, static_cast<unsigned>(e))) break;
         }
-#pragma unroll
-        for (int a = 0; a < 2; ++a)
-            if (a < nv) {
-                double sum = 0.0;
-#pragma unroll
-                for (int u = 0; u < M; ++u) sum += (lane + 32 * u < T) ? x[a][u] : 0.0;
-                g[(v0 + a) * 32 + lane] = sum;
-            }
+        g[e] = v;
     }
     __syncthreads();
     if (warp == NWARPS - 1) {
         if (lane < NPART) {
-            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-#pragma unroll
-            for (int k = 0; k < 32; k += 4) {
-                s0 += g[lane * 32 + k];
-                s1 += g[lane * 32 + k + 1];
-                s2 += g[lane * 32 + k + 2];
-                s3 += g[lane * 32 + k + 3];
+            double s0 = 0.0, s1 = 0.0;
+            int mbr = 0;
+#pragma unroll 1
+            for (; mbr + 1 < T; mbr += 2) {
+                s0 += g[mbr * NPART + lane];
+                s1 += g[(mbr + 1) * NPART + lane];
             }
-            sh.red[lane] = (s0 + s1) + (s2 + s3);
+            if (mbr < T) s0 += g[mbr * NPART + lane];
+            sh.red[lane] = s0 + s1;
         }
         __syncwarp();
     }
@@ -705,6 +689,7 @@ __device__ __noinline__ void team_solve_ldlt(const double sys[NACC], double dx[6
     ldlt6_solve_fast(JTJ, rhs, dx);
 }
 __device__ __noinline__ SE3 team_exp_large(const double dx[6]) { return se3_exp_fast(dx); }
+__device__ __noinline__ bool team_norm_below(double n2, double conv) { return sqrt(n2) < conv; }
 
 // one thread: dx = JTJ.ldlt().solve(-JTr), estimation = SE3::exp(dx), convergence test (Registration.cpp:156-157,163)
 __device__ __forceinline__ void team_solve(Shared &sh, double conv, bool last_allowed) {
@@ -724,7 +709,11 @@ __device__ __forceinline__ void team_solve(Shared &sh, double conv, bool last_al
 #pragma unroll
     for (int i = 0; i < 6; ++i) n2 += dx[i] * dx[i];
     sh.pending = est;
-    sh.flag = ((sqrt(n2) < conv) || last_allowed) ? 1 : 0;
+    // dx.norm() < convergence_criterion (:163): decided on the square unless it is within rounding of the boundary
+    const double c2 = conv * conv;
+    bool conv_reached = n2 < c2 * (1.0 - 1e-14);
+    if (!conv_reached && n2 <= c2 * (1.0 + 1e-14)) conv_reached = team_norm_below(n2, conv);  // cold
+    sh.flag = (conv_reached || last_allowed) ? 1 : 0;
 }
 
 // the iterations, on CTAs [0, T) of the launch. Precondition: icp_fill_pass + a grid barrier, map not empty,
@@ -764,14 +753,24 @@ __device__ __noinline__ void op_icp_team(const TeamScratch &ts, const Scratch &s
     for (;; ++j) {
         if (sc.profile == 1 && member == 0 && threadIdx.x == 0 && j < 20) sc.dbg[41 + j] = globaltimer_ns();
         const unsigned tag = tag_base + static_cast<unsigned>(j) + 1u;
+#ifdef KB_PROFILE_TEAM
         unsigned long long *dbg = (sc.profile == 1 && member == 0 && j == 4) ? sc.dbg : nullptr;
+#else
+        unsigned long long *dbg = nullptr;
+#endif
+#ifdef KB_PROFILE_TEAM
         const bool stamp = sc.profile == 1 && j == 4 && threadIdx.x == 0;
         if (stamp) sc.dbg[64 + 4 * member] = globaltimer_ns();
+#endif
         KB_TCYC(0);
-        team_queries(ll, sh, m, sm, vdiv, nq, j, max_dist, kscale, member, T, tag, dbg);
+        team_queries(ll, sh, m, sm, vdiv, ts.radius_frac, nq, j, max_dist, kscale, member, T, tag, dbg);
+#ifdef KB_PROFILE_TEAM
         if (stamp) sc.dbg[64 + 4 * member + 1] = globaltimer_ns();
+#endif
         team_gather(ll, sh, T, tag);  // (warp 15 holds the sums: no barrier between them and its solver lane)
+#ifdef KB_PROFILE_TEAM
         if (stamp) sc.dbg[64 + 4 * member + 2] = globaltimer_ns();
+#endif
         KB_TCYC(6);
         if (threadIdx.x == BLOCK - 1) team_solve(sh, conv, j + 1 >= max_iter);  // warp 15 owns no source point (TQ_MAX = 120)
         __syncthreads();

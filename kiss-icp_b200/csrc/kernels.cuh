@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(BLOCK, 1) k_register_frame(const FrameParams P
     }
     if (T > 0) {
         if (P.sc.profile && blockIdx.x == 0 && threadIdx.x == 0) P.sc.dbg[30] = globaltimer_ns();
-        icp_fill_pass(g, sh, P.m, fr.src, n_src, guess, P.team.qrec);
+        icp_fill_pass(g, sh, P.m, fr.src, n_src, guess, P.team.qrec, P.team.radius_frac);
         if (P.sc.profile && blockIdx.x == 0 && threadIdx.x == 0) P.sc.dbg[31] = globaltimer_ns();
         g.sync();
         if (P.sc.profile && blockIdx.x == 0 && threadIdx.x == 0) P.sc.dbg[32] = P.res->t_ns[7] = globaltimer_ns();
@@ -359,7 +359,7 @@ __global__ void __launch_bounds__(BLOCK, 1) k_icp(const IcpParams P) {
         T = icp_team_size(P.n, P.icp_team_q, static_cast<int>(gridDim.x), P.team.smem_bytes);
     }
     if (T > 0) {
-        icp_fill_pass(g, sh, P.m, P.src, P.n, P.guess, P.team.qrec);
+        icp_fill_pass(g, sh, P.m, P.src, P.n, P.guess, P.team.qrec, P.team.radius_frac);
         g.sync();
         if (static_cast<int>(blockIdx.x) >= T) return;
         op_icp_team(P.team, P.sc, sh, P.m, P.n, P.guess, P.max_dist, P.kscale, P.max_iter, P.conv,
