@@ -209,9 +209,30 @@ struct Exec {
         ++launches;
         return KB_OK;
     }
+    // wait for the stream with a deadline (KB_SYNC_TIMEOUT_S, default 30 s; 0 = wait forever): a launch that never
+    // ends is reported as KB_ERR_CUDA instead of hanging the caller (the device watchdog should have fired long before)
     int sync() {
-        CK(cudaStreamSynchronize(stream));
+        RET(wait_deadline([&] { return cudaStreamQuery(stream); }, "stream"));
         return watchdog_check_fwd(device);
+    }
+    template <class Q>
+    int wait_deadline(Q query, const char *what) {
+        static const double limit_s = [] {
+            const char *e = std::getenv("KB_SYNC_TIMEOUT_S");
+            return e ? std::atof(e) : 30.0;
+        }();
+        const auto t0 = std::chrono::steady_clock::now();
+        for (unsigned spins = 0;; ++spins) {
+            const cudaError_t e = query();
+            if (e == cudaSuccess) return KB_OK;
+            if (e != cudaErrorNotReady) return fail(KB_ERR_CUDA, "%s wait failed: %s", what, cudaGetErrorString(e));
+            if ((spins & 0x3ff) == 0x3ff && limit_s > 0.0 &&
+                std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > limit_s) {
+                const int wd = watchdog_check_fwd(device);
+                if (wd != KB_OK) return wd;
+                return fail(KB_ERR_CUDA, "the device did not finish the %s within %.0f s (launch %llu): giving up", what, limit_s, launches);
+            }
+        }
     }
 };
 
@@ -1489,7 +1510,8 @@ int kb_pipeline_register_frames(kb_pipeline *p, const void *const *xyz, const si
         const size_t k = next_absorb;
         {
             StallTrace t("queue: wait for oldest frame");
-            CK(cudaEventSynchronize(p->q[k % D].read));  // also frees this slot's buffers for frame k + D
+            cudaEvent_t ev = p->q[k % D].read;  // also frees this slot's buffers for frame k + D
+            RET(ex.wait_deadline([&] { return cudaEventQuery(ev); }, "queued frame"));
         }
         const FrameResult r = p->q_res[k % D];
         if (r.map_status & ST_NEED_GROW) {  // frames queued behind it were skipped on the device: replay from k
