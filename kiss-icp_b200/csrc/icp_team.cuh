@@ -105,9 +105,11 @@ struct TeamScratch {
 // team size for n source points at q_per_cta points per CTA; 0 when the lists would not fit in shared memory
 __device__ __forceinline__ int icp_team_size(int n, int q_per_cta, int grid, int smem_bytes) {
     q_per_cta = max(1, min(q_per_cta, TQ_MAX));
+    const int tmax = min(grid, TEAM_MAX);
+    if ((n + q_per_cta - 1) / q_per_cta > tmax) q_per_cta = (n + tmax - 1) / tmax;  // small grid (several pipelines per GPU) / big cloud: fuller CTAs
+    if (q_per_cta > TQ_MAX) return 0;
     int T = (n + q_per_cta - 1) / q_per_cta;
     T = max(T, 1);
-    if (T > min(grid, TEAM_MAX)) return 0;
     const int qmax = (n + T - 1) / T;
     const int head_bytes = (qmax * static_cast<int>(sizeof(TQHead)) + 15) & ~15;
     const int warps = (qmax + TQ_PER_WARP - 1) / TQ_PER_WARP;
