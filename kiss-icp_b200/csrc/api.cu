@@ -837,14 +837,14 @@ static int nn_launch(kb_map *map, const double *d_q, size_t n, double *d_p, doub
     const int threads = 256;
     const size_t want = (n * 32 + threads - 1) / threads;
     if (bulk) {
-        const size_t smem = static_cast<size_t>(NNB_WARPS) * NNB_STAGES * NNB_BUF;
+        const size_t smem = static_cast<size_t>(NNB_WARPS) * NNB_BUF;
         const void *k0 = reinterpret_cast<const void *>(&k_nn_query_bulk<false>), *k1 = reinterpret_cast<const void *>(&k_nn_query_bulk<true>);
         for (const void *k : {k0, k1})
             if (std::find(map->ex->smem_opted.begin(), map->ex->smem_opted.end(), k) == map->ex->smem_opted.end()) {
                 CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
                 map->ex->smem_opted.push_back(k);
             }
-        const unsigned blocks = static_cast<unsigned>(std::min<size_t>(want, static_cast<size_t>(sms) * 2));  // 2 CTAs/SM, grid-stride
+        const unsigned blocks = static_cast<unsigned>(std::min<size_t>(want, static_cast<size_t>(sms) * 3));  // 3 CTAs/SM, grid-stride
         if (d_cand)
             k_nn_query_bulk<true><<<blocks, threads, smem, map->ex->stream>>>(map->view(), d_q, n, d_p, d_d, d_cand);
         else

@@ -536,13 +536,13 @@ __global__ void __launch_bounds__(256, 4) k_nn_query(const MapView m, const doub
 // aligned: slot * cap * 24 with cap even), completion is counted by the warp's mbarrier, and while the ~3.5 KB of a
 // query are in flight the warp walks the NEXT query's probe chain; the reduction then reads dense 24-byte slots from
 // shared memory (conflict-free: 16 lanes x 24 B cover 16 distinct 8-byte bank pairs). 24 warps per SM x 3.5 KB in
-// flight is what Little's law asks for at the measured HBM bandwidth. Voxels with an odd count are copied with one
+// flight is what Little's law asks for at the measured HBM bandwidth. (A variant with two buffers per warp — query
+// i + 1 copied while query i is reduced, 16 warps per SM — was measured slower: 1.77 ms vs 1.59 ms.) Voxels with an odd count are copied with one
 // extra point (48-byte multiples); that pad slot is overwritten with +inf coordinates before the reduction, so it can
 // never win. Slot numbers increase with the reference's visiting order, so ties resolve like in k_nn_query.
-constexpr int NNB_BUF = 6144;             // bytes per staging buffer: 256 candidate slots (p95 of a KITTI-scale neighbourhood)
+constexpr int NNB_BUF = 8192;             // bytes per warp: 341 candidate slots (p99 of a KITTI-scale neighbourhood ~300)
 constexpr int NNB_SLOTS = NNB_BUF / 24;
-constexpr int NNB_STAGES = 2;             // two buffers per warp: query i + 1 is copied while query i is reduced
-constexpr int NNB_WARPS = 8;              // 256 threads, 2 CTAs per SM (2 x 96 KB of staging)
+constexpr int NNB_WARPS = 8;              // 256 threads, 3 CTAs per SM
 
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return static_cast<unsigned>(__cvta_generic_to_shared(p)); }
 __device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
@@ -598,30 +598,31 @@ __device__ __forceinline__ void nn_probe_finish(const MapView &m, const NNProbe 
 }
 
 template <bool COUNT>
-__global__ void __launch_bounds__(NNB_WARPS * 32, 2) k_nn_query_bulk(const MapView m, const double *__restrict__ q, size_t n,
+__global__ void __launch_bounds__(NNB_WARPS * 32, 3) k_nn_query_bulk(const MapView m, const double *__restrict__ q, size_t n,
                                                                     double *__restrict__ out_p, double *__restrict__ out_d,
                                                                     unsigned long long *cand_total) {
-    extern __shared__ __align__(128) unsigned char nnb_smem[];  // NNB_WARPS x NNB_STAGES x NNB_BUF
-    __shared__ __align__(8) unsigned long long bars[NNB_WARPS][NNB_STAGES];
-    __shared__ WarpNN wnn[NNB_WARPS];  // neighbourhoods that do not fit a buffer take k_nn_query's register path
+    extern __shared__ __align__(128) unsigned char nnb_smem[];  // NNB_WARPS x NNB_BUF
+    __shared__ __align__(8) unsigned long long bars[NNB_WARPS];
+    __shared__ WarpNN wnn[NNB_WARPS];  // neighbourhoods that do not fit the buffer take k_nn_query's register path
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    unsigned char *buf0 = nnb_smem + warp * (NNB_STAGES * NNB_BUF);
-    if (lane < NNB_STAGES) mbar_init(smem_u32(&bars[warp][lane]), 1);
+    unsigned char *buf = nnb_smem + warp * NNB_BUF;
+    const unsigned bar = smem_u32(&bars[warp]);
+    if (lane == 0) mbar_init(bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncwarp();
-    unsigned phase_bits = 0;  // bit s: parity the next wait on stage s expects
+    unsigned phase = 0;
     const size_t gw = (blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x) >> 5;
     const size_t nw = (static_cast<size_t>(gridDim.x) * blockDim.x) >> 5;
     const int cap = m.cap;
     const double inf = __longlong_as_double(0x7ff0000000000000LL);
     unsigned long long cand = 0;
 
-    // offsets of the neighbourhood in stage `st`'s buffer + the copies themselves
-    auto stage = [&](const V3 &qq, int cnt, int slot, int st) -> NNStaged {
-        NNStaged r;
-        r.q = qq;
-        r.cnt = cnt;
-        r.slot = slot;
+    // offsets of the neighbourhood in the buffer + the copies themselves
+    auto stage = [&](const V3 &qq, int cnt, int slot) -> NNStaged {
+        NNStaged st;
+        st.q = qq;
+        st.cnt = cnt;
+        st.slot = slot;
         const int pc = (cnt + 1) & ~1;
         int incl = pc, real = cnt;
 #pragma unroll
@@ -630,58 +631,50 @@ __global__ void __launch_bounds__(NNB_WARPS * 32, 2) k_nn_query_bulk(const MapVi
             if (lane >= o) incl += t;
             real += __shfl_xor_sync(FULL, real, o);
         }
-        r.startp = incl - pc;
-        r.totalp = __shfl_sync(FULL, incl, 31);
-        r.real = real;
-        r.staged = r.totalp > 0 && r.totalp <= NNB_SLOTS;
-        if (r.staged) {
-            const unsigned bar = smem_u32(&bars[warp][st]);
-            // the previous user's shared-memory reads and pad writes (generic proxy) come before these async-proxy writes
+        st.startp = incl - pc;
+        st.totalp = __shfl_sync(FULL, incl, 31);
+        st.real = real;
+        st.staged = st.totalp > 0 && st.totalp <= NNB_SLOTS;
+        if (st.staged) {
+            // the previous query's shared-memory reads and pad writes (generic proxy) come before these async-proxy writes
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            if (lane == 0) mbar_expect_tx(bar, static_cast<unsigned>(r.totalp) * 24u);
+            if (lane == 0) mbar_expect_tx(bar, static_cast<unsigned>(st.totalp) * 24u);
             __syncwarp();
             if (cnt > 0)
-                bulk_g2s(smem_u32(buf0 + st * NNB_BUF + r.startp * 24), m.points + static_cast<size_t>(slot) * cap * 3,
+                bulk_g2s(smem_u32(buf + st.startp * 24), m.points + static_cast<size_t>(slot) * cap * 3,
                          static_cast<unsigned>(pc) * 24u, bar);
         }
-        return r;
+        return st;
     };
 
-    // software pipeline per warp: [probe chain of query i+1 | copies of query i+1 issued] while [query i waits / reduces],
-    // first probes of query i+2 in flight behind them
     NNProbe nxt;
-    NNStaged cur, ahead;
-    bool have_ahead = false;
+    NNStaged cur;
     if (gw < n) {
         NNProbe first;
         nn_issue(m, q, gw, lane, first);
         int c0, s0;
         nn_probe_finish(m, first, lane, &c0, &s0);
-        cur = stage(first.q, c0, s0, 0);
+        cur = stage(first.q, c0, s0);
         if (gw + nw < n) nn_issue(m, q, gw + nw, lane, nxt);
     }
-    int it = 0;
-    for (size_t i = gw; i < n; i += nw, ++it) {
-        const int st = it & 1;
-        // (1) the next query: finish its probe chain and start its copies into the other buffer
-        have_ahead = i + nw < n;
-        if (have_ahead) {
-            int c1, s1;
+    for (size_t i = gw; i < n; i += nw) {
+        const bool more = i + nw < n;
+        // (1) while the blocks of query i fly: the probe chain of query i + 1, first probes of query i + 2
+        int c1 = 0, s1 = -1;
+        V3 q1{0.0, 0.0, 0.0};
+        if (more) {
             nn_probe_finish(m, nxt, lane, &c1, &s1);
-            ahead = stage(nxt.q, c1, s1, st ^ 1);
+            q1 = nxt.q;
             if (i + 2 * nw < n) nn_issue(m, q, i + 2 * nw, lane, nxt);
         }
-        // (2) reduce query i from its buffer
+        // (2) reduce query i
         NNResult r;
         if (cur.staged) {
-            const unsigned bar = smem_u32(&bars[warp][st]);
-            const unsigned parity = (phase_bits >> st) & 1u;
             unsigned spins = 0;
-            while (!mbar_try_wait(bar, parity)) {
-                if (kb_spin_check(spins, WD_NN_BULK, static_cast<unsigned>(i), parity)) break;
+            while (!mbar_try_wait(bar, phase)) {
+                if (kb_spin_check(spins, WD_NN_BULK, static_cast<unsigned>(i), phase)) break;
             }
-            phase_bits ^= 1u << st;
-            unsigned char *buf = buf0 + st * NNB_BUF;
+            phase ^= 1u;
             if (cur.cnt & 1) {  // pad slot of an odd voxel: can never win
                 double *pad = reinterpret_cast<double *>(buf + (cur.startp + cur.cnt) * 24);
                 pad[0] = inf;
@@ -723,7 +716,7 @@ __global__ void __launch_bounds__(NNB_WARPS * 32, 2) k_nn_query_bulk(const MapVi
                 nn_reduce(best, bseq, bp);
                 r = NNResult{best, bp, cur.real};
             }
-            __syncwarp();  // every lane is done with the buffer before it is reused (two queries from now)
+            __syncwarp();  // every lane is done with the buffer before the next query's copies land in it
         } else if (cur.totalp == 0) {
             r = NNResult{DBL_MAX, V3{0.0, 0.0, 0.0}, 0};
         } else {
@@ -736,7 +729,8 @@ __global__ void __launch_bounds__(NNB_WARPS * 32, 2) k_nn_query_bulk(const MapVi
             out_d[i] = r.d;
         }
         if (COUNT) cand += r.candidates;
-        if (have_ahead) cur = ahead;
+        // (3) copies of query i + 1
+        if (more) cur = stage(q1, c1, s1);
     }
     if (COUNT && lane == 0 && cand) atomicAdd(cand_total, cand);
 }
