@@ -239,12 +239,11 @@ def run_reference(args, rank, world):
     dt = float(np.median(win))
     val = nseq * args.steps / dt
     cfg = common_config(args, nseq)
-    cfg["windows"] = R
     line = {"impl": "reference", "metric": WORKLOADS[args.workload]["metric"], "value": val, "unit": "scans/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": cfg,
-            "windows": {"ms": [w * 1e3 for w in win]},
+            "windows": {"ms": [w * 1e3 for w in win], "timed": R, "note": "the reference arm times at most 5 of the --repeats windows (bounded run time)"},
             "note": "reference CPU path = dependency-free restatement of cpp/kiss_icp (oracle port, OpenMP for TBB); the real "
                     "TBB/Eigen build needs network-fetched deps. N sequences run concurrently on the host cores.",
             "cpu_baseline": {"value": val, "unit": "scans/s", "cores": nt * nseq, "kind": "port",

@@ -34,6 +34,17 @@ const double *mat4_arg(const arr &a) {  // Eigen::Matrix4d arguments: NumPy is r
     if (a.ndim() != 2 || a.shape(0) != 4 || a.shape(1) != 4) throw py::cast_error("expected a (4, 4) array");
     return a.data();
 }
+// blocking GPU work runs without the GIL (other Python threads — a ROS executor, a visualizer — keep running; the
+// reference holds it, SURVEY.md 8b "Threading")
+template <class F>
+void nogil(F &&call) {
+    int st;
+    {
+        py::gil_scoped_release release;
+        st = call();
+    }
+    check(st);
+}
 arr points_out(size_t n) { return arr({static_cast<py::ssize_t>(n), static_cast<py::ssize_t>(3)}); }
 py::object first_rows(const arr &a, size_t n) {  // the first n points of an output buffer sized for the worst case
     return a[py::slice(0, static_cast<py::ssize_t>(n), 1)].attr("copy")();
@@ -93,27 +104,32 @@ PYBIND11_MODULE(kiss_icp_pybind, m) {
                  check(kb_map_empty(s.h, &e));
                  return e != 0;
              })
-        // the two _update overloads of the reference: (points, origin[3]) and (points, pose[4,4])
+        // the two _update overloads of the reference (kiss_icp_pybind.cpp:59-70): (points, origin[3]) and (points, pose[4,4]),
+        // told apart like pybind11/eigen.h tells Vector3d from Matrix4d: by shape, next overload on a mismatch
         .def(
             "_update",
-            [](Map &s, const arr &pts, const arr &where) {
+            [](Map &s, const arr &pts, const arr &origin) {
+                if (origin.ndim() != 1 || origin.shape(0) != 3) throw py::reference_cast_error();  // -> try (points, pose)
                 points_arg(pts);
-                if (where.ndim() == 2)
-                    check(kb_map_update_pose(s.h, pts.data(), pts.shape(0), mat4_arg(where)));
-                else if (where.ndim() == 1 && where.shape(0) == 3)
-                    check(kb_map_update_origin(s.h, pts.data(), pts.shape(0), where.data()));
-                else
-                    throw py::cast_error("expected an origin (3,) or a pose (4, 4)");
+                nogil([&] { return kb_map_update_origin(s.h, pts.data(), pts.shape(0), origin.data()); });
+            },
+            "points"_a, "origin"_a)
+        .def(
+            "_update",
+            [](Map &s, const arr &pts, const arr &pose) {
+                if (pose.ndim() != 2 || pose.shape(0) != 4 || pose.shape(1) != 4) throw py::reference_cast_error();  // -> TypeError
+                points_arg(pts);
+                nogil([&] { return kb_map_update_pose(s.h, pts.data(), pts.shape(0), pose.data()); });
             },
             "points"_a, "pose"_a)
         .def(
-            "_add_points", [](Map &s, const arr &pts) { check(kb_map_add_points(s.h, points_arg(pts).data(), pts.shape(0))); },
+            "_add_points", [](Map &s, const arr &pts) { points_arg(pts); nogil([&] { return kb_map_add_points(s.h, pts.data(), pts.shape(0)); }); },
             "points"_a)
         .def(
             "_remove_far_away_points",
             [](Map &s, const arr &origin) {
                 if (origin.ndim() != 1 || origin.shape(0) != 3) throw py::cast_error("expected an origin (3,)");
-                check(kb_map_remove_far(s.h, origin.data()));
+                nogil([&] { return kb_map_remove_far(s.h, origin.data()); });
             },
             "origin"_a)
         .def("_point_cloud", [](Map &s) {
@@ -133,8 +149,9 @@ PYBIND11_MODULE(kiss_icp_pybind, m) {
                 const size_t n = static_cast<size_t>(pts.shape(0));
                 arr out = points_out(n);
                 size_t kept = 0;
-                check(kb_preprocessor_preprocess(s.h, pts.data(), n, timestamps.data(), static_cast<size_t>(timestamps.size()),
-                                                 mat4_arg(relative_motion), out.mutable_data(), n, &kept));
+                const double *M = mat4_arg(relative_motion);
+                double *o = out.mutable_data();
+                nogil([&] { return kb_preprocessor_preprocess(s.h, pts.data(), n, timestamps.data(), static_cast<size_t>(timestamps.size()), M, o, n, &kept); });
                 return first_rows(out, kept);
             },
             "points"_a, "timestamps"_a, "relative_motion"_a);
@@ -147,8 +164,9 @@ PYBIND11_MODULE(kiss_icp_pybind, m) {
                double kernel) {
                 points_arg(pts);
                 arr out({static_cast<py::ssize_t>(4), static_cast<py::ssize_t>(4)});
-                check(kb_registration_align_points_to_map(s.h, pts.data(), pts.shape(0), voxel_map.h, mat4_arg(initial_guess),
-                                                          max_correspondance_distance, kernel, out.mutable_data()));
+                const double *G = mat4_arg(initial_guess);
+                double *o = out.mutable_data();
+                nogil([&] { return kb_registration_align_points_to_map(s.h, pts.data(), pts.shape(0), voxel_map.h, G, max_correspondance_distance, kernel, o); });
                 return out;
             },
             "points"_a, "voxel_map"_a, "initial_guess"_a, "max_correspondance_distance"_a, "kernel"_a);
@@ -173,7 +191,8 @@ PYBIND11_MODULE(kiss_icp_pybind, m) {
             const size_t n = static_cast<size_t>(frame.shape(0));
             arr out = points_out(n);
             size_t kept = 0;
-            check(kb_voxel_down_sample(frame.data(), n, voxel_size, out.mutable_data(), n, &kept));
+            double *o = out.mutable_data();
+            nogil([&] { return kb_voxel_down_sample(frame.data(), n, voxel_size, o, n, &kept); });
             return first_rows(out, kept);
         },
         "frame"_a, "voxel_size"_a);

@@ -19,6 +19,7 @@ ROOT = os.path.dirname(_HERE)
 LIB_PATH = os.environ.get("KB_LIB") or os.path.join(_HERE, "libkiss_icp_b200.so")  # KB_LIB: A/B builds side by side
 CSRC = os.path.join(_HERE, "csrc")
 HEADER = os.path.join(ROOT, "include", "kiss_icp_b200.h")
+DEBUG_HEADER = os.path.join(ROOT, "include", "kiss_icp_b200_debug.h")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
@@ -35,7 +36,7 @@ def _nvcc():
 
 
 def sources():
-    return [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC))] + [HEADER]
+    return [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC))] + [HEADER, DEBUG_HEADER]
 
 
 def build(force: bool = False, verbose: bool = False) -> str:

@@ -19,6 +19,7 @@
 #include <vector>
 
 #include "../../include/kiss_icp_b200.h"
+#include "../../include/kiss_icp_b200_debug.h"
 #include "kernels.cuh"
 
 using namespace kb;
@@ -149,7 +150,6 @@ struct Exec {
         CK(cudaMemsetAsync(sc.bar, 0, BAR_WORDS * sizeof(unsigned), stream));
         CK(cudaMalloc(&sc.blk_d, sizeof(double) * 2 * grid * NPART));
         CK(cudaMalloc(&sc.blk_i, sizeof(int) * 2 * grid));
-        CK(cudaMalloc(&sc.icp_rec, sizeof(double) * 2 * ICP_REC));
         CK(cudaMalloc(&sc.ll_part, sizeof(uint4) * NPART * grid));
         CK(cudaMalloc(&sc.ll_res, sizeof(uint4) * LL_RES));
         CK(cudaMalloc(&sc.ll_group, sizeof(uint4) * NPART * 16));
@@ -172,7 +172,6 @@ struct Exec {
         if (sc.bar) cudaFree(sc.bar);
         if (sc.blk_d) cudaFree(sc.blk_d);
         if (sc.blk_i) cudaFree(sc.blk_i);
-        if (sc.icp_rec) cudaFree(sc.icp_rec);
         if (sc.ll_part) cudaFree(sc.ll_part);
         if (sc.ll_res) cudaFree(sc.ll_res);
         if (sc.ll_group) cudaFree(sc.ll_group);

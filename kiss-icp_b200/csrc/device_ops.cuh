@@ -35,7 +35,6 @@ constexpr int NACC = 16;  // unique accumulators of the 6x6 normal equations (se
 constexpr int NPART = NACC + 5;  // per-CTA partial: accumulators, #correspondences, #candidate points, cache hits/fills/overflows
 constexpr int DS_MAX_CHUNKS = 4096;  // downsample: 32-bucket chunks up to 131072 buckets (a 65k-point scan), coarser beyond
 constexpr int BAR_ARRIVE = 32, BAR_TEAM = 64, BAR_WORDS = 96;  // word offsets inside Scratch::bar (one 128-byte line each)
-constexpr int ICP_REC = 32;
 constexpr int LL_RES = 16;        // est(7) + done flag, final pose(7), spare      // est(7) t_icp(7) final(7) conv cand_total query_total ...
 
 enum Counter { C_LIVE = 0, C_TOMB = 1, C_POINTS = 2, C_STATUS = 3, C_TOUCHED = 4, C_NCOUNTERS = 8 };
@@ -80,7 +79,6 @@ struct Scratch {
     unsigned *bar;  // [0] grid barrier counter, [BAR_ARRIVE] CTAs that left the kernel (Grid::finish), [BAR_TEAM] barrier counter of the front-end team: one 128-B
                     // line each (arrival atomics must not fight the epoch pollers); zeroed before each launch
     double *blk_d;  // [2][NPART][grid] doubles (ping-pong by ICP iteration parity; value-major so the reduce is coalesced)
-    double *icp_rec;  // (unused by the tagged protocol; kept for the debug tools)
     uint4 *ll_part;   // [NPART][grid] epoch-tagged partial systems, one 16-B chunk per value and CTA
     uint4 *ll_res;    // [LL_RES] epoch-tagged result record published by the coordinator
     uint4 *ll_group;  // [NPART][16] epoch-tagged group partials (second level of the gather tree)

@@ -10,10 +10,18 @@ import pytest
 from conftest import ROOT
 
 
-def declared_symbols():
-    text = open(os.path.join(ROOT, "include", "kiss_icp_b200.h")).read()
-    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return sorted(set(re.findall(r"\b(kb_[a-z0-9_]+)\s*\(", text)))
+def declared_symbols(headers=("kiss_icp_b200.h", "kiss_icp_b200_debug.h")):
+    names = set()
+    for h in headers:
+        text = open(os.path.join(ROOT, "include", h)).read()
+        text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+        names |= set(re.findall(r"\b(kb_[a-z0-9_]+)\s*\(", text))
+    return sorted(names)
+
+
+def test_debug_entry_points_are_not_in_the_drop_in_header():
+    public = declared_symbols(("kiss_icp_b200.h",))
+    assert not [n for n in public if n.startswith("kb_debug_") or n.endswith("_profile") or "stamps" in n]
 
 
 def test_library_exports_every_declared_symbol():

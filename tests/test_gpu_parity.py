@@ -329,6 +329,30 @@ def test_pipeline_kitti_shape_full_size(K, O):
     assert g.local_map.num_points() == o.local_map.num_points()
 
 
+def test_pipeline_kitti_shape_500_scans_queued(K, O):
+    """500 full-size KITTI-shape scans, free running through the QUEUED path (front-end prefetch, ICP team) against the
+    oracle: pose per scan within 1e-6 m / 1e-6 rad (bar: 1e-4), identical iteration counts"""
+    import torch
+    from kiss_icp_b200 import synthetic
+    L = synthetic.kitti_shape(seed=4, device="cuda")
+    g, o = K.KissICP(K.load_config()), O.KissICP()
+    worst, mism = 0.0, 0
+    for lo in range(0, 500, 100):
+        scans = [L.scan_torch(k)[0].contiguous() for k in range(lo, lo + 100)]
+        torch.cuda.synchronize()
+        g.start_history(100)
+        poses = g._register_frames_raw([s.data_ptr() for s in scans], [s.shape[0] for s in scans], [None] * 100, [0] * 100, 2)
+        its = [h.iterations for h in g.history()]
+        for i, s in enumerate(scans):
+            o.register_frame(s.cpu().numpy(), np.empty(0), want_clouds=False)
+            dt, dr = pose_error(poses[i], o.pose)
+            worst = max(worst, dt, dr)
+            mism += int(its[i] != o.last_iterations)
+            assert dt < 1e-4 and dr < 1e-4, (lo + i, dt, dr)
+    assert worst < 1e-6 and mism == 0, (worst, mism)
+    assert g.local_map.num_points() == o.local_map.num_points()
+
+
 def test_pipeline_errors_and_state_accessors(K, O):
     icp = K.KissICP(K.load_config())
     with pytest.raises(IndexError):

@@ -149,8 +149,86 @@ def test_every_bound_call_equals_the_ctypes_mirror(mod):
     Ta = mod._Registration(500, 1e-4, 0)._align_points_to_map(src, ma, T, 3.0, 1.0)
     Tb = K.Registration(500, 1e-4, 0).align_points_to_map(src, mb, T, 3.0, 1.0)
     assert np.array_equal(Ta, Tb)
-    ma._update(ds, np.array([1.0, 0.0, 0.0]))  # the (points, origin) overload
+    ma._update(ds, np.array([1.0, 0.0, 0.0]))  # the (points, origin) overload, positional
     mb.update(ds, np.array([1.0, 0.0, 0.0]))
     assert np.array_equal(ma._point_cloud(), mb.point_cloud())
+    ma._update(points=ds[:50] + 0.3, origin=np.zeros(3))  # ... and by keyword, like the reference's two py::arg lists
+    ma._update(points=ds[:50] + 0.6, pose=np.eye(4))
+    mb.update(ds[:50] + 0.3, np.zeros(3))
+    mb.update(ds[:50] + 0.6, np.eye(4))
+    assert np.array_equal(ma._point_cloud(), mb.point_cloud())
+    with pytest.raises(TypeError):  # neither overload takes a (2, 2) second argument
+        ma._update(ds, np.zeros((2, 2)))
     ma._clear()
     assert ma._empty()
+
+
+class _ReferenceKissICP:
+    """python/kiss_icp/kiss_icp.py:33-80 (class KissICP) restated on the bound module — the GPU box has no reference
+    checkout; where /root/reference exists the test below uses the reference's own class instead"""
+
+    def __init__(self, mod, max_range=100.0, voxel_size=1.0):
+        self.m = mod
+        self.voxel_size = voxel_size
+        self.last_pose, self.last_delta = np.eye(4), np.eye(4)
+        self.threshold = mod._AdaptiveThreshold(2.0, 0.1, max_range)
+        self.pre = mod._Preprocessor(max_range, 0.0, True, 0)
+        self.reg = mod._Registration(500, 1e-4, 0)
+        self.map = mod._VoxelHashMap(voxel_size, max_range, 20)
+
+    def register_frame(self, frame, timestamps):
+        m = self.m
+        frame = np.asarray(self.pre._preprocess(m._Vector3dVector(frame), timestamps, self.last_delta))
+        ds = np.asarray(m._voxel_down_sample(m._Vector3dVector(frame), self.voxel_size * 0.5))
+        source = np.asarray(m._voxel_down_sample(m._Vector3dVector(ds), self.voxel_size * 1.5))
+        sigma = self.threshold._compute_threshold()
+        guess = self.last_pose @ self.last_delta
+        new_pose = self.reg._align_points_to_map(points=m._Vector3dVector(source), voxel_map=self.map, initial_guess=guess,
+                                                 max_correspondance_distance=3 * sigma, kernel=sigma)
+        self.threshold._update_model_deviation(np.linalg.inv(guess) @ new_pose)
+        self.map._update(m._Vector3dVector(ds), new_pose)
+        self.last_delta = np.linalg.inv(self.last_pose) @ new_pose
+        self.last_pose = new_pose
+        return frame, source
+
+
+@pytest.mark.gpu
+def test_reference_python_register_frame_loop_on_the_gpu(mod, O):
+    """the reference's Python RegisterFrame loop (python/kiss_icp/kiss_icp.py:43-75) over this backend's pybind module
+    against the oracle: 10 scans, pose per scan within 1e-9. Uses the reference's own unmodified class where the
+    checkout exists, its restatement above otherwise."""
+    import time
+    from kiss_icp_b200 import synthetic
+    L = synthetic.small_shape(seed=11, beams=32, cols=512, stamps="column")
+    icp = None
+    saved = {k: v for k, v in sys.modules.items() if k == "kiss_icp" or k.startswith("kiss_icp.")}
+    use_ref = os.path.isdir(os.path.join(REF, "kiss_icp"))
+    try:
+        if use_ref:
+            sys.path.insert(0, REF)
+            import kiss_icp
+            pkg = types.ModuleType("kiss_icp.pybind")
+            pkg.__path__ = []
+            pkg.kiss_icp_pybind = mod
+            sys.modules["kiss_icp.pybind"] = pkg
+            sys.modules["kiss_icp.pybind.kiss_icp_pybind"] = mod
+            kiss_icp.pybind = pkg
+            from kiss_icp.config import load_config
+            from kiss_icp.kiss_icp import KissICP
+            icp = KissICP(load_config(None))
+        else:
+            icp = _ReferenceKissICP(mod)
+        o = O.KissICP()
+        t0 = time.perf_counter()
+        for k in range(10):
+            p, t = L.scan(k)
+            icp.register_frame(p, t)
+            o.register_frame(p, t, want_clouds=False)
+            assert np.abs(np.asarray(icp.last_pose) - o.pose).max() < 1e-9, k
+        print("reference Python loop on the pybind module: %.0f scans/s (incl. the oracle's time)" % (10 / (time.perf_counter() - t0)))
+    finally:
+        if use_ref:
+            sys.path.remove(REF)
+            for k in [k for k in sys.modules if k == "kiss_icp" or k.startswith("kiss_icp.")]:
+                del sys.modules[k]
+            sys.modules.update(saved)
