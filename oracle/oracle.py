@@ -49,7 +49,7 @@ def lib():
         L.oracle_pipeline_map.restype = C.c_void_p
         L.oracle_pipeline_sigma.restype = C.c_double
         for name in ("oracle_map_num_voxels", "oracle_map_num_points", "oracle_map_pointcloud", "oracle_map_dump",
-                     "oracle_voxel_downsample", "oracle_preprocess"):
+                     "oracle_voxel_downsample", "oracle_preprocess", "oracle_robin_trace"):
             getattr(L, name).restype = C.c_long
         L.oracle_voxel_hash.restype = C.c_uint
         _lib = L

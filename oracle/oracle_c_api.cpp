@@ -252,4 +252,38 @@ int oracle_num_threads() {
 #endif
 }
 
+
+// a trace of map operations on the robin_map emulation -> iteration order afterwards (tests/test_oracle_robin_fuzz.py
+// replays the same trace on an independent Python emulation). ops[i] = {op, x, y, z}: 0 insert (value = i), 1 erase(find(key)),
+// 2 clear(), 3 reserve(x). out_keys: [cap][3] keys in iteration order, out_vals: [cap] their values.
+long oracle_robin_trace(const int *ops, long n_ops, int *out_keys, int *out_vals, long cap, long *bucket_count) {
+    oracle::RobinMap<int> m;
+    for (long i = 0; i < n_ops; ++i) {
+        const int *o = ops + 4 * i;
+        const oracle::Voxel key{o[1], o[2], o[3]};
+        if (o[0] == 0) {
+            m.insert(key, static_cast<int>(i));
+        } else if (o[0] == 1) {
+            const size_t ib = m.find_index(key);
+            if (m.bucket_count() && ib < m.bucket_count()) m.erase_at(ib);
+        } else if (o[0] == 2) {
+            m.clear();
+        } else if (o[0] == 3) {
+            m.reserve(static_cast<size_t>(o[1]));
+        }
+    }
+    long k = 0;
+    for (size_t ib = m.next_occupied(0); ib < m.bucket_count(); ib = m.next_occupied(ib + 1)) {
+        if (k < cap) {
+            out_keys[3 * k] = m.buckets()[ib].key.x;
+            out_keys[3 * k + 1] = m.buckets()[ib].key.y;
+            out_keys[3 * k + 2] = m.buckets()[ib].key.z;
+            out_vals[k] = m.buckets()[ib].value;
+        }
+        ++k;
+    }
+    if (bucket_count) *bucket_count = static_cast<long>(m.bucket_count());
+    return k;
+}
+
 }  // extern "C"

@@ -80,6 +80,18 @@ public:
         return nullptr;
     }
     const V *find(const Voxel &key) const { return const_cast<RobinMap *>(this)->find(key); }
+    // bucket index of `key` or bucket_count() (= end()): erase(find(key)) in the fuzz tests
+    size_t find_index(const Voxel &key) const {
+        if (buckets_.empty()) return 0;
+        size_t ib = voxel_hash(key) & mask_;
+        int32_t dist = 0;
+        while (dist <= buckets_[ib].dist) {
+            if (buckets_[ib].key == key) return ib;
+            ib = (ib + 1) & mask_;
+            ++dist;
+        }
+        return buckets_.size();
+    }
     bool contains(const Voxel &key) const { return find(key) != nullptr; }
 
     // insert_impl: returns false if the key was already present.
