@@ -61,6 +61,7 @@ int device_count() {
     return n;
 }
 
+bool device_is_stuck(int device);
 template <class T>
 struct DBuf {
     T *p = nullptr;
@@ -78,7 +79,7 @@ struct DBuf {
         return KB_OK;
     }
     ~DBuf() {
-        if (p) cudaFree(p);
+        if (p && !device_is_stuck(-1)) cudaFree(p);  // (-1: any device)
     }
 };
 
@@ -112,6 +113,8 @@ size_t pow2_at_least(size_t v) {
 
 int watchdog_check_fwd(int device);
 int watchdog_init_fwd(int device);
+void device_stuck_fwd(int device);
+std::string phase_marks_fwd(int device);
 
 // execution context: device, stream, persistent-grid size and the cross-CTA scratch
 struct Exec {
@@ -169,6 +172,7 @@ struct Exec {
         return KB_OK;
     }
     ~Exec() {
+        if (device_is_stuck(device)) return;
         if (sc.bar) cudaFree(sc.bar);
         if (sc.blk_d) cudaFree(sc.blk_d);
         if (sc.blk_i) cudaFree(sc.blk_i);
@@ -228,8 +232,10 @@ struct Exec {
             if ((spins & 0x3ff) == 0x3ff && limit_s > 0.0 &&
                 std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > limit_s) {
                 const int wd = watchdog_check_fwd(device);
+                device_stuck_fwd(device);
                 if (wd != KB_OK) return wd;
-                return fail(KB_ERR_CUDA, "the device did not finish the %s within %.0f s (launch %llu): giving up", what, limit_s, launches);
+                return fail(KB_ERR_CUDA, "the device did not finish the %s within %.0f s (launch %llu): giving up; %s", what, limit_s, launches,
+                            phase_marks_fwd(device).c_str());
             }
         }
     }
@@ -268,6 +274,44 @@ int watchdog_check(int device) {
                 names[code < 6 ? code : 0], block, thread, a, b);
 }
 
+bool g_stuck[64];
+void device_stuck_fwd(int device) {
+    if (device >= 0 && device < 64) g_stuck[device] = true;
+}
+// a launch on this device never ended: cudaFree & co. would block forever, so the destructors leak instead
+bool device_is_stuck(int device) {
+    if (device < 0) {
+        for (bool b : g_stuck)
+            if (b) return true;
+        return false;
+    }
+    return device < 64 && g_stuck[device];
+}
+std::string phase_marks_fwd(int device) {
+    // the compute stream is stuck: read the marks on a stream of their own (bounded wait, the copy engine is free)
+    unsigned marks[256];
+    cudaStream_t side = nullptr;
+    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking) != cudaSuccess) return "";
+    std::string out;
+    if (cudaMemcpyFromSymbolAsync(marks, g_kb_marks, sizeof(marks), 0, cudaMemcpyDeviceToHost, side) == cudaSuccess) {
+        const auto t0 = std::chrono::steady_clock::now();
+        cudaError_t q;
+        while ((q = cudaStreamQuery(side)) == cudaErrorNotReady &&
+               std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() < 5.0) {
+        }
+        if (q == cudaSuccess) {
+            out = "phase marks per CTA:";
+            char buf[16];
+            for (int i = 0; i < 160; ++i) {
+                std::snprintf(buf, sizeof(buf), " %x", marks[i]);
+                out += buf;
+            }
+        } else {
+            out = "(phase marks unreadable)";
+        }
+    }
+    return out;  // (the side stream is leaked with the rest of the stuck context)
+}
 int watchdog_check_fwd(int device) { return watchdog_check(device); }
 int watchdog_init_fwd(int device) { return watchdog_init(device); }
 
@@ -403,6 +447,7 @@ struct kb_map {
         counters = t.counters;
     }
     ~kb_map() {
+        if (ex && device_is_stuck(ex->device)) return;
         if (ex) cudaSetDevice(ex->device);
         Table t = current();
         free_table(t);
@@ -595,6 +640,10 @@ struct kb_pipeline {
     FrameResult *q_res = nullptr;      // [Q_DEPTH] pinned host copies of the frame results
     FrameResult *q_res_dev = nullptr;  // [Q_DEPTH] device side: where the kernels write them
     ~kb_pipeline() {
+        if (ex && device_is_stuck(ex->device)) {
+            map = nullptr;  // (leaked on purpose)
+            return;
+        }
         if (ex) cudaSetDevice(ex->device);
         for (Slot &s : q) {
             if (s.pin_xyz) cudaFreeHost(s.pin_xyz);

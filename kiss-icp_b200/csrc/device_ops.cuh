@@ -34,7 +34,7 @@ constexpr int NWARPS = BLOCK / 32;
 constexpr int NACC = 16;  // unique accumulators of the 6x6 normal equations (see icp_accumulate)
 constexpr int NPART = NACC + 5;  // per-CTA partial: accumulators, #correspondences, #candidate points, cache hits/fills/overflows
 constexpr int DS_MAX_CHUNKS = 4096;  // downsample: 32-bucket chunks up to 131072 buckets (a 65k-point scan), coarser beyond
-constexpr int BAR_ARRIVE = 32, BAR_TEAM = 64, BAR_WORDS = 96;  // word offsets inside Scratch::bar (one 128-byte line each)
+constexpr int BAR_ARRIVE = 32, BAR_TEAM = 64, BAR_TICKET = 96, BAR_WORDS = 128;  // word offsets inside Scratch::bar (one 128-byte line each)
 constexpr int LL_RES = 16;        // est(7) + done flag, final pose(7), spare      // est(7) t_icp(7) final(7) conv cand_total query_total ...
 
 enum Counter { C_LIVE = 0, C_TOMB = 1, C_POINTS = 2, C_STATUS = 3, C_TOUCHED = 4, C_NCOUNTERS = 8 };
@@ -146,6 +146,13 @@ __device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_re
 // ------------------------------------------------------------------------------------------
 __device__ unsigned g_kb_wd[8];          // [0] abort flag, [7] log2 of the poll limit (host-set)
 __device__ unsigned *g_kb_wd_host;       // mapped host memory: [0] flag, [1] code, [2] block, [3] thread, [4] a, [5] b
+// phase marks: thread 0 of every CTA drops a code into a device word at the phase boundaries of k_register_frame (one
+// fire-and-forget store each). When a launch never ends, the host reads the words on a side stream and reports where
+// every CTA was: the diagnostic for hangs that are not in a watched spin loop.
+__device__ unsigned g_kb_marks[256];
+__device__ __forceinline__ void kb_mark(unsigned code) {
+    if (threadIdx.x == 0) *reinterpret_cast<volatile unsigned *>(&g_kb_marks[blockIdx.x & 255]) = code;
+}
 enum WatchdogCode { WD_GRID_BARRIER = 1, WD_ICP_GATHER16 = 2, WD_ICP_RESULT = 3, WD_TEAM_GATHER = 4, WD_NN_BULK = 5 };
 
 __device__ __noinline__ bool kb_spin_giveup(unsigned spins, int code, unsigned a, unsigned b) {
@@ -210,6 +217,7 @@ struct Grid {
         if (threadIdx.x == 0 && atomicAdd(bar + BAR_ARRIVE, 1u) == gridDim.x - 1) {
             atomicExch(bar + BAR_ARRIVE, 0u);
             atomicExch(bar + BAR_TEAM, 0u);
+            atomicExch(bar + BAR_TICKET, 0u);
             atomicExch(bar, 0u);
         }
     }

@@ -292,13 +292,22 @@ __device__ __noinline__ NNResult nn_search_list(const MapView &m, const V3 &q, i
 
 // every CTA of `g`, one warp per source point: source = initial_guess * source (Registration.cpp:146-147),
 // 27-voxel search, candidate list -> qrec[point]
+// Scheduling: every warp takes point (its index) first; the points beyond one per warp are handed out through a ticket
+// counter, so that the ~14 % of warps that would have had a second point by static assignment do not set the length of
+// the pass (a point costs ~6 us) — whoever is done first takes the next one. `ticket` is zero at kernel start
+// (Grid::finish re-arms it).
 __device__ __noinline__ void icp_fill_pass(const Grid &g, Shared &sh, const MapView &m, const double *src, int n,
-                                           const SE3 &guess, QList *qrec, double radius_frac) {
+                                           const SE3 &guess, QList *qrec, double radius_frac, unsigned *ticket) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const double radius = radius_frac * m.voxel_size;
-    for (int qi = g.rank + g.size * warp; qi < n; qi += g.size * NWARPS) {
+    const int nwarps = g.size * NWARPS;
+    int qi = g.rank + g.size * warp;
+    while (qi < n) {
         const V3 p = se3_act(guess, V3{src[3 * qi], src[3 * qi + 1], src[3 * qi + 2]});
         nn_search_list(m, p, lane, sh.wnn[warp], &qrec[qi], radius);
+        unsigned t = 0;
+        if (lane == 0) t = atomicAdd(ticket, 1u);
+        qi = nwarps + static_cast<int>(__shfl_sync(FULL, t, 0));
     }
 }
 
@@ -755,6 +764,7 @@ __device__ __noinline__ void op_icp_team(const TeamScratch &ts, const Scratch &s
     for (;; ++j) {
         if (sc.profile == 1 && member == 0 && threadIdx.x == 0 && j < 20) sc.dbg[41 + j] = globaltimer_ns();
         const unsigned tag = tag_base + static_cast<unsigned>(j) + 1u;
+        kb_mark(0x410u + (static_cast<unsigned>(j) << 12));
 #ifdef KB_PROFILE_TEAM
         unsigned long long *dbg = (sc.profile == 1 && member == 0 && j == 4) ? sc.dbg : nullptr;
 #else

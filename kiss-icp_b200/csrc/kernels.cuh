@@ -140,6 +140,7 @@ __global__ void __launch_bounds__(BLOCK, 1) k_register_frame(const FrameParams P
         return;
     }
     const Front fr = P.ws.fr[P.id & 1];
+    kb_mark(0x100u + (static_cast<unsigned>(P.id) & 0xffu) * 0x10000u);
     if (front_id != P.id) {  // uniform: written only by an earlier launch
         op_front(g, P.sc, sh, P.ws, fr, P.in, P.n, P.ts, P.n_ts, P.deskew != 0, last_delta, P.max_range, P.min_range,
                  P.voxel_size, P.in_f32 != 0, P.sc.profile ? P.res->t_ns : nullptr);
@@ -165,6 +166,7 @@ __global__ void __launch_bounds__(BLOCK, 1) k_register_frame(const FrameParams P
             return;  // uniform across the grid
         }
     }
+    kb_mark(0x200u);
     // sigma, initial guess (KissICP.cpp:44,47)
     const double sigma = sqrt(model_sse / num_samples);
     const SE3 guess = se3_mul(last_pose, last_delta);
@@ -177,9 +179,11 @@ __global__ void __launch_bounds__(BLOCK, 1) k_register_frame(const FrameParams P
     }
     if (T > 0) {
         if (P.sc.profile && blockIdx.x == 0 && threadIdx.x == 0) P.sc.dbg[30] = globaltimer_ns();
-        icp_fill_pass(g, sh, P.m, fr.src, n_src, guess, P.team.qrec, P.team.radius_frac);
+        icp_fill_pass(g, sh, P.m, fr.src, n_src, guess, P.team.qrec, P.team.radius_frac, P.sc.bar + BAR_TICKET);
         if (P.sc.profile && blockIdx.x == 0 && threadIdx.x == 0) P.sc.dbg[31] = globaltimer_ns();
+        kb_mark(0x300u);
         g.sync();
+        kb_mark(0x400u + static_cast<unsigned>(T));
         if (P.sc.profile && blockIdx.x == 0 && threadIdx.x == 0) P.sc.dbg[32] = P.res->t_ns[7] = globaltimer_ns();
         if (static_cast<int>(blockIdx.x) < T) {
             op_icp_team(P.team, P.sc, sh, P.m, n_src, guess, 3.0 * sigma, sigma, P.max_iter, P.conv,
@@ -200,7 +204,9 @@ __global__ void __launch_bounds__(BLOCK, 1) k_register_frame(const FrameParams P
                 if (P.sc.profile) P.res->t_ns[11] = globaltimer_ns();  // (rank 0's own end: the other CTAs may still be emitting)
             }
         }
+        kb_mark(0x500u);
         g.sync();
+        kb_mark(0x600u);
         if (threadIdx.x == 0) team_collect(P.team, sh);
         __syncthreads();
     } else {
@@ -244,8 +250,11 @@ __global__ void __launch_bounds__(BLOCK, 1) k_register_frame(const FrameParams P
     }
     // local_map_.Update(frame_downsample, new_pose) (KissICP.cpp:61)
     op_map_add(g, sh, P.m, fr.ds1, n_ds, true, new_pose, P.ws.tp, P.ws.next, P.ws.touched, P.sc.profile ? &P.res->t_ns[8] : nullptr);
+    kb_mark(0x700u);
     op_map_remove_far(P.m, new_pose.t);
+    kb_mark(0x800u);
     g.sync();
+    kb_mark(0x900u);
     KB_STAMP(5);
     if (book) {
         P.st->model_sse = sse;
@@ -359,7 +368,7 @@ __global__ void __launch_bounds__(BLOCK, 1) k_icp(const IcpParams P) {
         T = icp_team_size(P.n, P.icp_team_q, static_cast<int>(gridDim.x), P.team.smem_bytes);
     }
     if (T > 0) {
-        icp_fill_pass(g, sh, P.m, P.src, P.n, P.guess, P.team.qrec, P.team.radius_frac);
+        icp_fill_pass(g, sh, P.m, P.src, P.n, P.guess, P.team.qrec, P.team.radius_frac, P.sc.bar + BAR_TICKET);
         g.sync();
         if (static_cast<int>(blockIdx.x) >= T) return;
         op_icp_team(P.team, P.sc, sh, P.m, P.n, P.guess, P.max_dist, P.kscale, P.max_iter, P.conv,

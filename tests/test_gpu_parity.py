@@ -572,3 +572,24 @@ def test_correct_kitti_scan_matches_oracle(K, O):
         assert np.array_equal(d_out.cpu().numpy(), K.correct_kitti_scan(p))
         N.check(N.lib().kb_pipeline_register_frame_dev(b._h, C.c_void_p(d_out.data_ptr()), len(p), None, 0))
         assert np.array_equal(a.last_pose, b.last_pose)
+
+
+def test_one_host_thread_two_devices(K, O):
+    """handles created by ONE host thread on device 0 and then on device 1 (kb_set_device): the opt-in to > 48 KB of dynamic
+    shared memory is a per-device attribute of the kernels (it used to be cached per thread)"""
+    from kiss_icp_b200 import _native as N, synthetic
+    if N.lib().kb_device_count() < 2:
+        pytest.skip("needs two GPUs")
+    L = synthetic.small_shape(seed=2, beams=32, cols=512)
+    try:
+        for dev in (0, 1, 0):
+            N.check(N.lib().kb_set_device(dev))
+            g, o = K.KissICP(K.load_config()), O.KissICP()
+            for k in range(4):
+                p, t = L.scan(k)
+                g.register_frame(p, t, return_clouds=False)
+                o.register_frame(p, t, want_clouds=False)
+                dt, dr = pose_error(g.last_pose, o.pose)
+                assert dt < 1e-9 and dr < 1e-9, (dev, k)
+    finally:
+        N.check(N.lib().kb_set_device(0))
