@@ -51,6 +51,10 @@ typedef struct kb_frame_stats {
     int map_points, map_voxels;
     int team;             /* CTAs of the ICP team that ran the iterations (0: whole-grid loop) */
 } kb_frame_stats;
+/* 1 if a launch on some device of this process never ended (the call that waited for it returned KB_ERR_CUDA after
+ * KB_SYNC_TIMEOUT_S seconds, default 30). Handles of that device then leak their device memory on destruction instead of
+ * blocking in cudaFree; the process should exit without CUDA's teardown (the Python package does, through os._exit). */
+int kb_any_device_stuck(void);
 int kb_pipeline_set_history(kb_pipeline *p, size_t capacity);
 int kb_pipeline_get_history(const kb_pipeline *p, kb_frame_stats *out, size_t capacity, size_t *n_out);
 /* the logged frames' in-kernel %globaltimer stamps (profiling on), ns modulo 2^40, 20 per frame: [0] kernel start, [1..3] front

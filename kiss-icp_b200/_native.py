@@ -7,6 +7,7 @@ entry point returns KB_ERR_NO_DEVICE, surfaced here as ``NoDeviceError``.
 """
 from __future__ import annotations
 
+import atexit
 import ctypes as C
 import os
 import shutil
@@ -153,6 +154,7 @@ SIGNATURES = {
     "kb_pipeline_last_iterations": (i32, [vp, C.POINTER(i32)]),
     "kb_pipeline_last_profile": (i32, [vp, vp, i32]),
     "kb_pipeline_set_profiling": (i32, [vp, i32]),
+    "kb_any_device_stuck": (i32, []),
     "kb_pipeline_set_history": (i32, [vp, sz]),
     "kb_pipeline_get_history": (i32, [vp, vp, sz, C.POINTER(sz)]),
     "kb_pipeline_launch_count": (i32, [vp, C.POINTER(C.c_ulonglong)]),
@@ -173,7 +175,18 @@ def lib():
             fn.restype = res
             fn.argtypes = args
         _lib = L
+        atexit.register(_exit_without_teardown_if_stuck)
     return _lib
+
+
+def _exit_without_teardown_if_stuck():
+    """A launch that never ended (reported as an error by the call that waited for it) would block the CUDA context's
+    teardown at interpreter exit forever: leave without it."""
+    if _lib is not None and _lib.kb_any_device_stuck():
+        import sys
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(1)
 
 
 def check(status: int):

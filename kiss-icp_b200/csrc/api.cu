@@ -1779,6 +1779,7 @@ int kb_pipeline_last_profile(const kb_pipeline *p, double *us, int n) {
     for (int i = 0; i < n && i < 6; ++i) us[i] = (static_cast<double>(p->last.t_ns[i + 1]) - static_cast<double>(p->last.t_ns[i])) * 1e-3;
     return KB_OK;
 }
+int kb_any_device_stuck(void) { return device_is_stuck(-1) ? 1 : 0; }
 int kb_pipeline_set_profiling(kb_pipeline *p, int enabled) {
     if (!p) return fail(KB_ERR_INVALID_ARG, "p == NULL");
     p->ex->sc.profile = enabled;  // 1: all stamps (incl. one per ICP iteration, ~1 us each); 2: phase boundaries only

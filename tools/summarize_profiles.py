@@ -51,8 +51,9 @@ def launches(path, tag):
 
 if __name__ == "__main__":
     g = os.path.join(ROOT, "gpurun_out")
-    for rep, tag in (("prof_r1_frame.ncu-rep", "r1_register_frame"), ("prof_r1_nn.ncu-rep", "r1_nn_query")):
+    rnd = sys.argv[1] if len(sys.argv) > 1 else "r2"
+    for rep, tag in ((f"prof_{rnd}_frame.ncu-rep", f"{rnd}_register_frame"), (f"prof_{rnd}_nn.ncu-rep", f"{rnd}_nn_query")):
         if os.path.exists(os.path.join(g, rep)):
             raw(os.path.join(g, rep), tag)
-    if os.path.exists(os.path.join(g, "launches_r1.csv")):
-        launches(os.path.join(g, "launches_r1.csv"), "r1_bench")
+    if os.path.exists(os.path.join(g, f"launches_{rnd}.csv")):
+        launches(os.path.join(g, f"launches_{rnd}.csv"), f"{rnd}_bench")
