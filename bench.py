@@ -613,25 +613,43 @@ def nn_leg(K, N, L, torch, dev, peak):
     N.check(L.kb_map_query_bytes_dev(m._h, C.c_void_p(q.data_ptr()), n_q, C.byref(b)))
     stream = torch.cuda.current_stream()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > L2 (126 MB)
-    times = []
-    for it in range(13):
-        flush.fill_(it & 0xff)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        N.check(L.kb_map_closest_neighbors_dev(m._h, C.c_void_p(q.data_ptr()), n_q, C.c_void_p(outp.data_ptr()),
-                                               C.c_void_p(outd.data_ptr())))
-        e1.record(stream)
-        torch.cuda.synchronize()
-        if it >= 3:
-            times.append(e0.elapsed_time(e1))
-    ms = float(np.mean(times))
+    def timed(variant):
+        """mean ms of 10 launches (after 3 untimed), L2 flushed before each; the library reads KB_NN_KERNEL per call"""
+        old = os.environ.get("KB_NN_KERNEL")
+        os.environ["KB_NN_KERNEL"] = variant
+        times = []
+        try:
+            for it in range(13):
+                flush.fill_(it & 0xff)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                N.check(L.kb_map_closest_neighbors_dev(m._h, C.c_void_p(q.data_ptr()), n_q, C.c_void_p(outp.data_ptr()),
+                                                       C.c_void_p(outd.data_ptr())))
+                e1.record(stream)
+                torch.cuda.synchronize()
+                if it >= 3:
+                    times.append(e0.elapsed_time(e1))
+        finally:
+            if old is None:
+                os.environ.pop("KB_NN_KERNEL", None)
+            else:
+                os.environ["KB_NN_KERNEL"] = old
+        return float(np.mean(times)), len(times)
+
+    variant = "bulk" if os.environ.get("KB_NN_KERNEL") == "bulk" else "regs"
+    ms, reps = timed(variant)
+    other = "regs" if variant == "bulk" else "bulk"
+    ms_other, _ = timed(other)
     ach = b.value / (ms * 1e-3) / 1e9
-    traffic, traffic_src = profiled_traffic("r2_nn_query")
-    kname = "k_nn_query (register-staged)" if os.environ.get("KB_NN_KERNEL") == "regs" else "k_nn_query_bulk (cp.async.bulk + mbarrier staging)"
-    return {"kernel": kname, "map_points": int(stored.shape[0]), "map_voxels": m.num_voxels(), "queries": n_q, "points_per_voxel": float(stored.shape[0]) / max(m.num_voxels(), 1),
+    names = {"regs": "k_nn_query (one warp per query, candidates staged in registers, next query's probes in flight)",
+             "bulk": "k_nn_query_bulk (candidate blocks staged in shared memory by cp.async.bulk + mbarrier)"}
+    # the ncu --set full captures: round 1 = k_nn_query, round 2 = k_nn_query_bulk
+    traffic, traffic_src = profiled_traffic("r1_nn_query" if variant == "regs" else "r2_nn_query")
+    return {"kernel": names[variant], "map_points": int(stored.shape[0]), "map_voxels": m.num_voxels(), "queries": n_q, "points_per_voxel": float(stored.shape[0]) / max(m.num_voxels(), 1),
             "algorithmic_bytes": b.value, "bytes_per_query": b.value / n_q, "ms": ms, "achieved": ach, "peak": peak,
             "unit": "GB/s", "frac": ach / peak, "traffic": traffic, "traffic_source": traffic_src,
-            "l2": "flushed (256 MiB write) before every timed launch", "reps": len(times)}
+            "l2": "flushed (256 MiB write) before every timed launch", "reps": reps,
+            "other_variant": {"kernel": names[other], "ms": ms_other, "frac": b.value / (ms_other * 1e-3) / 1e9 / peak}}
 
 
 def trajectory_quality(lidar, traj, cpu_poses):

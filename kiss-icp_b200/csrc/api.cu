@@ -875,12 +875,11 @@ static int nn_launch(kb_map *map, const double *d_q, size_t n, double *d_p, doub
     if (n == 0) return KB_OK;
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, map->ex->device);
-    // default: candidate blocks staged by bulk async copies (needs 16-byte aligned blocks: an even max_points_per_voxel
-    // <= 32); KB_NN_KERNEL=regs selects the register-staged kernel (A/B, odd capacities)
-    static const bool want_bulk = [] {
-        const char *e = std::getenv("KB_NN_KERNEL");
-        return !(e && std::strcmp(e, "regs") == 0);
-    }();
+    // default: the register-staged kernel (never slower in same-box A/Bs: 1.580 vs 1.585 ms, 1.588 vs 1.695 ms);
+    // KB_NN_KERNEL=bulk selects the variant that stages the candidate blocks with cp.async.bulk + mbarrier
+    // (needs 16-byte aligned blocks: an even max_points_per_voxel <= 32; read per call)
+    const char *env = std::getenv("KB_NN_KERNEL");
+    const bool want_bulk = env && std::strcmp(env, "bulk") == 0;
     const bool bulk = want_bulk && map->cap <= static_cast<unsigned>(NN_FLAT_CAP) && (map->cap & 1u) == 0;
     const int threads = 256;
     const size_t want = (n * 32 + threads - 1) / threads;
@@ -1246,10 +1245,20 @@ int kb_pipeline_create(const kb_config *cfg, kb_pipeline **out) {
         const double est = std::min(3.0 * 10.0 * 3.14159265358979 * r * r, double(size_t(1) << 20));
         size_t slots = std::max<size_t>(static_cast<size_t>(est), size_t(1) << 14);
         if (const char *e = std::getenv("KB_MAP_RESERVE_SLOTS")) slots = static_cast<size_t>(std::atoll(e));  // 0: none
-        if (slots) RET(p->map->reserve(std::min<size_t>(slots, size_t(1) << 31)));
+        if (slots) {
+            // out of device memory (many pipelines on one GPU): reserve less; the minimal table of map_create_impl grows on demand
+            size_t want = std::min<size_t>(slots, size_t(1) << 31);
+            int st;
+            while ((st = p->map->reserve(want)) != KB_OK && want > (size_t(1) << 14)) {
+                cudaGetLastError();
+                want >>= 2;
+            }
+            if (st != KB_OK) cudaGetLastError();
+        }
     }
     CK(cudaMalloc(&p->d_state, sizeof(PipeState)));
     CK(cudaMalloc(&p->d_res, sizeof(FrameResult)));
+    CK(cudaMemsetAsync(p->d_res, 0, sizeof(FrameResult), p->ex->stream));  // (fields a launch does not write are read back too)
     CK(cudaHostAlloc(&p->h_res, sizeof(FrameResult), cudaHostAllocDefault));
     std::memset(&p->last, 0, sizeof(p->last));
     se3_to_matrix(se3_identity(), p->last.pose);
@@ -1435,6 +1444,7 @@ static int queue_init(kb_pipeline *p, size_t max_n, bool any_ts, bool device_inp
         CK(cudaStreamCreateWithFlags(&p->res_stream, cudaStreamNonBlocking));
         CK(cudaHostAlloc(&p->q_res, sizeof(FrameResult) * kb_pipeline::Q_DEPTH, cudaHostAllocDefault));
         CK(cudaMalloc(&p->q_res_dev, sizeof(FrameResult) * kb_pipeline::Q_DEPTH));
+        CK(cudaMemsetAsync(p->q_res_dev, 0, sizeof(FrameResult) * kb_pipeline::Q_DEPTH, p->ex->stream));
     }
     if (!device_input)
         for (auto &s : p->q) {
@@ -1518,6 +1528,7 @@ int kb_pipeline_register_frames(kb_pipeline *p, const void *const *xyz, const si
         CK(cudaEventRecord(s.copied, p->copy_stream));
         return KB_OK;
     };
+    auto run = [&]() -> int {
     while (next_absorb < valid) {
         const size_t inflight = next_submit - next_absorb;
         bool submit = next_submit < valid && inflight + 1 < D;
@@ -1581,6 +1592,32 @@ int kb_pipeline_register_frames(kb_pipeline *p, const void *const *xyz, const si
         }
         if (poses_out) std::memcpy(poses_out + 16 * k, r.pose, sizeof(double) * 16);
         ++next_absorb;
+    }
+    return KB_OK;
+    };
+    const int st = run();
+    if (st != KB_OK) {
+        // an error in the middle of the queue: launches may still be in flight and finished frames not absorbed. Let them
+        // finish and absorb what completed, so that the host mirrors (pose, counters, last clouds) match the device.
+        const std::string msg = tl_err;
+        if (!device_is_stuck(ex.device) && cudaStreamSynchronize(p->copy_stream) == cudaSuccess && ex.sync() == KB_OK &&
+            cudaStreamSynchronize(p->res_stream) == cudaSuccess) {
+            for (; next_absorb < next_submit; ++next_absorb) {
+                const size_t k = next_absorb;
+                const FrameResult r = p->q_res[k % D];
+                if (r.map_status & ST_NEED_GROW) {
+                    pipeline_after_veto(p, r, n[k]);  // clears the sticky veto; the frames behind it were skipped
+                    break;
+                }
+                if (r.map_status & ST_SKIPPED) break;
+                p->next_id = id0 + static_cast<long long>(k) + 1;
+                if (pipeline_absorb(p, r, n[k], id0 + static_cast<long long>(k)) != KB_OK) break;
+                if (poses_out) std::memcpy(poses_out + 16 * k, r.pose, sizeof(double) * 16);
+            }
+        }
+        cudaGetLastError();
+        tl_err = msg;
+        return st;
     }
     if (bad_status != KB_OK) {
         tl_err = bad_msg;

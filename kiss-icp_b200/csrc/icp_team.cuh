@@ -442,6 +442,8 @@ __device__ __noinline__ void team_refill(Shared &sh, const MapView &m, const Tea
     __syncthreads();
 }
 
+// (Tried: keeping the four warps of the solver's scheduler free of source points so that the solver finds its code in that
+// scheduler's instruction cache - no effect, 4683 vs 4705 scans/s.)
 // cycle stamps inside the iteration: only in a profiling build (-DKB_PROFILE_TEAM). The iteration's code must stay small:
 // it is executed once per iteration by warps that are at different places, i.e. the instruction cache sees a cyclic
 // sweep over the whole loop body, and a body larger than the cache misses on every line (measured: 36 KB of loop body
