@@ -444,6 +444,8 @@ __device__ __noinline__ void team_refill(Shared &sh, const MapView &m, const Tea
 
 // (Tried: keeping the four warps of the solver's scheduler free of source points so that the solver finds its code in that
 // scheduler's instruction cache - no effect, 4683 vs 4705 scans/s.)
+// (Tried: running the solver's code once early per iteration on an idle thread of the same scheduler, outputs discarded, to
+// warm the instruction cache for the real run - slower, 4402 vs 4510 scans/s: the solve is not fetch-bound.)
 // cycle stamps inside the iteration: only in a profiling build (-DKB_PROFILE_TEAM). The iteration's code must stay small:
 // it is executed once per iteration by warps that are at different places, i.e. the instruction cache sees a cyclic
 // sweep over the whole loop body, and a body larger than the cache misses on every line (measured: 36 KB of loop body
