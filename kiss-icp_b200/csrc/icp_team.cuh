@@ -7,7 +7,7 @@
 //     runs the 27-voxel search of GetClosestNeighbor (core/VoxelHashMap.cpp:46-70) and leaves, per point, the
 //     short list of map points that can still become its nearest neighbour while it moves by <= R
 //     (exactness argument: QCache in device_ops.cuh);
-//   * the iterations then run on a small team (T = ceil(n / 64) CTAs, 43 for a KITTI scan): four lanes per source
+//   * the iterations then run on a small team (T = ceil(n / 80) CTAs, 31 for a KITTI scan): four lanes per source
 //     point walk its list — candidate COORDINATES staged in shared memory, interleaved so that the walk is
 //     bank-conflict free — and the T partial systems meet in ONE all-gather of epoch-tagged
 //     16-byte chunks: every team CTA polls all T partials, adds them in the same fixed order and solves the
@@ -26,7 +26,7 @@ constexpr int TEAM_MAX = 96;    // CTAs of an ICP team (the gathered partials, 2
 static_assert(NPART * TEAM_MAX * 8 <= DS_MAX_CHUNKS * 4, "the gathered partials live in Shared::chunk_pref");
 constexpr int TQ_LANES = 4;     // lanes that share one source point in the list walk
 constexpr int TQ_PER_WARP = 32 / TQ_LANES;
-constexpr int TQ_PER_CTA = 64;  // source points per team CTA by default (8 warps)
+constexpr int TQ_PER_CTA = 80;  // source points per team CTA by default (10 warps; A/B at KITTI shape: 48 -3 %, 64 0, 80 +1.5 %, 96 +1.3 %)
 constexpr int TQ_MAX = 120;     // upper bound of source points per team CTA (warps 0..14; the solver is thread 511)
 constexpr int TRED_STRIDE = NACC + 1;  // row of the per-point reduction scratch: 16 entries + the gate flag (odd: conflict-free)
 static_assert(TQ_MAX * TRED_STRIDE * 8 <= DS_MAX_CHUNKS * 4, "the reduction scratch lives in Shared::chunk_pref");
