@@ -32,7 +32,7 @@ thread_local cudaStream_t tl_user_stream = nullptr;
 thread_local int tl_grid_blocks = 0;
 
 int fail(int status, const char *fmt, ...) {
-    char buf[512];
+    char buf[4096];  // (room for the per-CTA phase marks of the hang reports)
     va_list ap;
     va_start(ap, fmt);
     vsnprintf(buf, sizeof(buf), fmt, ap);
@@ -255,7 +255,9 @@ int watchdog_init(int device) {
     std::memset(h, 0, 8 * sizeof(unsigned));
     CK(cudaHostGetDevicePointer(&d, h, 0));
     CK(cudaMemcpyToSymbol(g_kb_wd_host, &d, sizeof(d)));
-    unsigned init[8] = {0, 0, 0, 0, 0, 0, 0, 22};  // give up after 2^22 polls (seconds)
+    // give up after 2^24 polls (of the order of 10 s, below the host's 30 s deadline). 2^22 (a second or two) fired once in
+    // ~40 full-file test runs at the FIRST grid barrier of a launch; whether that was a stall or a deadlock is not known.
+    unsigned init[8] = {0, 0, 0, 0, 0, 0, 0, 24};
     if (const char *e = std::getenv("KB_WATCHDOG_SHIFT")) init[7] = static_cast<unsigned>(std::max(10, std::min(std::atoi(e), 31)));
     CK(cudaMemcpyToSymbol(g_kb_wd, init, sizeof(init)));
     g_wd[device].host = h;
@@ -270,8 +272,21 @@ int watchdog_check(int device) {
     unsigned zero = 0;
     cudaMemcpyToSymbol(g_kb_wd, &zero, sizeof(zero));  // re-arm
     static const char *names[] = {"?", "grid barrier", "ICP gather", "ICP result record", "ICP team gather", "NN bulk copy"};
-    return fail(KB_ERR_CUDA, "device watchdog: a kernel gave up waiting at the %s (block %u, thread %u, a=%u, b=%u); the results of that launch are invalid",
-                names[code < 6 ? code : 0], block, thread, a, b);
+    // where every CTA of the last k_register_frame was (the launch has ended: a plain copy)
+    std::string marks;
+    unsigned m[256];
+    if (cudaMemcpyFromSymbol(m, g_kb_marks, sizeof(m)) == cudaSuccess) {
+        marks = "; phase marks per CTA:";
+        char buf[16];
+        for (int i = 0; i < 160; ++i) {
+            std::snprintf(buf, sizeof(buf), " %x", m[i]);
+            marks += buf;
+        }
+    }
+    cudaGetLastError();
+    return fail(KB_ERR_CUDA, "device watchdog: a kernel gave up waiting at the %s (block %u, thread %u, a=%u, b=%u; grid barrier: a = target, b = counter); "
+                             "the results of that launch are invalid%s",
+                names[code < 6 ? code : 0], block, thread, a, b, marks.c_str());
 }
 
 bool g_stuck[64];

@@ -140,7 +140,7 @@ __device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_re
 // ------------------------------------------------------------------------------------------
 // watchdog of the spin loops: the kernels below wait for each other with hand-rolled barriers and tagged polls. A
 // protocol bug (or a CTA that died) would otherwise spin forever and take the GPU with it. Every spin loop counts
-// its polls; after 2^g_kb_wd[7] of them (seconds) the loop gives up, raises g_kb_wd[0] — which every other spin
+// its polls; after 2^g_kb_wd[7] of them (2^24: of the order of 10 s) the loop gives up, raises g_kb_wd[0] — which every other spin
 // loop checks every 1024 polls and then leaves too — and reports where it was stuck to a word of mapped host
 // memory. The launch then finishes with garbage and the host turns the flag into KB_ERR_CUDA.
 // ------------------------------------------------------------------------------------------
@@ -204,7 +204,8 @@ struct Grid {
             asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(old) : "l"(bar) : "memory");
             unsigned spins = 0;
             while (ld_relaxed_u32(bar) < target) {
-                if (kb_spin_check(spins, WD_GRID_BARRIER, target, static_cast<unsigned>(size))) break;
+                // (report: the target and what the counter holds - how many CTAs are missing)
+                if (kb_spin_check(spins, WD_GRID_BARRIER, target, ld_relaxed_u32(bar))) break;
             }
             __threadfence();  // acquire side; a gpu-scope fence also drops this SM's L1 lines (plain loads follow)
         }

@@ -7,11 +7,15 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import kiss_icp_b200 as K
 from kiss_icp_b200 import synthetic
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 10
+only_first = len(sys.argv) > 2 and sys.argv[2] == "long"  # the 300-scan stream of test_pipeline_long_stream_with_table_rebuilds alone
 L = synthetic.small_shape(seed=21, beams=32, cols=512)
 g = K.KissICP(K.load_config(max_range=40.0))
 for k in range(n):
     p, t = L.scan(k)
     g.register_frame(p, t, return_clouds=False)
+if only_first:
+    print("done", g.last_iterations, g.local_map.num_points(), "grow retries", g.grow_retries())
+    sys.exit(0)
 L2 = synthetic.small_shape(seed=22, beams=32, cols=512)
 h = K.KissICP(K.load_config(max_range=40.0))
 h.register_frames([L2.scan(k)[0] for k in range(n)], None)
