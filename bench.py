@@ -437,7 +437,7 @@ def main():
     # each copying its clouds in and out (KissICP(fused=False) = preprocess, voxelize x2, threshold, align, update on the
     # per-module C-ABI); host wall clock on rank 0, one window
     modular = None
-    if rank == 0 and not args.no_extra:
+    if rank == 0 and world == 1 and not args.no_extra:
         try:
             icp_m = K.KissICP(cfg, fused=False)
             host_scans = [(s[0].cpu().numpy(), s[1].cpu().numpy()) for s in scans_dev[:head + Kw]]
@@ -499,9 +499,11 @@ def main():
                         "candidate lists); kernel time = CUDA-event time of the median window / launches; see nn_kernel "
                         "for the bandwidth-bound NN query" % (iters.mean(), work[:, 0].mean() / max(iters.mean(), 1))}
 
-    ms_leg = multi_stream_leg(args, K, N, L, torch, dev, args.streams, cfg) if (args.streams > 1 and not args.no_extra) else None
-    nn = None if args.no_nn else nn_leg(K, N, L, torch, dev, peak)
-    cpu = None if args.no_cpu else cpu_leg(args, lidar)
+    # side legs on rank 0 at N = 1 only (a multi-GPU run measures scaling; the CPU legs would also compete for the host cores)
+    solo = world == 1
+    ms_leg = multi_stream_leg(args, K, N, L, torch, dev, args.streams, cfg) if (solo and args.streams > 1 and not args.no_extra) else None
+    nn = nn_leg(K, N, L, torch, dev, peak) if (solo and not args.no_nn) else None
+    cpu = cpu_leg(args, lidar) if (solo and not args.no_cpu) else None
     quality = trajectory_quality(lidar, traj, cpu.pop("poses", None) if cpu else None)
     wall_dev_a, wall_e2e_a = np.array(wall_dev), np.array(wall_e2e)
 
