@@ -203,9 +203,10 @@ struct Grid {
             unsigned old;  // release our writes / acquire everybody else's
             asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(old) : "l"(bar) : "memory");
             unsigned spins = 0;
-            while (ld_relaxed_u32(bar) < target) {
-                // (report: the target and what the counter holds - how many CTAs are missing)
-                if (kb_spin_check(spins, WD_GRID_BARRIER, target, ld_relaxed_u32(bar))) break;
+            unsigned seen;
+            while ((seen = ld_relaxed_u32(bar)) < target) {
+                // (report: the target and what the counter held - how many CTAs are missing)
+                if (kb_spin_check(spins, WD_GRID_BARRIER, target, seen)) break;
             }
             __threadfence();  // acquire side; a gpu-scope fence also drops this SM's L1 lines (plain loads follow)
         }
