@@ -12,7 +12,7 @@
 //     bank-conflict free — and the T partial systems meet in ONE all-gather of epoch-tagged
 //     16-byte chunks: every team CTA polls all T partials, adds them in the same fixed order and solves the
 //     6x6 itself, so there is no coordinator, no broadcast hop and one L2 round trip per iteration;
-//   * the rest of the launch (the other ~126 SMs) is free meanwhile: k_register_frame runs the NEXT scan's
+//   * the rest of the launch (the other ~117 SMs) is free meanwhile: k_register_frame runs the NEXT scan's
 //     preprocessing and voxel downsampling on it.
 // A point whose list is no longer valid (moved > R, or left its voxel) is searched again by its whole warp
 // inside the iteration (nn_search_list), exactly like the first time.
@@ -658,7 +658,7 @@ __device__ __forceinline__ void team_queries(uint4 *ll, Shared &sh, const MapVie
 
 // all-gather of the T tagged partial systems. Every member WRITES its partial once per reader (ll[parity][reader][member]
 // [value]: 21 x T stores of 16 bytes, coalesced 336-byte rows) so that every reader polls lines nobody else reads:
-// with one shared copy the 42 x 352 polling lanes of all CTAs hammered the same few L2 lines and the hop took 5 us
+// with one shared copy the 42 x 352 polling lanes of all CTAs (64 points per CTA then) hammered the same few L2 lines and the hop took 5 us
 // (measured; the members themselves arrived within 0.5 us of each other).
 // Reader: thread t polls chunks t, t + 512, ... of its T x 21 (a two-line loop: the iteration's code has to stay small)
 // and drops the values into shared memory; after one barrier 21 lanes of warp 15 add the members in order (the same
